@@ -1,0 +1,157 @@
+// hkf_internal.cuh — context, error plumbing and the device-side arithmetic contract.
+//
+// The reference's float arithmetic is whatever nvcc 12.9 made of its sources with default
+// flags (-fmad=true, IEEE div/sqrt).  Which a*b+c pairs were fused into FMAs decides which
+// pixel a voxel projects to and which side of zero a near-zero SDF falls on, so every
+// expression that feeds an index, a threshold or a parity-checked value is written here with
+// explicit round-to-nearest intrinsics in the association order read off the reference's
+// PTX/SASS (compiled for sm_100 by oracle/Makefile).  Nothing in this file is left to the
+// compiler's contraction heuristics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/hkf.h"
+
+#define HKF_MAX_LEVELS 3
+#define HKF_SUMS 27
+
+struct DMat44 { float m[16]; };
+
+// device-resident per-frame state shared by the fused kernels
+struct HkfDeviceState {
+    float pose[16];          // current camera pose (camera -> world)
+    float pose_inv[16];      // its inverse (float cofactors, Mat44::getInverse arithmetic)
+    float last_inv[16];      // snapshot of pose_inv at tracking start = inverse of the pose the model maps were raycast from
+    float cur[16];           // ICP/SDF working transform
+    int   track_status;      // HKF_TRACK_*
+    int   frame_valid;       // 0 until the first frame has been integrated
+    unsigned dmax_bits;      // max valid truncated depth of the current frame (float bits)
+    unsigned ticket;         // last-block-done counter for the solver kernels
+    unsigned mc_count;       // marching-cubes triangle counter
+    unsigned pad;
+    unsigned long long upd_count;
+    float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
+    int   sdf_done;          // SDF tracker: converged flag (|x| < 1e-3)
+};
+
+struct hkf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    HkfInitParams ip{};
+    std::string err;
+    uint64_t launches = 0;
+
+    int levels = 1;
+    unsigned cols[HKF_MAX_LEVELS]{}, rows[HKF_MAX_LEVELS]{};
+    // image buffers
+    uint16_t* depth_mm = nullptr;     // device copy of the raw 16-bit frame
+    uint16_t* depth_mm_pinned = nullptr; // pinned staging for pageable callers
+    float* raw_depth = nullptr;
+    float* trunc_depth = nullptr;
+    float* filtered_depth = nullptr;
+    float4* new_v[HKF_MAX_LEVELS]{};
+    float4* new_n[HKF_MAX_LEVELS]{};
+    float4* model_v[HKF_MAX_LEVELS]{};
+    float4* model_n[HKF_MAX_LEVELS]{};
+    unsigned long long* ray_keys = nullptr;
+    // solver scratch: [27][nblocks] partials for the largest level
+    float* partials = nullptr;
+    unsigned max_blocks = 0;
+    // volume slab
+    float2* vol = nullptr;
+    unsigned z_lo = 0, z_hi = 0;       // stored planes
+    unsigned own_z0 = 0, own_z1 = 0;   // owned planes
+    // marching cubes
+    HkfTriangle* tris = nullptr;
+    // device state
+    HkfDeviceState* st = nullptr;
+    HkfDeviceState* st_host = nullptr; // pinned mirror for result read-back
+    // sharding
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    float* ray_payload = nullptr;
+};
+
+#define HKF_CUDA(ctx, call)                                                        \
+    do {                                                                           \
+        cudaError_t _e = (call);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);       \
+            return HKF_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+#define HKF_LAUNCH_CHECK(ctx)                                                      \
+    do {                                                                           \
+        (ctx)->launches++;                                                         \
+        cudaError_t _e = cudaGetLastError();                                       \
+        if (_e != cudaSuccess) {                                                   \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(_e);  \
+            return HKF_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device arithmetic contract
+#ifdef __CUDACC__
+
+// (int)(p + 0.5) as the reference compiles it: the literal 0.5 is a double, so the add is in
+// fp64 and the cast truncates toward zero (src/cuda/DepthCamera.h:39-43;
+// PTX: cvt.f64.f32 ; add.f64 0.5 ; cvt.rzi.s32.f64)
+__device__ __forceinline__ int hkf_round_px(float p)
+{
+    return __double2int_rz(__dadd_rn((double)p, 0.5));
+}
+
+// projectSkeletonToScreenfloat: (v*f)/z + c   (mul, div.rn, add)
+__device__ __forceinline__ float hkf_project1(float v, float f, float z, float c)
+{
+    return __fadd_rn(__fdiv_rn(__fmul_rn(v, f), z), c);
+}
+
+// dot(a,a) / dot(a,b) as nvcc contracts x*x' + y*y' + z*z':  fma(z,z', fma(x,x', y*y'))
+__device__ __forceinline__ float hkf_dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fmaf_rn(az, bz, __fmaf_rn(ax, bx, __fmul_rn(ay, by)));
+}
+
+// a*b - c*d as ptxas fuses it everywhere in the reference: fma(a, b, -(c*d))
+__device__ __forceinline__ float hkf_det2(float a, float b, float c, float d)
+{
+    return __fmaf_rn(a, b, -__fmul_rn(c, d));
+}
+
+// normalize(float3) (src/cuda/cuda_declar.h:89-94): len = sqrt.rn(dot); if ((double)len < 1e-8) -> 0;
+// v * (float)(1.0/len) which nvcc lowers to an IEEE float reciprocal (rcp.rn)
+__device__ __forceinline__ float3 hkf_normalize(float x, float y, float z)
+{
+    float len = __fsqrt_rn(hkf_dot3(x, y, z, x, y, z));
+    if ((double)len < 1e-8) return make_float3(0.f, 0.f, 0.f);
+    float r = __frcp_rn(len);
+    return make_float3(__fmul_rn(x, r), __fmul_rn(y, r), __fmul_rn(z, r));
+}
+
+__device__ __forceinline__ bool hkf_is_zero4(const float4& v)
+{
+    return v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f;
+}
+
+// Mat44 * (x,y,z,w): per row ((m1*x + m2*y) + m3*z) + m4*w.  The reference's PTX shows two
+// different contractions of the leading pair depending on the call site:
+//   LEAD_FIRST : mul(m1*x) then fma(y,m2,.), fma(z,m3,.), fma(w,m4,.)
+//   LEAD_SECOND: mul(m2*y) then fma(x,m1,.), fma(z,m3,.), fma(w,m4,.)
+template <bool LEAD_FIRST>
+__device__ __forceinline__ float hkf_row4(float m1, float m2, float m3, float m4, float x, float y, float z, float w)
+{
+    float t = LEAD_FIRST ? __fmaf_rn(y, m2, __fmul_rn(x, m1)) : __fmaf_rn(x, m1, __fmul_rn(y, m2));
+    return __fmaf_rn(w, m4, __fmaf_rn(z, m3, t));
+}
+
+__device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
+
+#endif // __CUDACC__

@@ -1,0 +1,393 @@
+// preprocess.cu — depth decode, truncation, bilateral filter, vertex/normal maps, pyramids.
+//
+// Replaces reference kernels K1–K6:
+//   trucDepthKernel / biateralFilterKernel      src/cuda/DataPreprocesser.cu:17-79
+//   depthToVerticesKernel / verticesToNormals   src/cuda/VerticesNormalsCalculater.cu:15-66
+//   pryDownVerticesKernel / pryDownNormals      src/cuda/sample.cu:16-60
+// and the host mm->m loop of HybKinectfu::copyFrameToGPU (src/HybKinectfu.cpp:69-75).
+//
+// Design: the reference runs six launches with a device-wide sync after each and 81 uncached
+// global loads per pixel in the bilateral filter.  Here the whole per-frame chain is two
+// launches: (A) one tile kernel that decodes the 16-bit frame, truncates, stages the truncated
+// tile (+apron) in shared memory, filters, back-projects and differentiates; (B) one kernel that
+// builds every coarser pyramid level of both maps.  HBM traffic is the algorithmic minimum:
+// 2 B/px in, 3 x 4 B + 2 x 16 B out at level 0.  The per-wrapper entry points reuse the same
+// device functions on global memory so that each stage can be parity-checked in isolation.
+#include "hkf_internal.cuh"
+
+// ---------------------------------------------------------------- shared device functions
+
+// (float)(ushort * 0.001): the multiply is in double (src/HybKinectfu.cpp:73)
+__device__ __forceinline__ float decode_mm(uint16_t mm)
+{
+    return (float)__dmul_rn((double)mm, 0.001);
+}
+
+// trucDepthKernel: keep min < d < max (strict), else 0
+__device__ __forceinline__ float trunc_depth(float d, float tmin, float tmax)
+{
+    return (d < tmax && d > tmin) ? d : 0.f;
+}
+
+// biateralFilterKernel body.  `at(cx,cy)` reads the truncated depth at image coordinates.
+// Arithmetic as compiled (SASS of the reference):
+//   arg  = fma(space2, ss, data2*sd);   w = __expf(-arg);   sum1 = fma(tmp,w,sum1);   sum2 += w
+// Window rows outer, columns inner, clamped to the image.  Any valid neighbour further than
+// 5*sigma_d from the centre aborts to pass-through (DataPreprocesser.cu:66-69).
+template <typename At>
+__device__ __forceinline__ float bilateral_px(At at, int x, int y, int cols, int rows, int radius,
+                                              float ss, float sd, float thresh)
+{
+    float value = at(x, y);
+    if (value == 0.f) return value;
+    int x0 = max(x - radius, 0), x1 = min(x + radius, cols - 1);
+    int y0 = max(y - radius, 0), y1 = min(y + radius, rows - 1);
+    float sum1 = 0.f, sum2 = 0.f;
+    for (int cy = y0; cy <= y1; ++cy) {
+        for (int cx = x0; cx <= x1; ++cx) {
+            float tmp = at(cx, cy);
+            if (tmp == 0.f) continue;
+            if (fabsf(__fsub_rn(tmp, value)) > thresh) return value;
+            float space2 = (float)((x - cx) * (x - cx) + (y - cy) * (y - cy));
+            float d = __fsub_rn(value, tmp);
+            float data2 = __fmul_rn(d, d);
+            float arg = __fmaf_rn(space2, ss, __fmul_rn(data2, sd));
+            float w = __expf(-arg);
+            sum1 = __fmaf_rn(tmp, w, sum1);
+            sum2 = __fadd_rn(sum2, w);
+        }
+    }
+    if (sum2 > 0.f) return __fdiv_rn(sum1, sum2);
+    return value;
+}
+
+// DepthCamera::depthToSkeleton (src/cuda/DepthCamera.h:19-29): (z*(u-cx))/fx
+__device__ __forceinline__ float4 back_project(unsigned ux, unsigned uy, float depth, float cx, float cy, float fx, float fy)
+{
+    if (depth == 0.f) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float vx = __fdiv_rn(__fmul_rn(depth, __fsub_rn((float)ux, cx)), fx);
+    float vy = __fdiv_rn(__fmul_rn(depth, __fsub_rn((float)uy, cy)), fy);
+    return make_float4(vx, vy, depth, 1.0f);
+}
+
+// verticesToNormalsKernel body: normalize(cross(up - down, right - left)); any invalid -> 0
+__device__ __forceinline__ float4 normal_from(const float4& v0, const float4& vr, const float4& vu,
+                                              const float4& vl, const float4& vd)
+{
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v0.z == 0.f || vr.z == 0.f || vu.z == 0.f || vl.z == 0.f || vd.z == 0.f) return zero;
+    float ax = __fsub_rn(vu.x, vd.x), ay = __fsub_rn(vu.y, vd.y), az = __fsub_rn(vu.z, vd.z);
+    float bx = __fsub_rn(vr.x, vl.x), by = __fsub_rn(vr.y, vl.y), bz = __fsub_rn(vr.z, vl.z);
+    float cxp = hkf_det2(ay, bz, az, by);
+    float cyp = hkf_det2(az, bx, ax, bz);
+    float czp = hkf_det2(ax, by, ay, bx);
+    float3 n = hkf_normalize(cxp, cyp, czp);
+    return make_float4(n.x, n.y, n.z, 0.f);
+}
+
+// pryDownVerticesKernel: ((p00+p01)+p10)+p11 then *0.25, all four components; 0 if any z==0
+__device__ __forceinline__ float4 down_vertex(const float4& p00, const float4& p01, const float4& p10, const float4& p11)
+{
+    if (p00.z == 0.f || p01.z == 0.f || p10.z == 0.f || p11.z == 0.f) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r;
+    r.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.x, p01.x), p10.x), p11.x), 0.25f);
+    r.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.y, p01.y), p10.y), p11.y), 0.25f);
+    r.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.z, p01.z), p10.z), p11.z), 0.25f);
+    r.w = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.w, p01.w), p10.w), p11.w), 0.25f);
+    return r;
+}
+// pryDownNormalsKernel: 0 if any of the four is all-zero; mean then renormalise
+__device__ __forceinline__ float4 down_normal(const float4& p00, const float4& p01, const float4& p10, const float4& p11)
+{
+    if (hkf_is_zero4(p01) || hkf_is_zero4(p10) || hkf_is_zero4(p00) || hkf_is_zero4(p11)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.x, p01.x), p10.x), p11.x), 0.25f);
+    float y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.y, p01.y), p10.y), p11.y), 0.25f);
+    float z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p00.z, p01.z), p10.z), p11.z), 0.25f);
+    float3 n = hkf_normalize(x, y, z);
+    return make_float4(n.x, n.y, n.z, 0.f);
+}
+
+// ---------------------------------------------------------------- per-wrapper kernels (layer 2)
+
+__global__ void k_decode_mm(const uint16_t* __restrict__ mm, float* __restrict__ raw, unsigned n)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) raw[i] = decode_mm(mm[i]);
+}
+
+__global__ void k_trunc(const float* __restrict__ raw, float* __restrict__ out, unsigned n, float tmin, float tmax,
+                        unsigned* __restrict__ dmax_bits)
+{
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    float d = 0.f;
+    if (i < n) { d = trunc_depth(raw[i], tmin, tmax); out[i] = d; }
+    unsigned b = __float_as_uint(d);
+    b = __reduce_max_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(dmax_bits, b);
+}
+
+__global__ void k_bilateral(const float* __restrict__ in, float* __restrict__ out, int cols, int rows, int radius,
+                            float ss, float sd, float thresh)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    auto at = [&](int cx, int cy) { return __ldg(in + (size_t)cy * cols + cx); };
+    out[(size_t)y * cols + x] = bilateral_px(at, x, y, cols, rows, radius, ss, sd, thresh);
+}
+
+__global__ void k_vertices(const float* __restrict__ depth, float4* __restrict__ out, unsigned cols, unsigned rows,
+                           float cx, float cy, float fx, float fy)
+{
+    unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    out[(size_t)y * cols + x] = back_project(x, y, depth[(size_t)y * cols + x], cx, cy, fx, fy);
+}
+
+__global__ void k_normals(const float4* __restrict__ v, float4* __restrict__ out, int cols, int rows)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(x == cols - 1 || y == rows - 1 || x == 0 || y == 0)) {
+        size_t i = (size_t)y * cols + x;
+        r = normal_from(ld_f4(v + i), ld_f4(v + i + 1), ld_f4(v + i + cols), ld_f4(v + i - 1), ld_f4(v + i - cols));
+    }
+    out[(size_t)y * cols + x] = r;
+}
+
+template <bool NORMALS>
+__global__ void k_down(const float4* __restrict__ in, float4* __restrict__ out, unsigned in_cols, unsigned out_cols, unsigned out_rows)
+{
+    unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= out_cols || y >= out_rows) return;
+    const float4* p = in + (size_t)(2 * y) * in_cols + 2 * x;
+    float4 p00 = ld_f4(p), p01 = ld_f4(p + 1), p10 = ld_f4(p + in_cols), p11 = ld_f4(p + in_cols + 1);
+    out[(size_t)y * out_cols + x] = NORMALS ? down_normal(p00, p01, p10, p11) : down_vertex(p00, p01, p10, p11);
+}
+
+// ---------------------------------------------------------------- fused kernel A
+// One 32x8 pixel tile per block.  Shared memory: truncated depth for the tile grown by (radius+1)
+// on every side, then filtered depth for the tile grown by 1.
+#define TILE_W 32
+#define TILE_H 8
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, float* __restrict__ trunc_out,
+                   float* __restrict__ filt_out, float4* __restrict__ v_out, float4* __restrict__ n_out,
+                   int cols, int rows, int radius, float tmin, float tmax, float ss, float sd, float thresh,
+                   float cx, float cy, float fx, float fy, unsigned* __restrict__ dmax_bits)
+{
+    extern __shared__ float smem[];
+    const int ap = radius + 1;
+    const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
+    const int fw = TILE_W + 2, fh = TILE_H + 2;
+    float* s_trunc = smem;              // tw*th, 0 outside the image
+    float* s_filt = smem + tw * th;     // fw*fh
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * TILE_H;
+
+    unsigned local_max = 0;
+    for (int i = tid; i < tw * th; i += TILE_W * TILE_H) {
+        int lx = i % tw, ly = i / tw;
+        int gx = bx0 - ap + lx, gy = by0 - ap + ly;
+        float t = 0.f;
+        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+            float d = decode_mm(__ldg(mm + (size_t)gy * cols + gx));
+            t = trunc_depth(d, tmin, tmax);
+            if (lx >= ap && lx < ap + TILE_W && ly >= ap && ly < ap + TILE_H) {
+                raw_out[(size_t)gy * cols + gx] = d;
+                trunc_out[(size_t)gy * cols + gx] = t;
+                local_max = max(local_max, __float_as_uint(t));
+            }
+        }
+        s_trunc[i] = t;
+    }
+    local_max = __reduce_max_sync(0xffffffffu, local_max);
+    if ((tid & 31) == 0 && local_max) atomicMax(dmax_bits, local_max);
+    __syncthreads();
+
+    auto at = [&](int gx, int gy) { return s_trunc[(gy - by0 + ap) * tw + (gx - bx0 + ap)]; };
+    for (int i = tid; i < fw * fh; i += TILE_W * TILE_H) {
+        int lx = i % fw, ly = i / fw;
+        int gx = bx0 - 1 + lx, gy = by0 - 1 + ly;
+        float f = 0.f;
+        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows)
+            f = bilateral_px(at, gx, gy, cols, rows, radius, ss, sd, thresh);
+        s_filt[i] = f;
+    }
+    __syncthreads();
+
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    const int fi = (threadIdx.y + 1) * fw + threadIdx.x + 1;
+    const float f0 = s_filt[fi];
+    const size_t gi = (size_t)y * cols + x;
+    filt_out[gi] = f0;
+    float4 v0 = back_project(x, y, f0, cx, cy, fx, fy);
+    v_out[gi] = v0;
+    float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(x == cols - 1 || y == rows - 1 || x == 0 || y == 0)) {
+        float4 vr = back_project(x + 1, y, s_filt[fi + 1], cx, cy, fx, fy);
+        float4 vu = back_project(x, y + 1, s_filt[fi + fw], cx, cy, fx, fy);
+        float4 vl = back_project(x - 1, y, s_filt[fi - 1], cx, cy, fx, fy);
+        float4 vd = back_project(x, y - 1, s_filt[fi - fw], cx, cy, fx, fy);
+        n = normal_from(v0, vr, vu, vl, vd);
+    }
+    n_out[gi] = n;
+}
+
+// ---------------------------------------------------------------- fused kernel B: all coarser levels
+// Thread per level-2 pixel: builds its four level-1 pixels (vertices and normals) from the 4x4
+// level-0 block, then the level-2 pixel from those, entirely in registers.  With two levels only
+// the level-1 part runs.
+__global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __restrict__ n0,
+                                 float4* __restrict__ v1, float4* __restrict__ n1,
+                                 float4* __restrict__ v2, float4* __restrict__ n2,
+                                 unsigned c0, unsigned c1, unsigned r1, unsigned c2, unsigned r2)
+{
+    unsigned X = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned Y = blockIdx.y * blockDim.y + threadIdx.y;
+    float4 lv[2][2], ln[2][2];
+    bool have[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            unsigned x1 = 2 * X + i, y1 = 2 * Y + j;
+            have[j][i] = (x1 < c1 && y1 < r1);
+            if (have[j][i]) {
+                const float4* pv = v0 + (size_t)(2 * y1) * c0 + 2 * x1;
+                const float4* pn = n0 + (size_t)(2 * y1) * c0 + 2 * x1;
+                lv[j][i] = down_vertex(ld_f4(pv), ld_f4(pv + 1), ld_f4(pv + c0), ld_f4(pv + c0 + 1));
+                ln[j][i] = down_normal(ld_f4(pn), ld_f4(pn + 1), ld_f4(pn + c0), ld_f4(pn + c0 + 1));
+                v1[(size_t)y1 * c1 + x1] = lv[j][i];
+                n1[(size_t)y1 * c1 + x1] = ln[j][i];
+            }
+        }
+    if (v2 != nullptr && X < c2 && Y < r2) {
+        v2[(size_t)Y * c2 + X] = down_vertex(lv[0][0], lv[0][1], lv[1][0], lv[1][1]);
+        n2[(size_t)Y * c2 + X] = down_normal(ln[0][0], ln[0][1], ln[1][0], ln[1][1]);
+    }
+}
+
+// ---------------------------------------------------------------- host entry points
+
+static inline void bilateral_consts(float sigma_pixel, float sigma_depth, int* radius, float* ss, float* sd, float* thresh)
+{
+    // host wrapper arithmetic: 0.5 / (sigma*sigma) in double (float*float promoted), narrowed
+    // (src/cuda/DataPreprocesser.cu:95-96); kernel: (int)ceil(2.0*sigma_pixel), 5*sigma_data (:45,66)
+    float s2d = sigma_depth * sigma_depth;
+    float s2p = sigma_pixel * sigma_pixel;
+    *sd = (float)(0.5 / (double)s2d);
+    *ss = (float)(0.5 / (double)s2p);
+    *radius = (int)ceil(2.0 * (double)sigma_pixel);
+    *thresh = sigma_depth * 5.0f;
+}
+
+extern "C" int hkf_upload_depth_mm(hkf_ctx* c, const uint16_t* depth_mm, int is_device)
+{
+    if (!c || !depth_mm) return HKF_ERR_ARG;
+    unsigned n = c->cols[0] * c->rows[0];
+    const uint16_t* src = depth_mm;
+    if (!is_device) {
+        HKF_CUDA(c, cudaMemcpyAsync(c->depth_mm, depth_mm, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        src = c->depth_mm;
+    }
+    k_decode_mm<<<div_up(n, 256), 256, 0, c->stream>>>(src, c->raw_depth, n);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_trunc_depth(hkf_ctx* c, float tmin, float tmax)
+{
+    if (!c) return HKF_ERR_ARG;
+    unsigned n = c->cols[0] * c->rows[0];
+    HKF_CUDA(c, cudaMemsetAsync(&c->st->dmax_bits, 0, sizeof(unsigned), c->stream));
+    k_trunc<<<div_up(n, 256), 256, 0, c->stream>>>(c->raw_depth, c->trunc_depth, n, tmin, tmax, &c->st->dmax_bits);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_bilateral_filter_depth(hkf_ctx* c, float sigma_pixel, float sigma_depth)
+{
+    if (!c) return HKF_ERR_ARG;
+    int radius; float ss, sd, thresh;
+    bilateral_consts(sigma_pixel, sigma_depth, &radius, &ss, &sd, &thresh);
+    dim3 b(32, 8), g(div_up(c->cols[0], 32), div_up(c->rows[0], 8));
+    k_bilateral<<<g, b, 0, c->stream>>>(c->trunc_depth, c->filtered_depth, c->cols[0], c->rows[0], radius, ss, sd, thresh);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_calculate_new_vertices(hkf_ctx* c, const HkfCameraParams* cam)
+{
+    if (!c || !cam) return HKF_ERR_ARG;
+    dim3 b(32, 8), g(div_up(c->cols[0], 32), div_up(c->rows[0], 8));
+    k_vertices<<<g, b, 0, c->stream>>>(c->filtered_depth, c->new_v[0], c->cols[0], c->rows[0], cam->cx, cam->cy, cam->fx, cam->fy);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_calculate_new_normals(hkf_ctx* c)
+{
+    if (!c) return HKF_ERR_ARG;
+    dim3 b(32, 8), g(div_up(c->cols[0], 32), div_up(c->rows[0], 8));
+    k_normals<<<g, b, 0, c->stream>>>(c->new_v[0], c->new_n[0], c->cols[0], c->rows[0]);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+template <bool NORMALS>
+static int downsample(hkf_ctx* c, float4** pyr)
+{
+    for (int l = 0; l < c->levels - 1; ++l) {
+        dim3 b(32, 8), g(div_up(c->cols[l + 1], 32), div_up(c->rows[l + 1], 8));
+        k_down<NORMALS><<<g, b, 0, c->stream>>>(pyr[l], pyr[l + 1], c->cols[l], c->cols[l + 1], c->rows[l + 1]);
+        HKF_LAUNCH_CHECK(c);
+    }
+    return HKF_OK;
+}
+extern "C" int hkf_downsample_new_vertices(hkf_ctx* c) { return c ? downsample<false>(c, c->new_v) : HKF_ERR_ARG; }
+extern "C" int hkf_downsample_new_normals(hkf_ctx* c) { return c ? downsample<true>(c, c->new_n) : HKF_ERR_ARG; }
+extern "C" int hkf_downsample_model_vertices(hkf_ctx* c) { return c ? downsample<false>(c, c->model_v) : HKF_ERR_ARG; }
+extern "C" int hkf_downsample_model_normals(hkf_ctx* c) { return c ? downsample<true>(c, c->model_n) : HKF_ERR_ARG; }
+
+// all coarser levels of one (vertices, normals) pyramid pair in a single launch
+int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn)
+{
+    if (c->levels < 2) return HKF_OK;
+    bool three = c->levels >= 3;
+    unsigned gx = div_up(c->cols[1], 2), gy = div_up(c->rows[1], 2);
+    dim3 b(32, 4), g(div_up(gx, 32), div_up(gy, 4));
+    k_pyramids_fused<<<g, b, 0, c->stream>>>(pv[0], pn[0], pv[1], pn[1], three ? pv[2] : nullptr, three ? pn[2] : nullptr,
+                                             c->cols[0], c->cols[1], c->rows[1], three ? c->cols[2] : 0, three ? c->rows[2] : 0);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_preprocess(hkf_ctx* c, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp)
+{
+    if (!c || !depth_mm || !fp) return HKF_ERR_ARG;
+    unsigned n = c->cols[0] * c->rows[0];
+    const uint16_t* src = depth_mm;
+    if (!is_device) {
+        HKF_CUDA(c, cudaMemcpyAsync(c->depth_mm, depth_mm, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        src = c->depth_mm;
+    }
+    int radius; float ss, sd, thresh;
+    bilateral_consts(fp->sigma_pixel, fp->sigma_depth, &radius, &ss, &sd, &thresh);
+    if (radius < 0 || radius > 12) { c->err = "hkf_preprocess: bilateral radius out of range for the fused kernel"; return HKF_ERR_ARG; }
+    HKF_CUDA(c, cudaMemsetAsync(&c->st->dmax_bits, 0, sizeof(unsigned), c->stream));
+    const int ap = radius + 1;
+    size_t smem = ((TILE_W + 2 * ap) * (TILE_H + 2 * ap) + (TILE_W + 2) * (TILE_H + 2)) * sizeof(float);
+    dim3 b(TILE_W, TILE_H), g(div_up(c->cols[0], TILE_W), div_up(c->rows[0], TILE_H));
+    const HkfCameraParams& cam = c->ip.depth_camera;
+    k_preprocess_fused<<<g, b, smem, c->stream>>>(src, c->raw_depth, c->trunc_depth, c->filtered_depth, c->new_v[0], c->new_n[0],
+                                                  (int)c->cols[0], (int)c->rows[0], radius, fp->trunc_min, fp->trunc_max, ss, sd, thresh,
+                                                  cam.cx, cam.cy, cam.fx, cam.fy, &c->st->dmax_bits);
+    HKF_LAUNCH_CHECK(c);
+    return hkf_pyramids_fused(c, c->new_v, c->new_n);
+}
