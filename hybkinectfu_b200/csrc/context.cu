@@ -126,7 +126,6 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
 extern "C" void hkf_destroy(hkf_ctx* c)
 {
     if (!c) return;
-    extern void hkf_shard_release(hkf_ctx*);
     hkf_shard_release(c);
     free_all(c);
     delete c;

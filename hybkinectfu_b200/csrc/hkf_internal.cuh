@@ -97,6 +97,10 @@ struct hkf_ctx {
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+// internal cross-file helpers (C++ linkage)
+void hkf_shard_release(hkf_ctx* c);
+int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn);
+
 // ---------------------------------------------------------------- device arithmetic contract
 #ifdef __CUDACC__
 
