@@ -1,0 +1,179 @@
+// raycast.cu — fixed-step ray marching of the TSDF into world-frame vertex / normal maps.
+//
+// Replaces raycastKernel / raySample / gradientForPoint / getMinTime / getMaxTime and
+// cudaRaycastingVolume (src/cuda/raycastingVolume.cu:15-176).
+//
+// Parity is defined by the sample positions, not just the surface: t starts at t_min and is advanced by
+// repeated float addition of the increment; each sample reads the NEAREST voxel's tsdf; the first
+// (+ -> -) pair ends the ray whether or not the two trilinear refinements and the six gradient
+// evaluations succeed (a failure leaves the pixel zero).  None of that is altered here.
+//
+// What changes: packed 8-byte voxels (a sample touches one 4-byte word instead of a 12-byte AoS record),
+// warps mapped to 8x4 pixel patches so that the rays of a warp traverse neighbouring voxels and share
+// sectors, all eight corner loads of a trilinear evaluation issued before any is tested, the pose taken
+// from device memory (no host round trip), and a z-slab mode for sharded volumes in which each rank
+// reports at most the crossings whose later sample lies in its OWNED planes, as a 64-bit
+// (t | ok | rank) key for nearest-hit compositing.
+//
+// Arithmetic contract (PTX of the reference built for sm_100):
+//   cam_dir = (vx, vy, 1) * rcp.rn(sqrt.rn(fma(vx,vx, vy*vy) + 1)),  vx = ((float)x - cx) / fx
+//   dir     = fma(m_4, 0, fma(cd.z, m_3, fma(cd.x, m_1, cd.y*m_2)))   per pose row; 0 -> 1e-15
+//   t_min   = max(max over axes of ((dir>0 ? 0 : S) - o)/dir, near/cd.z), t_max likewise with min
+//   pos     = fma(dir, t, o);  t += inc
+//   alpha   = t - (inc*ftdt)/(ftdt - ft);  vertex = fma(dir, alpha, o)
+//   normal  = (fx1-fx2, fy1-fy2, fz1-fz2) * rcp.rn(len), len = sqrt.rn(dot3), fails if (double)len < 1e-8
+#include "tsdf_sample.cuh"
+
+struct RaycastArgs {
+    VolView V;
+    int cols, rows;
+    float cx, cy, fx, fy;
+    float inc, near_plane, far_plane;
+    float pose[16];
+    int own_z0, own_z1, rank;
+};
+
+template <bool FROM_STATE, bool SLAB>
+__global__ void __launch_bounds__(256)
+k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
+          unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
+{
+    // 16x16 pixel block, warps as 8x4 patches
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= A.cols || y >= A.rows) return;
+    const size_t pix = (size_t)y * A.cols + x;
+    float4 ov = make_float4(0.f, 0.f, 0.f, 0.f), on = ov;
+    unsigned long long key = ~0ull;
+
+    const float* P = FROM_STATE ? st->pose : A.pose;
+    const float m11 = P[0], m12 = P[1], m13 = P[2], ox = P[3];
+    const float m21 = P[4], m22 = P[5], m23 = P[6], oy = P[7];
+    const float m31 = P[8], m32 = P[9], m33 = P[10], oz = P[11];
+    const VolView& V = A.V;
+    const float S = V.S;
+
+    const float vx = __fdiv_rn(__fsub_rn((float)(unsigned)x, A.cx), A.fx);
+    const float vy = __fdiv_rn(__fsub_rn((float)(unsigned)y, A.cy), A.fy);
+    const float len = __fsqrt_rn(__fadd_rn(__fmaf_rn(vx, vx, __fmul_rn(vy, vy)), 1.0f));
+    float cdx = 0.f, cdy = 0.f, cdz = 0.f;
+    if (!((double)len < 1e-8)) { const float r = __frcp_rn(len); cdx = __fmul_rn(vx, r); cdy = __fmul_rn(vy, r); cdz = r; }
+    float dx = __fmaf_rn(ox, 0.f, __fmaf_rn(cdz, m13, __fmaf_rn(cdx, m11, __fmul_rn(cdy, m12))));
+    float dy = __fmaf_rn(oy, 0.f, __fmaf_rn(cdz, m23, __fmaf_rn(cdx, m21, __fmul_rn(cdy, m22))));
+    float dz = __fmaf_rn(oz, 0.f, __fmaf_rn(cdz, m33, __fmaf_rn(cdx, m31, __fmul_rn(cdy, m32))));
+    if (dx == 0.f) dx = 1e-15f;
+    if (dy == 0.f) dy = 1e-15f;
+    if (dz == 0.f) dz = 1e-15f;
+    const float txmin = __fdiv_rn(__fsub_rn(dx > 0.f ? 0.f : S, ox), dx);
+    const float tymin = __fdiv_rn(__fsub_rn(dy > 0.f ? 0.f : S, oy), dy);
+    const float tzmin = __fdiv_rn(__fsub_rn(dz > 0.f ? 0.f : S, oz), dz);
+    const float txmax = __fdiv_rn(__fsub_rn(dx > 0.f ? S : 0.f, ox), dx);
+    const float tymax = __fdiv_rn(__fsub_rn(dy > 0.f ? S : 0.f, oy), dy);
+    const float tzmax = __fdiv_rn(__fsub_rn(dz > 0.f ? S : 0.f, oz), dz);
+    float tmin = fmaxf(fmaxf(txmin, tymin), tzmin);
+    float tmax = fminf(fminf(txmax, tymax), tzmax);
+    tmin = fmaxf(tmin, __fdiv_rn(A.near_plane, cdz));
+    tmax = fminf(tmax, __fdiv_rn(A.far_plane, cdz));
+
+    if (tmin < tmax) {
+        const int R = V.R;
+        float t = tmin, last_sdf = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
+        bool last_known = true;
+        while (t < tmax) {
+            const float px = __fmaf_rn(dx, t, ox), py = __fmaf_rn(dy, t, oy), pz = __fmaf_rn(dz, t, oz);
+            const int gx = max(0, min(vol_w2v(V, px), R - 1));
+            const int gy = max(0, min(vol_w2v(V, py), R - 1));
+            const int gz = max(0, min(vol_w2v(V, pz), R - 1));
+            bool known = true;
+            float sdf = 0.f;
+            if (SLAB && (gz < V.z_lo || gz >= V.z_hi)) known = false;
+            else sdf = __ldg(&V.vol[vol_index(V, gx, gy, gz)].x);
+            if (known && last_known && last_sdf > 0.0f && sdf < 0.0f) {
+                // first zero crossing: the ray ends here whatever happens next
+                const bool mine = !SLAB || (gz >= A.own_z0 && gz < A.own_z1);
+                if (mine) {
+                    bool ok = false;
+                    float ftdt, ft;
+                    float wx = 0.f, wy = 0.f, wz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+                    do {
+                        if (vol_interp_sdf<SLAB>(V, px, py, pz, ftdt) != 1) break;
+                        if (vol_interp_sdf<SLAB>(V, lx, ly, lz, ft) != 1) break;
+                        const float alpha = __fsub_rn(t, __fdiv_rn(__fmul_rn(A.inc, ftdt), __fsub_rn(ftdt, ft)));
+                        wx = __fmaf_rn(dx, alpha, ox); wy = __fmaf_rn(dy, alpha, oy); wz = __fmaf_rn(dz, alpha, oz);
+                        // gradientForPoint(volume, last_world_pos, vertex)
+                        const int hx = vol_w2v(V, lx), hy = vol_w2v(V, ly), hz = vol_w2v(V, lz);
+                        if (hx <= 1 || hx >= R - 2) break;
+                        if (hy <= 1 || hy >= R - 2) break;
+                        if (hz <= 1 || hz >= R - 2) break;
+                        const float cell = V.cell;
+                        float f1, f2;
+                        if (vol_interp_sdf<SLAB>(V, __fadd_rn(wx, cell), wy, wz, f1) != 1) break;
+                        if (vol_interp_sdf<SLAB>(V, __fsub_rn(wx, cell), wy, wz, f2) != 1) break;
+                        nx = __fsub_rn(f1, f2);
+                        if (vol_interp_sdf<SLAB>(V, wx, __fadd_rn(wy, cell), wz, f1) != 1) break;
+                        if (vol_interp_sdf<SLAB>(V, wx, __fsub_rn(wy, cell), wz, f2) != 1) break;
+                        ny = __fsub_rn(f1, f2);
+                        if (vol_interp_sdf<SLAB>(V, wx, wy, __fadd_rn(wz, cell), f1) != 1) break;
+                        if (vol_interp_sdf<SLAB>(V, wx, wy, __fsub_rn(wz, cell), f2) != 1) break;
+                        nz = __fsub_rn(f1, f2);
+                        const float l = __fsqrt_rn(hkf_dot3(nx, ny, nz, nx, ny, nz));
+                        if ((double)l < 1e-8) break;
+                        const float r = __frcp_rn(l);
+                        nx = __fmul_rn(nx, r); ny = __fmul_rn(ny, r); nz = __fmul_rn(nz, r);
+                        ok = true;
+                    } while (0);
+                    if (ok) { ov = make_float4(wx, wy, wz, 1.0f); on = make_float4(nx, ny, nz, 0.f); }
+                    key = ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)(ok ? 1u : 0u) << 8) | (unsigned)A.rank;
+                    break;
+                }
+                if (!SLAB) break;
+                // another rank owns this crossing and the ray ends there; nothing later can win
+                break;
+            }
+            last_sdf = sdf; last_known = known; lx = px; ly = py; lz = pz;
+            t = __fadd_rn(A.inc, t);
+        }
+    }
+    out_v[pix] = ov;
+    out_n[pix] = on;
+    if (SLAB) keys[pix] = key;
+}
+
+static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParams* rp, const HkfCameraParams* cam,
+                          float near_plane, float far_plane, RaycastArgs* A)
+{
+    A->V = make_volview(c);
+    A->cols = (int)cam->cols; A->rows = (int)cam->rows;
+    A->cx = cam->cx; A->cy = cam->cy; A->fx = cam->fx; A->fy = cam->fy;
+    A->inc = rp->fRayIncrement; A->near_plane = near_plane; A->far_plane = far_plane;
+    if (pose) memcpy(A->pose, pose, 64); else memset(A->pose, 0, 64);
+    A->own_z0 = (int)c->own_z0; A->own_z1 = (int)c->own_z1; A->rank = c->rank;
+}
+
+static inline bool is_slab(const hkf_ctx* c) { return !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution); }
+
+extern "C" int hkf_raycasting_volume(hkf_ctx* c, int has_color, const HkfMat44* transform, const HkfRayCasterParams* rp,
+                                     const HkfCameraParams* cam, float near_plane, float far_plane)
+{
+    if (!c || !transform || !rp || !cam) return HKF_ERR_ARG;
+    if (has_color) { c->err = "colour raycast is out of scope (use_color=0)"; return HKF_ERR_ARG; }
+    if (cam->cols != c->cols[0] || cam->rows != c->rows[0]) { c->err = "camera size mismatch"; return HKF_ERR_ARG; }
+    RaycastArgs A; fill_ray_args(c, transform->m, rp, cam, near_plane, far_plane, &A);
+    dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
+    if (is_slab(c)) k_raycast<false, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    else k_raycast<false, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
+{
+    if (!c || !fp) return HKF_ERR_ARG;
+    RaycastArgs A; fill_ray_args(c, nullptr, &fp->raycast, &c->ip.depth_camera, fp->trunc_min, fp->trunc_max, &A);
+    dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
+    if (is_slab(c)) k_raycast<true, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    else k_raycast<true, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
