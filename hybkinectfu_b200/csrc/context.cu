@@ -173,6 +173,7 @@ static void* buf_ptr(hkf_ctx* c, int buffer, unsigned level, size_t* nbytes)
     case HKF_BUF_VOLUME: *nbytes = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution * sizeof(float2); return c->vol;
     case HKF_BUF_SOLVER_SUMS: *nbytes = HKF_SUMS * sizeof(float); return c->st->sums;
     case HKF_BUF_POSE: *nbytes = 16 * sizeof(float); return c->st->pose;
+    case 100: *nbytes = 8 * sizeof(long long); return c->st->dbg;      // development aid, not part of the ABI
     case HKF_BUF_RAYCAST_KEYS: *nbytes = n0 * sizeof(unsigned long long); return c->ray_keys;
     default: return nullptr;
     }

@@ -29,6 +29,12 @@
 #define HKF_SQRT(a) sqrtf((a))
 #endif
 
+#if defined(__CUDACC__)
+#define HKF_UNROLL4 _Pragma("unroll")
+#else
+#define HKF_UNROLL4
+#endif
+
 // three-factor product (a*b)*c
 #define HKF_M3(a, b, c) HKF_MUL(HKF_MUL((a), (b)), (c))
 
@@ -36,13 +42,16 @@
 HKF_HD void hkf_mat44_mul(const float* a, const float* b, float* c)
 {
     float r[16];
+    HKF_UNROLL4
     for (int i = 0; i < 4; ++i)
+        HKF_UNROLL4
         for (int j = 0; j < 4; ++j) {
             float s = HKF_ADD(HKF_MUL(a[i * 4 + 0], b[0 * 4 + j]), HKF_MUL(a[i * 4 + 1], b[1 * 4 + j]));
             s = HKF_ADD(s, HKF_MUL(a[i * 4 + 2], b[2 * 4 + j]));
             s = HKF_ADD(s, HKF_MUL(a[i * 4 + 3], b[3 * 4 + j]));
             r[i * 4 + j] = s;
         }
+    HKF_UNROLL4
     for (int i = 0; i < 16; ++i) c[i] = r[i];
 }
 
@@ -89,5 +98,6 @@ HKF_HD void hkf_mat44_inverse(const float* e, float* out)
     inv[15] = hkf_cof6(e, 0,5,10, 0,6,9, 4,1,10, 4,2,9, 8,1,6, 8,2,5, false);
     float det = HKF_ADD(HKF_ADD(HKF_ADD(HKF_MUL(e[0], inv[0]), HKF_MUL(e[1], inv[4])), HKF_MUL(e[2], inv[8])), HKF_MUL(e[3], inv[12]));
     float detr = HKF_DIV(1.0f, det);
+    HKF_UNROLL4
     for (int i = 0; i < 16; ++i) out[i] = HKF_MUL(inv[i], detr);
 }

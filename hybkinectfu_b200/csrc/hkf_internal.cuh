@@ -36,6 +36,7 @@ struct HkfDeviceState {
     unsigned long long upd_count;
     float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
     int   sdf_done;          // SDF tracker: converged flag (|x| < 1e-3)
+    long long dbg[8];        // development aid: SM-clock stamps of the last block of a tracking kernel
 };
 
 struct hkf_ctx {
@@ -157,5 +158,14 @@ __device__ __forceinline__ float hkf_row4(float m1, float m2, float m3, float m4
 }
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
+
+// raw MUFU.RCP (1 ulp): only ever used to PRE-classify a value whose exact IEEE result is then either
+// provably implied or recomputed with div.rn
+__device__ __forceinline__ float hkf_rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 #endif // __CUDACC__

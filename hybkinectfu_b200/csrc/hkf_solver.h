@@ -6,14 +6,20 @@
 // src/utils/eigen_utils.cpp:39-127).  Here the last thread block of each tracking kernel runs it on the
 // device so the pose never leaves HBM; the host classes' step-by-step mode calls the very same code on
 // the CPU.  All float operations go through HKF_MUL/ADD/... (explicit round-to-nearest intrinsics on the
-// device, uncontracted operators on the host), so both sides produce the same bits; sin/cos are taken
-// in double and narrowed, which agrees with the float libm the reference's host build would call
-// except for ~2^-16 of arguments (then by one ulp).
+// device, uncontracted operators on the host), so both sides produce the same bits except for the three
+// sinf/cosf pairs and the atan2f of the shake gate, where the CUDA and glibc float libms may differ by an
+// ulp (double-precision trig was measured to cost ~4 us of single-thread latency per iteration).
 //
 // Eigen is an un-vendored, un-pinned dependency of the reference (README.md:14): the algorithms below are
 // Eigen 3.4's (unblocked LLT, partial-pivot LU determinant, AngleAxis/Quaternion conversions) restated.
 #pragma once
 #include "hkf_hostdev_math.h"
+
+#if defined(__CUDACC__)
+#define HKF_UNROLL _Pragma("unroll")
+#else
+#define HKF_UNROLL
+#endif
 
 #define HKF_SOLVE_OK 0
 #define HKF_SOLVE_SINGULAR 1
@@ -21,40 +27,72 @@
 
 HKF_HD void hkf_unpack27(const float* s, float* A, float* b)
 {
-    int shift = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 7; ++j) {
-            float v = s[shift++];
-            if (j == 6) b[i] = v;
-            else { A[i * 6 + j] = v; A[j * 6 + i] = v; }
+    // row i of the packed upper triangle starts at i*7 - i*(i-1)/2
+    HKF_UNROLL
+    for (int i = 0; i < 6; ++i) {
+        const int base = i * 7 - (i * (i - 1)) / 2;
+        HKF_UNROLL
+        for (int j = 0; j < 7; ++j) {
+            if (j >= i) {
+                float v = s[base + (j - i)];
+                if (j == 6) b[i] = v;
+                else { A[i * 6 + j] = v; A[j * 6 + i] = v; }
+            }
         }
+    }
 }
 
+// NOTE on loop shapes: nvcc only keeps these 6x6 work arrays in registers when every loop has constant
+// bounds (triangular "for (i = k+1; ...)" nests are left partially rolled and force the arrays into local
+// memory, which made the single-thread solve ~50 us).  Hence full-range loops with "if (i > k)" guards,
+// which fold away after unrolling.
 HKF_HD float hkf_det6(const float* Ain)
 {
     float a[36];
+    HKF_UNROLL
     for (int i = 0; i < 36; ++i) a[i] = Ain[i];
     float sign = 1.0f;
+    bool singular = false;
+    HKF_UNROLL
     for (int k = 0; k < 6; ++k) {
         int piv = k;
         float best = fabsf(a[k * 6 + k]);
-        for (int i = k + 1; i < 6; ++i) {
-            float v = fabsf(a[i * 6 + k]);
-            if (v > best) { best = v; piv = i; }
+        HKF_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                float v = fabsf(a[i * 6 + k]);
+                if (v > best) { best = v; piv = i; }
+            }
         }
-        if (best == 0.0f) return 0.0f;
-        if (piv != k) {
-            for (int j = 0; j < 6; ++j) { float t = a[k * 6 + j]; a[k * 6 + j] = a[piv * 6 + j]; a[piv * 6 + j] = t; }
-            sign = -sign;
+        if (best == 0.0f) singular = true;
+        HKF_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                const bool sw = (piv == i);
+                HKF_UNROLL
+                for (int j = 0; j < 6; ++j) {
+                    const float t0 = a[k * 6 + j], t1 = a[i * 6 + j];
+                    a[k * 6 + j] = sw ? t1 : t0;
+                    a[i * 6 + j] = sw ? t0 : t1;
+                }
+                sign = sw ? -sign : sign;
+            }
         }
-        float pk = a[k * 6 + k];
-        for (int i = k + 1; i < 6; ++i) {
-            float f = HKF_DIV(a[i * 6 + k], pk);
-            a[i * 6 + k] = f;
-            for (int j = k + 1; j < 6; ++j) a[i * 6 + j] = HKF_SUB(a[i * 6 + j], HKF_MUL(f, a[k * 6 + j]));
+        const float pk = a[k * 6 + k];
+        HKF_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                const float f = HKF_DIV(a[i * 6 + k], pk);
+                a[i * 6 + k] = f;
+                HKF_UNROLL
+                for (int j = 0; j < 6; ++j)
+                    if (j > k) a[i * 6 + j] = HKF_SUB(a[i * 6 + j], HKF_MUL(f, a[k * 6 + j]));
+            }
         }
     }
+    if (singular) return 0.0f;
     float p = a[0];
+    HKF_UNROLL
     for (int k = 1; k < 6; ++k) p = HKF_MUL(p, a[k * 6 + k]);
     return HKF_MUL(sign, p);
 }
@@ -62,42 +100,63 @@ HKF_HD float hkf_det6(const float* Ain)
 HKF_HD void hkf_llt_solve6(const float* A, const float* b, float* x)
 {
     float L[36];
+    HKF_UNROLL
     for (int i = 0; i < 36; ++i) L[i] = 0.0f;
+    HKF_UNROLL
     for (int k = 0; k < 6; ++k) {
         float d = A[k * 6 + k];
-        for (int j = 0; j < k; ++j) d = HKF_SUB(d, HKF_MUL(L[k * 6 + j], L[k * 6 + j]));
-        float lkk = HKF_SQRT(d);
+        HKF_UNROLL
+        for (int j = 0; j < 6; ++j)
+            if (j < k) d = HKF_SUB(d, HKF_MUL(L[k * 6 + j], L[k * 6 + j]));
+        const float lkk = HKF_SQRT(d);
         L[k * 6 + k] = lkk;
-        for (int i = k + 1; i < 6; ++i) {
-            float v = A[i * 6 + k];
-            for (int j = 0; j < k; ++j) v = HKF_SUB(v, HKF_MUL(L[i * 6 + j], L[k * 6 + j]));
-            L[i * 6 + k] = HKF_DIV(v, lkk);
+        HKF_UNROLL
+        for (int i = 0; i < 6; ++i) {
+            if (i > k) {
+                float v = A[i * 6 + k];
+                HKF_UNROLL
+                for (int j = 0; j < 6; ++j)
+                    if (j < k) v = HKF_SUB(v, HKF_MUL(L[i * 6 + j], L[k * 6 + j]));
+                L[i * 6 + k] = HKF_DIV(v, lkk);
+            }
         }
     }
     float y[6];
+    HKF_UNROLL
     for (int i = 0; i < 6; ++i) {
         float v = b[i];
-        for (int j = 0; j < i; ++j) v = HKF_SUB(v, HKF_MUL(L[i * 6 + j], y[j]));
+        HKF_UNROLL
+        for (int j = 0; j < 6; ++j)
+            if (j < i) v = HKF_SUB(v, HKF_MUL(L[i * 6 + j], y[j]));
         y[i] = HKF_DIV(v, L[i * 6 + i]);
     }
-    for (int i = 5; i >= 0; --i) {
+    HKF_UNROLL
+    for (int ii = 0; ii < 6; ++ii) {
+        const int i = 5 - ii;
         float v = y[i];
-        for (int j = i + 1; j < 6; ++j) v = HKF_SUB(v, HKF_MUL(L[j * 6 + i], x[j]));
+        // ascending j as in the reference restatement: j = i+1 .. 5
+        HKF_UNROLL
+        for (int j = 0; j < 6; ++j)
+            if (j > i) v = HKF_SUB(v, HKF_MUL(L[j * 6 + i], x[j]));
         x[i] = HKF_DIV(v, L[i * 6 + i]);
     }
 }
 
 HKF_HD void hkf_mat3_mul(const float* a, const float* b, float* c)
 {
+    HKF_UNROLL
     for (int i = 0; i < 3; ++i)
+        HKF_UNROLL
         for (int j = 0; j < 3; ++j)
             c[i * 3 + j] = HKF_ADD(HKF_ADD(HKF_MUL(a[i * 3 + 0], b[0 * 3 + j]), HKF_MUL(a[i * 3 + 1], b[1 * 3 + j])), HKF_MUL(a[i * 3 + 2], b[2 * 3 + j]));
 }
 
 HKF_HD void hkf_rot_axis(int axis, float ang, float* R)
 {
-    float s = (float)sin((double)ang), c = (float)cos((double)ang);
+    // Eigen's AngleAxisf uses the float libm (sinf/cosf); host and device libms may differ by an ulp here
+    float s = sinf(ang), c = cosf(ang);
     float one = HKF_ADD(HKF_SUB(1.0f, c), c);
+    HKF_UNROLL
     for (int i = 0; i < 9; ++i) R[i] = 0.0f;
     if (axis == 0) { R[0] = one; R[4] = c; R[5] = -s; R[7] = s; R[8] = c; }
     else if (axis == 1) { R[4] = one; R[0] = c; R[2] = s; R[6] = -s; R[8] = c; }
@@ -116,23 +175,22 @@ HKF_HD float hkf_rotation_angle(const float* m)
         qx = HKF_MUL(HKF_SUB(m[7], m[5]), t);
         qy = HKF_MUL(HKF_SUB(m[2], m[6]), t);
         qz = HKF_MUL(HKF_SUB(m[3], m[1]), t);
-    } else {
-        int i = 0;
-        if (m[4] > m[0]) i = 1;
-        if (m[8] > m[i * 3 + i]) i = 2;
-        int j = (i + 1) % 3, k = (j + 1) % 3;
-        float q[3];
-        t = HKF_SQRT(HKF_ADD(HKF_SUB(HKF_SUB(m[i * 3 + i], m[j * 3 + j]), m[k * 3 + k]), 1.0f));
-        q[i] = HKF_MUL(0.5f, t);
-        t = HKF_DIV(0.5f, t);
-        qw = HKF_MUL(HKF_SUB(m[k * 3 + j], m[j * 3 + k]), t);
-        q[j] = HKF_MUL(HKF_ADD(m[j * 3 + i], m[i * 3 + j]), t);
-        q[k] = HKF_MUL(HKF_ADD(m[k * 3 + i], m[i * 3 + k]), t);
-        qx = q[0]; qy = q[1]; qz = q[2];
+    } else if (m[0] >= m[4] && m[0] >= m[8]) {          // i = 0, j = 1, k = 2
+        t = HKF_SQRT(HKF_ADD(HKF_SUB(HKF_SUB(m[0], m[4]), m[8]), 1.0f));
+        qx = HKF_MUL(0.5f, t); t = HKF_DIV(0.5f, t);
+        qw = HKF_MUL(HKF_SUB(m[7], m[5]), t); qy = HKF_MUL(HKF_ADD(m[3], m[1]), t); qz = HKF_MUL(HKF_ADD(m[6], m[2]), t);
+    } else if (m[4] > m[0] && m[4] >= m[8]) {           // i = 1, j = 2, k = 0
+        t = HKF_SQRT(HKF_ADD(HKF_SUB(HKF_SUB(m[4], m[8]), m[0]), 1.0f));
+        qy = HKF_MUL(0.5f, t); t = HKF_DIV(0.5f, t);
+        qw = HKF_MUL(HKF_SUB(m[2], m[6]), t); qz = HKF_MUL(HKF_ADD(m[7], m[5]), t); qx = HKF_MUL(HKF_ADD(m[1], m[3]), t);
+    } else {                                            // i = 2, j = 0, k = 1
+        t = HKF_SQRT(HKF_ADD(HKF_SUB(HKF_SUB(m[8], m[0]), m[4]), 1.0f));
+        qz = HKF_MUL(0.5f, t); t = HKF_DIV(0.5f, t);
+        qw = HKF_MUL(HKF_SUB(m[3], m[1]), t); qx = HKF_MUL(HKF_ADD(m[2], m[6]), t); qy = HKF_MUL(HKF_ADD(m[5], m[7]), t);
     }
     float n = HKF_SQRT(HKF_ADD(HKF_ADD(HKF_MUL(qx, qx), HKF_MUL(qy, qy)), HKF_MUL(qz, qz)));
     if (n == 0.0f) return 0.0f;
-    return (float)(2.0 * atan2((double)n, (double)fabsf(qw)));
+    return HKF_MUL(2.0f, atan2f(n, fabsf(qw)));
 }
 
 // x -> T = [Rx*Ry*Rz | t] with the shake gate; returns false when gated (a NaN passes, as in the reference)
@@ -155,6 +213,7 @@ HKF_HD bool hkf_vector6_to_transform(const float* x, float angle_shake, float di
 HKF_HD float hkf_norm6(const float* x)
 {
     float s = HKF_MUL(x[0], x[0]);
+    HKF_UNROLL
     for (int i = 1; i < 6; ++i) s = HKF_ADD(s, HKF_MUL(x[i], x[i]));
     return HKF_SQRT(s);
 }

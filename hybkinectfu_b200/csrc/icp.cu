@@ -37,51 +37,71 @@ struct IcpArgs {
     float cur[16], last_inv[16];   // only used when !FROM_STATE
 };
 
-// one pixel: findCorrs + buildPointToPlaneSolverRows.  r[7] = 0 when there is no correspondence.
-__device__ __forceinline__ void icp_row(const IcpArgs& A, const float* __restrict__ cur, const float* __restrict__ li,
-                                        int x, int y, float* r)
+// Correspondence + solver row for a batch of NB pixels of one lane, in three phases so that the NB
+// coalesced loads and then the NB gathers are all in flight together (findCorrs +
+// buildPointToPlaneSolverRows; r[.][7] = 0 when there is no correspondence).
+template <int NB>
+__device__ __forceinline__ void icp_rows(const IcpArgs& A, const float* __restrict__ cur, const float* __restrict__ li,
+                                         const int* xs, const int* ys, float (*r)[7])
 {
+    float4 n[NB], v[NB];
+    bool ok[NB];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) r[k] = 0.f;
-    if (x >= A.cols || y >= A.rows || y < A.y0 || y >= A.y1) return;
-    const size_t idx = (size_t)y * A.cols + x;
-    const float4 n = ld_f4(A.new_n + idx);
-    if (hkf_is_zero4(n)) return;
-    const float4 v = ld_f4(A.new_v + idx);
-    // v_input_g = cur * v (lead-first), n_input_g = cur * n (lead-second): as contracted in the reference PTX
-    const float qx = hkf_row4<true>(cur[0], cur[1], cur[2], cur[3], v.x, v.y, v.z, v.w);
-    const float qy = hkf_row4<true>(cur[4], cur[5], cur[6], cur[7], v.x, v.y, v.z, v.w);
-    const float qz = hkf_row4<true>(cur[8], cur[9], cur[10], cur[11], v.x, v.y, v.z, v.w);
-    const float qw = hkf_row4<true>(cur[12], cur[13], cur[14], cur[15], v.x, v.y, v.z, v.w);
-    const float nix = hkf_row4<false>(cur[0], cur[1], cur[2], cur[3], n.x, n.y, n.z, n.w);
-    const float niy = hkf_row4<false>(cur[4], cur[5], cur[6], cur[7], n.x, n.y, n.z, n.w);
-    const float niz = hkf_row4<false>(cur[8], cur[9], cur[10], cur[11], n.x, n.y, n.z, n.w);
-    // v_cp = last_inv * v_input_g (lead-second); projective association, no z > 0 test
-    const float px = hkf_row4<false>(li[0], li[1], li[2], li[3], qx, qy, qz, qw);
-    const float py = hkf_row4<false>(li[4], li[5], li[6], li[7], qx, qy, qz, qw);
-    const float pz = hkf_row4<false>(li[8], li[9], li[10], li[11], qx, qy, qz, qw);
-    const int u = hkf_round_px(hkf_project1(px, A.fx, pz, A.cx));
-    const int w = hkf_round_px(hkf_project1(py, A.fy, pz, A.cy));
-    if (u < 0 || u >= A.cols || w < 0 || w >= A.rows) return;
-    const size_t midx = (size_t)w * A.cols + u;
-    const float4 nt = ld_f4(A.model_n + midx);
-    if (hkf_is_zero4(nt)) return;
-    const float4 p = ld_f4(A.model_v + midx);
-    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
-    const float d = __fsqrt_rn(hkf_dot3(dx, dy, dz, dx, dy, dz));
-    const float sx = hkf_det2(nt.y, niz, nt.z, niy);
-    const float sy = hkf_det2(nt.z, nix, nt.x, niz);
-    const float sz = hkf_det2(nt.x, niy, nt.y, nix);
-    const float s = __fsqrt_rn(hkf_dot3(sx, sy, sz, sx, sy, sz));
-    if (d > A.dist_thres || s > A.sin_thres) return;
-    r[0] = hkf_det2(qy, nt.z, qz, nt.y);
-    r[1] = hkf_det2(qz, nt.x, qx, nt.z);
-    r[2] = hkf_det2(qx, nt.y, qy, nt.x);
-    r[3] = nt.x; r[4] = nt.y; r[5] = nt.z;
-    r[6] = hkf_dot3(nt.x, nt.y, nt.z, dx, dy, dz);
+    for (int b = 0; b < NB; ++b) {
+        ok[b] = !(xs[b] >= A.cols || ys[b] >= A.rows || ys[b] < A.y0 || ys[b] >= A.y1);
+        const size_t idx = ok[b] ? (size_t)ys[b] * A.cols + xs[b] : 0;
+        n[b] = ld_f4(A.new_n + idx);
+        v[b] = ld_f4(A.new_v + idx);
+    }
+    float qx[NB], qy[NB], qz[NB], nix[NB], niy[NB], niz[NB];
+    size_t midx[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        ok[b] = ok[b] && !hkf_is_zero4(n[b]);
+        // v_input_g = cur * v (lead-first), n_input_g = cur * n (lead-second): as contracted in the reference PTX
+        qx[b] = hkf_row4<true>(cur[0], cur[1], cur[2], cur[3], v[b].x, v[b].y, v[b].z, v[b].w);
+        qy[b] = hkf_row4<true>(cur[4], cur[5], cur[6], cur[7], v[b].x, v[b].y, v[b].z, v[b].w);
+        qz[b] = hkf_row4<true>(cur[8], cur[9], cur[10], cur[11], v[b].x, v[b].y, v[b].z, v[b].w);
+        const float qw = hkf_row4<true>(cur[12], cur[13], cur[14], cur[15], v[b].x, v[b].y, v[b].z, v[b].w);
+        nix[b] = hkf_row4<false>(cur[0], cur[1], cur[2], cur[3], n[b].x, n[b].y, n[b].z, n[b].w);
+        niy[b] = hkf_row4<false>(cur[4], cur[5], cur[6], cur[7], n[b].x, n[b].y, n[b].z, n[b].w);
+        niz[b] = hkf_row4<false>(cur[8], cur[9], cur[10], cur[11], n[b].x, n[b].y, n[b].z, n[b].w);
+        // v_cp = last_inv * v_input_g (lead-second); projective association, no z > 0 test
+        const float px = hkf_row4<false>(li[0], li[1], li[2], li[3], qx[b], qy[b], qz[b], qw);
+        const float py = hkf_row4<false>(li[4], li[5], li[6], li[7], qx[b], qy[b], qz[b], qw);
+        const float pz = hkf_row4<false>(li[8], li[9], li[10], li[11], qx[b], qy[b], qz[b], qw);
+        const int u = hkf_round_px(hkf_project1(px, A.fx, pz, A.cx));
+        const int w = hkf_round_px(hkf_project1(py, A.fy, pz, A.cy));
+        ok[b] = ok[b] && !(u < 0 || u >= A.cols || w < 0 || w >= A.rows);
+        midx[b] = ok[b] ? (size_t)w * A.cols + u : 0;
+    }
+    float4 nt[NB], p[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        nt[b] = ld_f4(A.model_n + midx[b]);
+        p[b] = ld_f4(A.model_v + midx[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        ok[b] = ok[b] && !hkf_is_zero4(nt[b]);
+        const float dx = __fsub_rn(p[b].x, qx[b]), dy = __fsub_rn(p[b].y, qy[b]), dz = __fsub_rn(p[b].z, qz[b]);
+        const float d = __fsqrt_rn(hkf_dot3(dx, dy, dz, dx, dy, dz));
+        const float sx = hkf_det2(nt[b].y, niz[b], nt[b].z, niy[b]);
+        const float sy = hkf_det2(nt[b].z, nix[b], nt[b].x, niz[b]);
+        const float sz = hkf_det2(nt[b].x, niy[b], nt[b].y, nix[b]);
+        const float s = __fsqrt_rn(hkf_dot3(sx, sy, sz, sx, sy, sz));
+        ok[b] = ok[b] && !(d > A.dist_thres || s > A.sin_thres);
+        r[b][0] = ok[b] ? hkf_det2(qy[b], nt[b].z, qz[b], nt[b].y) : 0.f;
+        r[b][1] = ok[b] ? hkf_det2(qz[b], nt[b].x, qx[b], nt[b].z) : 0.f;
+        r[b][2] = ok[b] ? hkf_det2(qx[b], nt[b].y, qy[b], nt[b].x) : 0.f;
+        r[b][3] = ok[b] ? nt[b].x : 0.f;
+        r[b][4] = ok[b] ? nt[b].y : 0.f;
+        r[b][5] = ok[b] ? nt[b].z : 0.f;
+        r[b][6] = ok[b] ? hkf_dot3(nt[b].x, nt[b].y, nt[b].z, dx, dy, dz) : 0.f;
+    }
 }
 
-#define ICP_WARPS 4
+#define ICP_WARPS 8
 
 template <bool FROM_STATE>
 __global__ void __launch_bounds__(ICP_WARPS * 32)
@@ -90,6 +110,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     __shared__ float s_sums[HKF_SUMS];
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long t0 = clock64();
     if (FROM_STATE && st->track_status != HKF_TRACK_OK) return;      // a failed iteration ends the frame's tracking
 
     float cur[16], li[16];
@@ -106,9 +127,14 @@ k_icp(IcpArgs A, HkfDeviceState* st)
         const int bx = tile % A.gx, by = tile / A.gx;
         float r[8][7];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int tid = lane + 32 * j;
-            icp_row(A, cur, li, bx * 16 + (tid & 15), by * 16 + (tid >> 4), r[j]);
+        for (int jb = 0; jb < 8; jb += 4) {
+            int xs[4], ys[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int tid = lane + 32 * (jb + b);
+                xs[b] = bx * 16 + (tid & 15); ys[b] = by * 16 + (tid >> 4);
+            }
+            icp_rows<4>(A, cur, li, xs, ys, &r[jb]);
         }
         int shift = 0;
 #pragma unroll
@@ -125,6 +151,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     }
 
     // ---- last block folds the partials and (fused mode) advances the pose
+    const long long t1 = clock64();
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -133,12 +160,11 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     }
     __syncthreads();
     if (!s_last) return;
+    const long long t2 = clock64();
     __threadfence();
-    for (int k = warp; k < HKF_SUMS; k += ICP_WARPS) {
-        const float c = second_stage_row(A.partials + (size_t)k * A.ntiles, A.ntiles, lane);
-        if (lane == 0) s_sums[k] = c;
-    }
+    second_stage_all<ICP_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
     __syncthreads();
+    const long long t3 = clock64();
     if (threadIdx.x < HKF_SUMS) st->sums[threadIdx.x] = s_sums[threadIdx.x];
     if (threadIdx.x == 0) {
         st->ticket = 0;
@@ -160,6 +186,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
                 }
             }
         }
+        st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3;
     }
 }
 

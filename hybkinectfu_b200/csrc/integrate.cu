@@ -7,24 +7,34 @@
 // field by field, every voxel of the cube projected every frame, plus a cudaMalloc/cudaFree/D2H
 // and an atomicAdd per thread per call.
 //
-// This design (HBM-bound integer/float streaming, no tensor cores):
+// This design (HBM-bound streaming, no tensor cores):
 //  * storage is packed {f32 tsdf, f32 weight} (8 B) in [z][y][x] order, x fastest;
-//  * one warp owns one (y,z) row at a time; a lane owns two adjacent voxels, so a warp moves
-//    512 contiguous bytes per 128-bit load/store instruction;
-//  * before touching memory the warp intersects its row (a straight line in camera space) with
-//    the view frustum and the frame's depth range analytically, so voxels that cannot be updated
-//    are neither projected nor read.  The analytic interval is a conservative superset (1 px /
-//    1 voxel margins); the per-voxel test that decides an update is the reference's exact
-//    arithmetic below, so the update mask is bit-identical;
-//  * the depth map (1.2 MB) is read through the read-only path and stays L1/L2-resident; adjacent
-//    rows of a block are adjacent in y so their depth footprints overlap;
-//  * voxels whose tests fail are not written: DRAM traffic ~ 16 B x N_upd.
+//  * one warp owns one (y,z) row; a lane owns voxel x = chunk + lane, so a warp moves 256 contiguous
+//    bytes per load/store instruction and rows of a block are adjacent in y (overlapping depth footprints);
+//  * before touching memory the warp intersects its row (a straight line in camera space) with the view
+//    frustum and the frame's depth range analytically, so voxels that cannot be updated are neither
+//    projected nor read.  The interval is a conservative superset (1 px / 1 voxel margins); the per-voxel
+//    tests that decide an update are the reference's, so the update mask is bit-identical;
+//  * the first ncu capture (profiles/r1_integrate_a.txt) showed the straightforward kernel to be
+//    ISSUE-bound (74 % issue-active, 21 % DRAM), not HBM-bound: ~170 instructions per voxel, dominated by
+//    three IEEE divisions, f64 rounding and int<->float conversions on the quarter-rate XU pipe.  The
+//    inner loop therefore decides everything it can from cheap approximations and only falls back to the
+//    reference's exact sequence where the approximation cannot prove the result:
+//      - pixel index: one MUFU.RCP shared by both axes gives the pixel coordinate to < 2e-4 px; unless it
+//        lies within 2^-9 px of a rounding boundary the reference's integer is already decided
+//        (float->int through the 1.5*2^23 magic constant: FMA-pipe only, no XU conversions);
+//      - tsdf = fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19) (free space): no division;
+//      - t' = fma(t,w,tsdf)/(w+1) is exactly 1 when t == tsdf == 1: no division;
+//      - a voxel whose bits do not change (saturated weight, unchanged tsdf) is not stored.
+//    Every voxel still ends with exactly the reference's bits (tests/test_gpu_stages.py).
+//  * the depth map (1.2 MB) is read through the read-only path and stays L1/L2-resident;
+//  * DRAM traffic ~ 16 B x N_upd.
 //
 // Arithmetic contract (SASS of the reference built for sm_100, see oracle/Makefile):
 //   cell = S / (float)R                     (div.rn, per axis)
 //   w?   = ((float)i + 0.5f) * cell         (add, mul)
 //   X    = fma(wz, m13, fma(wx, m11, wy*m12)) + m14     (likewise Y, Z with rows 2, 3 of T^-1)
-//   skip if !(Z > 0)
+//   skip if Z <= 0
 //   u    = (int)trunc((double)((X*fx)/Z + cx) + 0.5)    (mul, div.rn, add, f64 add, cvt.rzi)
 //   skip unless 1 <= u < cols-1 and 1 <= v < rows-1
 //   d    = trunc_depth[v][u]; skip if d == 0 or !(d < fMaxIntegrateDist)
@@ -45,12 +55,13 @@ struct IntegrateArgs {
     float size;         // S
 };
 
-// clip the world-x interval [lo,hi] with a*wx + b >= 0
+// clip the world-x interval [lo,hi] with a*wx + b >= 0 (approximate division: the caller adds margins)
 __device__ __forceinline__ void clip_lin(float& lo, float& hi, float a, float b)
 {
     const float eps = 1e-12f;
-    if (a > eps) lo = fmaxf(lo, -b / a);
-    else if (a < -eps) hi = fminf(hi, -b / a);
+    const float q = __fdividef(-b, a);
+    if (a > eps) lo = fmaxf(lo, q);
+    else if (a < -eps) hi = fminf(hi, q);
     else if (b < 0.f) { lo = 1.f; hi = 0.f; }
 }
 
@@ -114,63 +125,66 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
     else if (hasA) { lo = loA; hi = hiA; }
     else if (hasB) { lo = loB; hi = hiB; }
     else return;
-    int x_lo = (int)floorf(lo / cell - 0.5f) - 1;
-    int x_hi = (int)ceilf(hi / cell - 0.5f) + 1;
+    const float rcell = __fdividef(1.0f, cell);
+    int x_lo = (int)floorf(lo * rcell - 0.5f) - 1;
+    int x_hi = (int)ceilf(hi * rcell - 0.5f) + 1;
     x_lo = max(x_lo, 0); x_hi = min(x_hi, R - 1);
     if (x_lo > x_hi) return;
 
     float2* rowp = vol + (size_t)row * R;
     const int cols = A.cols, rows = A.rows;
+    const unsigned ulim = (unsigned)(cols - 2), vlim = (unsigned)(rows - 2);
     const float ntrunc = -A.trunc;
-    unsigned long long local_count = 0;
+    const float thr_one = A.trunc * 1.000002f;
+    const float cxh = A.cx + 0.5f, cyh = A.cy + 0.5f;
+    const float MAGIC = 12582912.0f;             // 1.5 * 2^23: float add rounds to the nearest integer, kept in the mantissa
+    const float eps = 0.001953125f;              // 2^-9 px
+    unsigned local_count = 0;
 
-    for (int xb = (x_lo & ~63); xb <= x_hi; xb += 64) {
-        const int x0 = xb + 2 * lane;
-        if (x0 >= R) continue;
-        float tsdf_new[2];
-        bool upd[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            upd[k] = false;
-            tsdf_new[k] = 0.f;
-            const int x = x0 + k;
-            const float wx = __fmul_rn(__fadd_rn((float)x, 0.5f), cell);
-            const float Z = __fadd_rn(__fmaf_rn(wz, m33, __fmaf_rn(wx, m31, ty3)), m34);
-            if (Z <= 0.f) continue;                 // reference: pf.z <= 0 (a NaN falls through, as there)
-            const float X = __fadd_rn(__fmaf_rn(wz, m13, __fmaf_rn(wx, m11, ty1)), m14);
-            const float Y = __fadd_rn(__fmaf_rn(wz, m23, __fmaf_rn(wx, m21, ty2)), m24);
-            const int u = hkf_round_px(hkf_project1(X, A.fx, Z, A.cx));
-            const int v = hkf_round_px(hkf_project1(Y, A.fy, Z, A.cy));
-            if (u < 1 || v < 1 || u >= cols - 1 || v >= rows - 1) continue;
-            const float d = __ldg(depth + (size_t)v * cols + u);
-            if (d == 0.f) continue;
-            if (!(d < A.maxdist)) continue;
-            const float sdf = __fsub_rn(d, Z);
-            if (!(sdf > ntrunc)) continue;
-            tsdf_new[k] = fminf(__fdiv_rn(sdf, A.trunc), 1.0f);
-            upd[k] = true;
+    const int xs = (x_lo & ~31) + lane;
+    float xf = (float)xs;
+#pragma unroll 2
+    for (int x = xs; x <= x_hi; x += 32, xf += 32.0f) {
+        const float wx = __fmul_rn(__fadd_rn(xf, 0.5f), cell);
+        const float Z = __fadd_rn(__fmaf_rn(wz, m33, __fmaf_rn(wx, m31, ty3)), m34);
+        const float X = __fadd_rn(__fmaf_rn(wz, m13, __fmaf_rn(wx, m11, ty1)), m14);
+        const float Y = __fadd_rn(__fmaf_rn(wz, m23, __fmaf_rn(wx, m21, ty2)), m24);
+        const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
+        bool live = (x < R) && (Z > 0.f);
+        // approximate pixel coordinate + 0.5, its nearest integer and floor without leaving the FMA/ALU pipes
+        const float rz = hkf_rcp_approx(Z);
+        const float fu = __fmaf_rn(ax, rz, cxh), fv = __fmaf_rn(ay, rz, cyh);
+        const float tu = __fadd_rn(fu, MAGIC), tv = __fadd_rn(fv, MAGIC);
+        const float du = __fsub_rn(fu, __fsub_rn(tu, MAGIC)), dv = __fsub_rn(fv, __fsub_rn(tv, MAGIC));
+        int u = __float_as_int(tu) - 0x4B400000 - (du < 0.f ? 1 : 0);
+        int v = __float_as_int(tv) - 0x4B400000 - (dv < 0.f ? 1 : 0);
+        if (live && (fabsf(du) < eps || fabsf(dv) < eps || !(Z >= 0.01f))) {
+            // within 2^-9 px of a rounding boundary (or ill-conditioned): the reference's exact sequence decides
+            u = hkf_round_px(hkf_project1(X, A.fx, Z, A.cx));
+            v = hkf_round_px(hkf_project1(Y, A.fy, Z, A.cy));
         }
+        live = live && ((unsigned)(u - 1) < ulim) && ((unsigned)(v - 1) < vlim);
+        float d = 0.f;
+        if (live) d = __ldg(depth + v * cols + u);
+        const float sdf = __fsub_rn(d, Z);
+        live = live && (d != 0.f) && (d < A.maxdist) && (sdf > ntrunc);
         if (COUNT_ONLY) {
-            local_count += (upd[0] ? 1 : 0) + (upd[1] ? 1 : 0);
-        } else if (upd[0] || upd[1]) {
-            float4* p = reinterpret_cast<float4*>(rowp + x0);
-            float4 vx = *p;
-            if (upd[0]) {
-                float w1 = __fadd_rn(vx.y, 1.0f);
-                vx.x = __fdiv_rn(__fmaf_rn(vx.x, vx.y, tsdf_new[0]), w1);
-                vx.y = fminf(w1, A.wmax);
-            }
-            if (upd[1]) {
-                float w1 = __fadd_rn(vx.w, 1.0f);
-                vx.z = __fdiv_rn(__fmaf_rn(vx.z, vx.w, tsdf_new[1]), w1);
-                vx.w = fminf(w1, A.wmax);
-            }
-            *p = vx;
+            local_count += live ? 1u : 0u;
+        } else if (live) {
+            const float2 old = rowp[x];
+            // fminf(sdf/trunc, 1): the quotient is >= 1 for sure once sdf >= trunc*(1+2^-19): free space, no division
+            const float tsdf = (sdf >= thr_one) ? 1.0f : fminf(__fdiv_rn(sdf, A.trunc), 1.0f);
+            const float w1 = __fadd_rn(old.y, 1.0f);
+            // fma(1,w,1) == w+1 exactly, so the quotient is exactly 1 when t == tsdf == 1
+            const float tn = (old.x == 1.0f && tsdf == 1.0f) ? 1.0f : __fdiv_rn(__fmaf_rn(old.x, old.y, tsdf), w1);
+            const float wn = fminf(w1, A.wmax);
+            // a voxel whose bits do not change (saturated weight, unchanged tsdf) needs no store
+            if (tn != old.x || wn != old.y) rowp[x] = make_float2(tn, wn);
         }
     }
     if (COUNT_ONLY) {
         for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xffffffffu, local_count, o);
-        if (lane == 0 && local_count) atomicAdd(&st->upd_count, local_count);
+        if (lane == 0 && local_count) atomicAdd(&st->upd_count, (unsigned long long)local_count);
     }
 }
 

@@ -138,10 +138,7 @@ k_sdf(SdfArgs A, HkfDeviceState* st)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int k = warp; k < HKF_SUMS; k += SDF_WARPS) {
-        const float c = second_stage_row(A.partials + (size_t)k * A.ntiles, A.ntiles, lane);
-        if (lane == 0) s_sums[k] = c;
-    }
+    second_stage_all<SDF_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
     __syncthreads();
     if (threadIdx.x < HKF_SUMS) st->sums[threadIdx.x] = s_sums[threadIdx.x];
     if (threadIdx.x == 0) {
