@@ -219,16 +219,30 @@ HKF_HD float hkf_norm6(const float* x)
 }
 
 // One ICP iteration's host part (minimizePointToPlaneErrFunc + vector6ToTransformMatrix + left-multiply)
-// sums27 -> cur <- T_inc * cur.  Returns HKF_SOLVE_*.
-HKF_HD int hkf_icp_update(const float* sums27, float angle_shake, float dist_shake, float* cur)
+// sums27 -> cur <- T_inc * cur.  Returns HKF_SOLVE_*.  Split in two independent halves so that the fused
+// kernel can run the determinant gate on one warp while another one solves (the gate's outcome is only
+// combined at the end): hkf_icp_singular() and hkf_icp_step().
+HKF_HD bool hkf_icp_singular(const float* sums27)
+{
+    float A[36], b[6];
+    hkf_unpack27(sums27, A, b);
+    return (double)hkf_det6(A) < 1E-10;
+}
+
+HKF_HD int hkf_icp_step(const float* sums27, float angle_shake, float dist_shake, float* cur)
 {
     float A[36], b[6], x[6], T[16];
     hkf_unpack27(sums27, A, b);
-    if ((double)hkf_det6(A) < 1E-10) return HKF_SOLVE_SINGULAR;
     hkf_llt_solve6(A, b, x);
     if (!hkf_vector6_to_transform(x, angle_shake, dist_shake, T)) return HKF_SOLVE_SHAKE;
     hkf_mat44_mul(T, cur, cur);
     return HKF_SOLVE_OK;
+}
+
+HKF_HD int hkf_icp_update(const float* sums27, float angle_shake, float dist_shake, float* cur)
+{
+    if (hkf_icp_singular(sums27)) return HKF_SOLVE_SINGULAR;
+    return hkf_icp_step(sums27, angle_shake, dist_shake, cur);
 }
 
 // se(3) exponential map in double (src/utils/eigen_utils.cpp:84-127, ViSP-derived)

@@ -9,17 +9,22 @@
 // block), a second kernel reduces the block partials, then the host blocks on a 27-float D2H copy and
 // solves with Eigen, 19 times per frame.
 //
-// This design: one warp owns one 16x16 pixel tile (the reference's block), a lane owns the 8 pixels
-// tid = lane + 32 j of that tile.  The reference's block reduction adds tid with tid+128, +64, +32 and
-// then folds the remaining 32 values 16/8/4/2/1: in our mapping the first three levels are additions
-// among the 8 values a lane already holds in registers, ((p0+p4)+(p2+p6))+((p1+p5)+(p3+p7)), and the
-// last five are a __shfl_down tree.  No shared memory, no barrier, no atomics on data, and the float
-// sums are BIT-IDENTICAL to the reference's.  The last block to finish (one ticket atomic per block)
-// folds the per-tile partials with the reference's second-stage tree (512-strided sums, then
-// 256/128/64/32 in registers, then shuffles), and thread 0 runs the Cholesky solve, the determinant and
-// shake gates and the pose update from hkf_solver.h.  ICP's working set (<= 20 MB) is L2-resident on
-// B200, so this stage is latency-bound, not HBM-bound: what matters is the number of dependent
-// launches/barriers, which drops from 19 x (2 launches + sync + D2H + host solve) to 19 launches.
+// This design (latency-bound: the <= 20 MB working set is L2-resident on B200, and a frame is a chain of
+// 19 dependent iterations, so what counts is the length of the dependent chain inside one iteration):
+//  * a block owns two of the reference's 16x16 pixel tiles, one thread per pixel.  The pixel's new-frame
+//    vertex/normal are loaded BEFORE the grid dependency wait (programmatic dependent launch: the blocks of
+//    iteration k+1 are already resident and have their coalesced loads in flight while the last block of
+//    iteration k is still solving), then the pose is read, the model maps are gathered and the 7-float
+//    solver row goes to shared memory (7 KB per tile);
+//  * ONE barrier later the 16 warps share the 2 x 27 sums: a lane multiplies r_i r_j for the 8 reference
+//    threads tid = lane + 32 m and folds them ((p0+p4)+(p2+p6))+((p1+p5)+(p3+p7)), i.e. the reference's
+//    tid <-> tid+128, +64, +32 levels, followed by a __shfl_down tree for its 16/8/4/2/1 levels.  No atomics
+//    on data, 1 barrier instead of 108, and the float sums are BIT-IDENTICAL to the reference's;
+//  * the last block to finish (one ticket atomic per block) folds the per-tile partials with the
+//    reference's second-stage tree (512-strided sums, then 256/128/64/32 in registers, then shuffles), all
+//    loads of a row in flight at once, two rows per warp;
+//  * warp 0 then runs the Cholesky solve, the Euler/shake gate and the pose update while warp 1 evaluates
+//    the determinant gate concurrently (hkf_solver.h).
 #include "hkf_internal.cuh"
 #include "hkf_solver.h"
 #include "reduce27.cuh"
@@ -37,117 +42,93 @@ struct IcpArgs {
     float cur[16], last_inv[16];   // only used when !FROM_STATE
 };
 
-// Correspondence + solver row for a batch of NB pixels of one lane, in three phases so that the NB
-// coalesced loads and then the NB gathers are all in flight together (findCorrs +
-// buildPointToPlaneSolverRows; r[.][7] = 0 when there is no correspondence).
-template <int NB>
-__device__ __forceinline__ void icp_rows(const IcpArgs& A, const float* __restrict__ cur, const float* __restrict__ li,
-                                         const int* xs, const int* ys, float (*r)[7])
-{
-    float4 n[NB], v[NB];
-    bool ok[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        ok[b] = !(xs[b] >= A.cols || ys[b] >= A.rows || ys[b] < A.y0 || ys[b] >= A.y1);
-        const size_t idx = ok[b] ? (size_t)ys[b] * A.cols + xs[b] : 0;
-        n[b] = ld_f4(A.new_n + idx);
-        v[b] = ld_f4(A.new_v + idx);
-    }
-    float qx[NB], qy[NB], qz[NB], nix[NB], niy[NB], niz[NB];
-    size_t midx[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        ok[b] = ok[b] && !hkf_is_zero4(n[b]);
-        // v_input_g = cur * v (lead-first), n_input_g = cur * n (lead-second): as contracted in the reference PTX
-        qx[b] = hkf_row4<true>(cur[0], cur[1], cur[2], cur[3], v[b].x, v[b].y, v[b].z, v[b].w);
-        qy[b] = hkf_row4<true>(cur[4], cur[5], cur[6], cur[7], v[b].x, v[b].y, v[b].z, v[b].w);
-        qz[b] = hkf_row4<true>(cur[8], cur[9], cur[10], cur[11], v[b].x, v[b].y, v[b].z, v[b].w);
-        const float qw = hkf_row4<true>(cur[12], cur[13], cur[14], cur[15], v[b].x, v[b].y, v[b].z, v[b].w);
-        nix[b] = hkf_row4<false>(cur[0], cur[1], cur[2], cur[3], n[b].x, n[b].y, n[b].z, n[b].w);
-        niy[b] = hkf_row4<false>(cur[4], cur[5], cur[6], cur[7], n[b].x, n[b].y, n[b].z, n[b].w);
-        niz[b] = hkf_row4<false>(cur[8], cur[9], cur[10], cur[11], n[b].x, n[b].y, n[b].z, n[b].w);
-        // v_cp = last_inv * v_input_g (lead-second); projective association, no z > 0 test
-        const float px = hkf_row4<false>(li[0], li[1], li[2], li[3], qx[b], qy[b], qz[b], qw);
-        const float py = hkf_row4<false>(li[4], li[5], li[6], li[7], qx[b], qy[b], qz[b], qw);
-        const float pz = hkf_row4<false>(li[8], li[9], li[10], li[11], qx[b], qy[b], qz[b], qw);
-        const int u = hkf_round_px(hkf_project1(px, A.fx, pz, A.cx));
-        const int w = hkf_round_px(hkf_project1(py, A.fy, pz, A.cy));
-        ok[b] = ok[b] && !(u < 0 || u >= A.cols || w < 0 || w >= A.rows);
-        midx[b] = ok[b] ? (size_t)w * A.cols + u : 0;
-    }
-    float4 nt[NB], p[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        nt[b] = ld_f4(A.model_n + midx[b]);
-        p[b] = ld_f4(A.model_v + midx[b]);
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        ok[b] = ok[b] && !hkf_is_zero4(nt[b]);
-        const float dx = __fsub_rn(p[b].x, qx[b]), dy = __fsub_rn(p[b].y, qy[b]), dz = __fsub_rn(p[b].z, qz[b]);
-        const float d = __fsqrt_rn(hkf_dot3(dx, dy, dz, dx, dy, dz));
-        const float sx = hkf_det2(nt[b].y, niz[b], nt[b].z, niy[b]);
-        const float sy = hkf_det2(nt[b].z, nix[b], nt[b].x, niz[b]);
-        const float sz = hkf_det2(nt[b].x, niy[b], nt[b].y, nix[b]);
-        const float s = __fsqrt_rn(hkf_dot3(sx, sy, sz, sx, sy, sz));
-        ok[b] = ok[b] && !(d > A.dist_thres || s > A.sin_thres);
-        r[b][0] = ok[b] ? hkf_det2(qy[b], nt[b].z, qz[b], nt[b].y) : 0.f;
-        r[b][1] = ok[b] ? hkf_det2(qz[b], nt[b].x, qx[b], nt[b].z) : 0.f;
-        r[b][2] = ok[b] ? hkf_det2(qx[b], nt[b].y, qy[b], nt[b].x) : 0.f;
-        r[b][3] = ok[b] ? nt[b].x : 0.f;
-        r[b][4] = ok[b] ? nt[b].y : 0.f;
-        r[b][5] = ok[b] ? nt[b].z : 0.f;
-        r[b][6] = ok[b] ? hkf_dot3(nt[b].x, nt[b].y, nt[b].z, dx, dy, dz) : 0.f;
-    }
-}
+#define ICP_TILES 2
+#define ICP_THREADS (ICP_TILES * 256)
+#define ICP_WARPS (ICP_THREADS / 32)
 
-#define ICP_WARPS 8
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <bool FROM_STATE>
-__global__ void __launch_bounds__(ICP_WARPS * 32)
+__global__ void __launch_bounds__(ICP_THREADS, 2)
 k_icp(IcpArgs A, HkfDeviceState* st)
 {
+    __shared__ float s_r[ICP_TILES][7][256];
+    __shared__ float s_m[32];                  // cur | last_inv
     __shared__ float s_sums[HKF_SUMS];
-    __shared__ int s_last;
+    __shared__ int s_flag[4];                  // 0: tracking live, 1: last block, 2: singular, 3: step result
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tl = threadIdx.x >> 8, t = threadIdx.x & 255;
     const long long t0 = clock64();
-    if (FROM_STATE && st->track_status != HKF_TRACK_OK) return;      // a failed iteration ends the frame's tracking
+    pdl_launch_dependents();
 
-    float cur[16], li[16];
+    // ---- independent of the previous iteration: this thread's pixel of the new frame
+    const int tile = blockIdx.x * ICP_TILES + tl;
+    const int bx = tile % A.gx, by = tile / A.gx;
+    const int x = bx * 16 + (t & 15), y = by * 16 + (t >> 4);
+    bool ok = tile < A.ntiles && !(x >= A.cols || y >= A.rows || y < A.y0 || y >= A.y1);
+    const size_t idx = ok ? (size_t)y * A.cols + x : 0;
+    const float4 n = ld_f4(A.new_n + idx);
+    const float4 v = ld_f4(A.new_v + idx);
+
+    // ---- everything below depends on the previous launch (pose, status, ticket, partials)
+    pdl_wait();
     if (FROM_STATE) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { cur[i] = st->cur[i]; li[i] = st->last_inv[i]; }
+        if (threadIdx.x < 32) s_m[threadIdx.x] = __ldcg(threadIdx.x < 16 ? &st->cur[threadIdx.x] : &st->last_inv[threadIdx.x - 16]);
+        if (threadIdx.x == 32) s_flag[0] = (__ldcg(&st->track_status) == HKF_TRACK_OK);
     } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { cur[i] = A.cur[i]; li[i] = A.last_inv[i]; }
+        if (threadIdx.x < 32) s_m[threadIdx.x] = threadIdx.x < 16 ? A.cur[threadIdx.x] : A.last_inv[threadIdx.x - 16];
+        if (threadIdx.x == 32) s_flag[0] = 1;
     }
+    __syncthreads();
+    if (!s_flag[0]) return;                    // a failed iteration ends the frame's tracking
+    const float* cur = s_m; const float* li = s_m + 16;
 
-    const int tile = blockIdx.x * ICP_WARPS + warp;
-    if (tile < A.ntiles) {
-        const int bx = tile % A.gx, by = tile / A.gx;
-        float r[8][7];
-#pragma unroll
-        for (int jb = 0; jb < 8; jb += 4) {
-            int xs[4], ys[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int tid = lane + 32 * (jb + b);
-                xs[b] = bx * 16 + (tid & 15); ys[b] = by * 16 + (tid >> 4);
-            }
-            icp_rows<4>(A, cur, li, xs, ys, &r[jb]);
-        }
-        int shift = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = i; j < 7; ++j) {
-                float p[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) p[k] = __fmul_rn(r[k][i], r[k][j]);
-                const float c = tile_tree(p);
-                if (lane == 0) A.partials[(size_t)shift * A.ntiles + tile] = c;
-                ++shift;
-            }
+    // findCorrs + buildPointToPlaneSolverRows; r = 0 when there is no correspondence
+    ok = ok && !hkf_is_zero4(n);
+    // v_input_g = cur * v (lead-first), n_input_g = cur * n (lead-second): as contracted in the reference PTX
+    const float qx = hkf_row4<true>(cur[0], cur[1], cur[2], cur[3], v.x, v.y, v.z, v.w);
+    const float qy = hkf_row4<true>(cur[4], cur[5], cur[6], cur[7], v.x, v.y, v.z, v.w);
+    const float qz = hkf_row4<true>(cur[8], cur[9], cur[10], cur[11], v.x, v.y, v.z, v.w);
+    const float qw = hkf_row4<true>(cur[12], cur[13], cur[14], cur[15], v.x, v.y, v.z, v.w);
+    const float nix = hkf_row4<false>(cur[0], cur[1], cur[2], cur[3], n.x, n.y, n.z, n.w);
+    const float niy = hkf_row4<false>(cur[4], cur[5], cur[6], cur[7], n.x, n.y, n.z, n.w);
+    const float niz = hkf_row4<false>(cur[8], cur[9], cur[10], cur[11], n.x, n.y, n.z, n.w);
+    // v_cp = last_inv * v_input_g (lead-second); projective association, no z > 0 test
+    const float px = hkf_row4<false>(li[0], li[1], li[2], li[3], qx, qy, qz, qw);
+    const float py = hkf_row4<false>(li[4], li[5], li[6], li[7], qx, qy, qz, qw);
+    const float pz = hkf_row4<false>(li[8], li[9], li[10], li[11], qx, qy, qz, qw);
+    const int u = hkf_round_px(hkf_project1(px, A.fx, pz, A.cx));
+    const int w = hkf_round_px(hkf_project1(py, A.fy, pz, A.cy));
+    ok = ok && !(u < 0 || u >= A.cols || w < 0 || w >= A.rows);
+    const size_t midx = ok ? (size_t)w * A.cols + u : 0;
+    const float4 nt = ld_f4(A.model_n + midx);
+    const float4 p = ld_f4(A.model_v + midx);
+    ok = ok && !hkf_is_zero4(nt);
+    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+    const float d = __fsqrt_rn(hkf_dot3(dx, dy, dz, dx, dy, dz));
+    const float sx = hkf_det2(nt.y, niz, nt.z, niy);
+    const float sy = hkf_det2(nt.z, nix, nt.x, niz);
+    const float sz = hkf_det2(nt.x, niy, nt.y, nix);
+    const float sn = __fsqrt_rn(hkf_dot3(sx, sy, sz, sx, sy, sz));
+    ok = ok && !(d > A.dist_thres || sn > A.sin_thres);
+    s_r[tl][0][t] = ok ? hkf_det2(qy, nt.z, qz, nt.y) : 0.f;
+    s_r[tl][1][t] = ok ? hkf_det2(qz, nt.x, qx, nt.z) : 0.f;
+    s_r[tl][2][t] = ok ? hkf_det2(qx, nt.y, qy, nt.x) : 0.f;
+    s_r[tl][3][t] = ok ? nt.x : 0.f;
+    s_r[tl][4][t] = ok ? nt.y : 0.f;
+    s_r[tl][5][t] = ok ? nt.z : 0.f;
+    s_r[tl][6][t] = ok ? hkf_dot3(nt.x, nt.y, nt.z, dx, dy, dz) : 0.f;
+    __syncthreads();
+
+    // ---- first stage: 2 x 27 (tile, sum) jobs over 16 warps
+#pragma unroll 1
+    for (int job = warp; job < ICP_TILES * HKF_SUMS; job += ICP_WARPS) {
+        const int jt = job / HKF_SUMS, k = job - jt * HKF_SUMS;
+        const int tile2 = blockIdx.x * ICP_TILES + jt;
+        if (tile2 >= A.ntiles) break;
+        const float c = tile_sum_from_rows(s_r[jt], k, lane);
+        if (lane == 0) __stcg(A.partials + (size_t)k * A.ntiles + tile2, c);
     }
 
     // ---- last block folds the partials and (fused mode) advances the pose
@@ -155,38 +136,47 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        const unsigned tk = atomicAdd(&st->ticket, 1u);
+        s_flag[1] = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_flag[1]) return;
     const long long t2 = clock64();
     __threadfence();
     second_stage_all<ICP_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
     __syncthreads();
     const long long t3 = clock64();
-    if (threadIdx.x < HKF_SUMS) st->sums[threadIdx.x] = s_sums[threadIdx.x];
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + HKF_SUMS) st->sums[threadIdx.x - 64] = s_sums[threadIdx.x - 64];
+    if (threadIdx.x == 64) st->ticket = 0;
+    if (!FROM_STATE) {
+        if (threadIdx.x == 0) { st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3; }
+        return;
+    }
+    float c2[16];
+    long long t4 = 0;
     if (threadIdx.x == 0) {
-        st->ticket = 0;
-        if (FROM_STATE) {
-            float c2[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) c2[i] = cur[i];
-            const int rc = hkf_icp_update(s_sums, A.angle_shake, A.dist_shake, c2);
-            if (rc != HKF_SOLVE_OK) {
-                st->track_status = (rc == HKF_SOLVE_SINGULAR) ? HKF_TRACK_SINGULAR : HKF_TRACK_SHAKE;
-            } else {
+        for (int i = 0; i < 16; ++i) c2[i] = cur[i];
+        s_flag[3] = hkf_icp_step(s_sums, A.angle_shake, A.dist_shake, c2);
+        t4 = clock64();
+    } else if (threadIdx.x == 32) {
+        s_flag[2] = hkf_icp_singular(s_sums) ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_flag[2]) st->track_status = HKF_TRACK_SINGULAR;          // det(AtA) < 1e-10 is tested first (CameraPoseFinderICP.cpp:138)
+        else if (s_flag[3] != HKF_SOLVE_OK) st->track_status = HKF_TRACK_SHAKE;
+        else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) st->cur[i] = c2[i];
-                if (A.is_last) {                      // _pose = cur_transform (CameraPoseFinderICP.cpp:84)
-                    float inv[16];
-                    hkf_mat44_inverse(c2, inv);
+            for (int i = 0; i < 16; ++i) st->cur[i] = c2[i];
+            if (A.is_last) {                      // _pose = cur_transform (CameraPoseFinderICP.cpp:84)
+                float inv[16];
+                hkf_mat44_inverse(c2, inv);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { st->pose[i] = c2[i]; st->pose_inv[i] = inv[i]; }
-                }
+                for (int i = 0; i < 16; ++i) { st->pose[i] = c2[i]; st->pose_inv[i] = inv[i]; }
             }
         }
-        st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3;
+        st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3; st->dbg[4] = t4 - t3;
     }
 }
 
@@ -222,7 +212,7 @@ extern "C" int hkf_cal_point_to_plane_err_solver_params(hkf_ctx* c, unsigned lev
     if (cam->cols != c->cols[level] || cam->rows != c->rows[level]) { c->err = "level camera size mismatch"; return HKF_ERR_ARG; }
     IcpArgs A; fill_icp_args(c, (int)level, cam, dist_thres, norm_sin_thres, &A);
     memcpy(A.cur, cur->m, 64); memcpy(A.last_inv, last_inv->m, 64);
-    k_icp<false><<<div_up(A.ntiles, ICP_WARPS), ICP_WARPS * 32, 0, c->stream>>>(A, c->st);
+    k_icp<false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -258,7 +248,15 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
         A.angle_shake = fp->icp_angle_shake; A.dist_shake = fp->icp_dist_shake;
         for (int it = 0; it < iters[l]; ++it) {
             A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
-            k_icp<true><<<div_up(A.ntiles, ICP_WARPS), ICP_WARPS * 32, 0, c->stream>>>(A, c->st);
+            // programmatic dependent launch: the next iteration's blocks become resident and issue their
+            // pose-independent loads while this iteration's last block is still reducing and solving
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(div_up(A.ntiles, ICP_TILES)); cfg.blockDim = dim3(ICP_THREADS); cfg.stream = c->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_icp<true>, A, c->st);
             HKF_LAUNCH_CHECK(c);
         }
     }
