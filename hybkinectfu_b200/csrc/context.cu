@@ -42,7 +42,7 @@ static void free_all(hkf_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
-    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->tris); cudaFree(c->st);
+    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->st);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->depth_mm_pinned) cudaFreeHost(c->depth_mm_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -62,7 +62,7 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     if (!p || !out) return HKF_ERR_ARG;
     *out = nullptr;
     if (p->pyramid_levels < 1 || p->pyramid_levels > HKF_MAX_LEVELS) { g_create_err = "pyramid_levels must be 1..3 (CameraPoseFinderICP::initPoseFinder)"; return HKF_ERR_ARG; }
-    if (p->volume_resolution < 4 || (p->volume_resolution & 1)) { g_create_err = "volume_resolution must be even and >= 4"; return HKF_ERR_ARG; }
+    if (p->volume_resolution < 4 || (p->volume_resolution & 1) || p->volume_resolution > 2048) { g_create_err = "volume_resolution must be even and in 4..2048"; return HKF_ERR_ARG; }
     if (p->depth_camera.cols == 0 || p->depth_camera.rows == 0) { g_create_err = "empty depth camera"; return HKF_ERR_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -112,6 +112,9 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * R * R;
     CREATE_CUDA(cudaMalloc(&c->vol, nvox * sizeof(float2)));
     CREATE_CUDA(cudaMemset(c->vol, 0, nvox * sizeof(float2)));
+    // one work item per 128 voxels of a row at most (integrate.cu)
+    CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)(c->z_hi - c->z_lo) * R * div_up(R, 128) * sizeof(uint2)));
+    c->sm_count = prop.multiProcessorCount;
     if (p->max_triangles) CREATE_CUDA(cudaMalloc(&c->tris, (size_t)p->max_triangles * sizeof(HkfTriangle)));
     CREATE_CUDA(cudaMalloc(&c->st, sizeof(HkfDeviceState)));
     CREATE_CUDA(cudaMemset(c->st, 0, sizeof(HkfDeviceState)));

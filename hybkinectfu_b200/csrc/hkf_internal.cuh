@@ -36,6 +36,7 @@ struct HkfDeviceState {
     unsigned long long upd_count;
     float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
     int   sdf_done;          // SDF tracker: converged flag (|x| < 1e-3)
+    unsigned int_items[2];   // integration work-item counters (double-buffered: one is appended to while the other is cleared)
     long long dbg[8];        // development aid: SM-clock stamps of the last block of a tracking kernel
 };
 
@@ -64,6 +65,9 @@ struct hkf_ctx {
     unsigned max_blocks = 0;
     // volume slab
     float2* vol = nullptr;
+    uint2* int_items = nullptr;        // integration work items (row, 128-voxel segment, interval)
+    int int_parity = 0;
+    int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes
     unsigned own_z0 = 0, own_z1 = 0;   // owned planes
     // marching cubes

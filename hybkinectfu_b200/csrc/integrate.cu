@@ -65,127 +65,233 @@ __device__ __forceinline__ void clip_lin(float& lo, float& hi, float a, float b)
     else if (b < 0.f) { lo = 1.f; hi = 0.f; }
 }
 
-template <bool FROM_STATE, bool COUNT_ONLY>
-__global__ void __launch_bounds__(256)
-k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict__ vol, HkfDeviceState* __restrict__ st)
+// Conservative voxel interval [x_lo, x_hi] of row (y, z) that can possibly be updated: the row is a straight
+// line in camera space, intersected analytically with the view frustum and the frame's depth range.  A superset
+// (1 px / 1 voxel margins); the per-voxel tests that decide an update are the reference's.  Returns false when empty.
+__device__ __forceinline__ bool row_interval(const IntegrateArgs& A, const float* m, float wy, float wz, float dmax,
+                                             int& x_lo, int& x_hi)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp_in_block = threadIdx.x >> 5;
-    const int R = A.R;
-    const int row = blockIdx.x * 8 + warp_in_block;          // row = (z - z_lo) * R + y
-    const int nrows = (A.z_hi - A.z_lo) * R;
-    if (row >= nrows) return;
-
-    float m11, m12, m13, m14, m21, m22, m23, m24, m31, m32, m33, m34;
-    if (FROM_STATE) {
-        if (st->track_status != HKF_TRACK_OK) return;        // "camera lost": no integration (HybKinectfu.cpp:123-147)
-        const float* p = st->pose_inv;                        // inverse of the tracked pose, written by the tracker
-        m11 = p[0]; m12 = p[1]; m13 = p[2]; m14 = p[3];
-        m21 = p[4]; m22 = p[5]; m23 = p[6]; m24 = p[7];
-        m31 = p[8]; m32 = p[9]; m33 = p[10]; m34 = p[11];
-    } else {
-        m11 = A.inv[0]; m12 = A.inv[1]; m13 = A.inv[2]; m14 = A.inv[3];
-        m21 = A.inv[4]; m22 = A.inv[5]; m23 = A.inv[6]; m24 = A.inv[7];
-        m31 = A.inv[8]; m32 = A.inv[9]; m33 = A.inv[10]; m34 = A.inv[11];
-    }
-
-    const int zrel = row / R;
-    const int y = row - zrel * R;
-    const int z = zrel + A.z_lo;
-    const float cell = A.cell;
-    const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
-    const float wz = __fmul_rn(__fadd_rn((float)z, 0.5f), cell);
-    const float ty1 = __fmul_rn(wy, m12), ty2 = __fmul_rn(wy, m22), ty3 = __fmul_rn(wy, m32);
-
-    // ---- conservative x-interval of this row (analytic, lane-uniform) ----
-    const float bx = m12 * wy + m13 * wz + m14;
-    const float by = m22 * wy + m23 * wz + m24;
-    const float bz = m32 * wy + m33 * wz + m34;
-    const float dmax = __uint_as_float(st->dmax_bits);
+    const float bx = m[1] * wy + m[2] * wz + m[3];
+    const float by = m[5] * wy + m[6] * wz + m[7];
+    const float bz = m[9] * wy + m[10] * wz + m[11];
     const float zmax = fminf(dmax, A.maxdist) + A.trunc + 2e-3f;
     const float z_safe = 0.05f;
     // region A: Zc >= z_safe, pixel within [0.5-1, cols-1.5+1] x [0.5-1, rows-1.5+1], Zc <= zmax
     float loA = 0.f, hiA = A.size;
-    clip_lin(loA, hiA, m31, bz - z_safe);
-    clip_lin(loA, hiA, -m31, zmax - bz);
+    clip_lin(loA, hiA, m[8], bz - z_safe);
+    clip_lin(loA, hiA, -m[8], zmax - bz);
     {
         const float pxmin = -0.5f, pxmax = (float)A.cols - 0.5f, pymin = -0.5f, pymax = (float)A.rows - 0.5f;
-        clip_lin(loA, hiA, A.fx * m11 + (A.cx - pxmin) * m31, A.fx * bx + (A.cx - pxmin) * bz);
-        clip_lin(loA, hiA, -(A.fx * m11 + (A.cx - pxmax) * m31), -(A.fx * bx + (A.cx - pxmax) * bz));
-        clip_lin(loA, hiA, A.fy * m21 + (A.cy - pymin) * m31, A.fy * by + (A.cy - pymin) * bz);
-        clip_lin(loA, hiA, -(A.fy * m21 + (A.cy - pymax) * m31), -(A.fy * by + (A.cy - pymax) * bz));
+        clip_lin(loA, hiA, A.fx * m[0] + (A.cx - pxmin) * m[8], A.fx * bx + (A.cx - pxmin) * bz);
+        clip_lin(loA, hiA, -(A.fx * m[0] + (A.cx - pxmax) * m[8]), -(A.fx * bx + (A.cx - pxmax) * bz));
+        clip_lin(loA, hiA, A.fy * m[4] + (A.cy - pymin) * m[8], A.fy * by + (A.cy - pymin) * bz);
+        clip_lin(loA, hiA, -(A.fy * m[4] + (A.cy - pymax) * m[8]), -(A.fy * by + (A.cy - pymax) * bz));
     }
     // region B: -0.01 <= Zc <= z_safe (projection is ill-conditioned there: no pixel culling)
     float loB = 0.f, hiB = A.size;
-    clip_lin(loB, hiB, m31, bz + 0.01f);
-    clip_lin(loB, hiB, -m31, z_safe - bz);
+    clip_lin(loB, hiB, m[8], bz + 0.01f);
+    clip_lin(loB, hiB, -m[8], z_safe - bz);
     float lo, hi;
     const bool hasA = loA <= hiA, hasB = loB <= hiB;
     if (hasA && hasB) { lo = fminf(loA, loB); hi = fmaxf(hiA, hiB); }
     else if (hasA) { lo = loA; hi = hiA; }
     else if (hasB) { lo = loB; hi = hiB; }
-    else return;
-    const float rcell = __fdividef(1.0f, cell);
-    int x_lo = (int)floorf(lo * rcell - 0.5f) - 1;
-    int x_hi = (int)ceilf(hi * rcell - 0.5f) + 1;
-    x_lo = max(x_lo, 0); x_hi = min(x_hi, R - 1);
-    if (x_lo > x_hi) return;
+    else return false;
+    const float rcell = __fdividef(1.0f, A.cell);
+    x_lo = max((int)floorf(lo * rcell - 0.5f) - 1, 0);
+    x_hi = min((int)ceilf(hi * rcell - 0.5f) + 1, A.R - 1);
+    return x_lo <= x_hi;
+}
 
-    float2* rowp = vol + (size_t)row * R;
-    const int cols = A.cols, rows = A.rows;
-    const unsigned ulim = (unsigned)(cols - 2), vlim = (unsigned)(rows - 2);
-    const float ntrunc = -A.trunc;
+#define INT_NC 4                       // 32-voxel chunks a warp has in flight: a work item is 128 voxels of one row
+#define INT_SEG (32 * INT_NC)
+#define INT_THREADS 256
+
+__device__ __forceinline__ void load_pose_inv(const IntegrateArgs& A, const HkfDeviceState* st, bool from_state, float* m)
+{
+    if (from_state) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) m[i] = st->pose_inv[i];   // inverse of the tracked pose, written by the tracker
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) m[i] = A.inv[i];
+    }
+}
+
+// work item: .x = y | zrel << 12 | segment << 24 ; .y = first | last << 8 (voxel offsets inside the 128-voxel
+// segment that can be updated) | chunk mask << 16
+__device__ __forceinline__ uint2 make_item(int y, int zrel, int seg, int lo_rel, int hi_rel)
+{
+    unsigned mask = 0;
+#pragma unroll
+    for (int c = 0; c < INT_NC; ++c) if (hi_rel >= 32 * c && lo_rel <= 32 * c + 31) mask |= 1u << c;
+    return make_uint2((unsigned)y | ((unsigned)zrel << 12) | ((unsigned)seg << 24),
+                      (unsigned)lo_rel | ((unsigned)hi_rel << 8) | (mask << 16));
+}
+
+// Pass 1 (thread per voxel row, ~2 M warp instructions in total): the row's conservative interval, cut into
+// 128-voxel work items and appended to a compact list (one warp-aggregated atomic per 32 rows), so that pass 2
+// is perfectly balanced and never looks at the ~60 % of rows that cannot be touched this frame.
+template <bool FROM_STATE>
+__global__ void __launch_bounds__(256)
+k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, int parity)
+{
+    const int lane = threadIdx.x & 31;
+    const int R = A.R;
+    const int nrows = (A.z_hi - A.z_lo) * R;                  // row = (z - z_lo) * R + y
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->int_items[parity ^ 1] = 0;   // the counter the NEXT call appends to
+    if (FROM_STATE && st->track_status != HKF_TRACK_OK) return;   // "camera lost": no integration (HybKinectfu.cpp:123-147)
+    float m[12];
+    load_pose_inv(A, st, FROM_STATE, m);
+    int x_lo = 1, x_hi = 0, y = 0, zrel = 0;
+    if (row < nrows) {
+        zrel = row / R;
+        y = row - zrel * R;
+        const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), A.cell);
+        const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), A.cell);
+        if (!row_interval(A, m, wy, wz, __uint_as_float(st->dmax_bits), x_lo, x_hi)) { x_lo = 1; x_hi = 0; }
+    }
+    const int seg0 = x_lo / INT_SEG, seg1 = x_hi / INT_SEG;
+    const int n = (x_lo <= x_hi) ? seg1 - seg0 + 1 : 0;
+    int incl = n;                                              // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    unsigned base = 0;
+    if (lane == 31) base = atomicAdd(&st->int_items[parity], (unsigned)total);
+    base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - n);
+    for (int k = 0; k < n; ++k) {
+        const int seg = seg0 + k;
+        items[base + k] = make_item(y, zrel, seg, max(x_lo - seg * INT_SEG, 0), min(x_hi - seg * INT_SEG, INT_SEG - 1));
+    }
+}
+
+// Pass 2: persistent warps stride over the work items; a lane owns voxels x = seg*128 + 32 c + lane, c = 0..3, so
+// every warp load/store instruction moves 256 contiguous bytes and a warp keeps 4 of them in flight.
+template <bool FROM_STATE, bool COUNT_ONLY>
+__global__ void __launch_bounds__(INT_THREADS, 5)
+k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict__ vol, HkfDeviceState* __restrict__ st,
+            const uint2* __restrict__ items, int parity)
+{
+    const int lane = threadIdx.x & 31;
+    const int R = A.R;
+    const unsigned n_items = st->int_items[parity];
+    const unsigned wid = (blockIdx.x * INT_THREADS + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * INT_THREADS) >> 5;
+    if (wid >= n_items) return;
+    float m[12];
+    load_pose_inv(A, st, FROM_STATE, m);
+    const float cell = A.cell;
+    const int cols = A.cols;
+    const unsigned ulim = (unsigned)(A.cols - 2), vlim = (unsigned)(A.rows - 2);
+    const float trunc = A.trunc, ntrunc = -A.trunc;
     const float thr_one = A.trunc * 1.000002f;
-    const float cxh = A.cx + 0.5f, cyh = A.cy + 0.5f;
-    const float MAGIC = 12582912.0f;             // 1.5 * 2^23: float add rounds to the nearest integer, kept in the mantissa
-    const float eps = 0.001953125f;              // 2^-9 px
+    const float MAGIC = 12582912.0f;              // 1.5 * 2^23: adding it leaves the nearest integer in the mantissa
+    const float edge = 0.5f - 0.00048828125f;     // within 2^-11 px of a rounding boundary -> the exact sequence decides
     unsigned local_count = 0;
 
-    const int xs = (x_lo & ~31) + lane;
-    float xf = (float)xs;
-#pragma unroll 2
-    for (int x = xs; x <= x_hi; x += 32, xf += 32.0f) {
-        const float wx = __fmul_rn(__fadd_rn(xf, 0.5f), cell);
-        const float Z = __fadd_rn(__fmaf_rn(wz, m33, __fmaf_rn(wx, m31, ty3)), m34);
-        const float X = __fadd_rn(__fmaf_rn(wz, m13, __fmaf_rn(wx, m11, ty1)), m14);
-        const float Y = __fadd_rn(__fmaf_rn(wz, m23, __fmaf_rn(wx, m21, ty2)), m24);
-        const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
-        bool live = (x < R) && (Z > 0.f);
-        // approximate pixel coordinate + 0.5, its nearest integer and floor without leaving the FMA/ALU pipes
-        const float rz = hkf_rcp_approx(Z);
-        const float fu = __fmaf_rn(ax, rz, cxh), fv = __fmaf_rn(ay, rz, cyh);
-        const float tu = __fadd_rn(fu, MAGIC), tv = __fadd_rn(fv, MAGIC);
-        const float du = __fsub_rn(fu, __fsub_rn(tu, MAGIC)), dv = __fsub_rn(fv, __fsub_rn(tv, MAGIC));
-        int u = __float_as_int(tu) - 0x4B400000 - (du < 0.f ? 1 : 0);
-        int v = __float_as_int(tv) - 0x4B400000 - (dv < 0.f ? 1 : 0);
-        if (live && (fabsf(du) < eps || fabsf(dv) < eps || !(Z >= 0.01f))) {
-            // within 2^-9 px of a rounding boundary (or ill-conditioned): the reference's exact sequence decides
-            u = hkf_round_px(hkf_project1(X, A.fx, Z, A.cx));
-            v = hkf_round_px(hkf_project1(Y, A.fy, Z, A.cy));
+    uint2 it = __ldg(items + wid);
+#pragma unroll 1
+    for (unsigned item = wid; item < n_items; item += nwarps) {
+        const uint2 cur = it;
+        if (item + nwarps < n_items) it = __ldg(items + item + nwarps);      // prefetch the next item
+        const int y = (int)(cur.x & 0xfffu), zrel = (int)((cur.x >> 12) & 0xfffu);
+        const int xb = (int)(cur.x >> 24) * INT_SEG;
+        const int rel = lane - (int)(cur.y & 0xffu);                          // voxel offset relative to the first live one
+        const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
+        const unsigned mask = cur.y >> 16;
+        const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
+        const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
+        const float ty1 = __fmul_rn(wy, m[1]), ty2 = __fmul_rn(wy, m[5]), ty3 = __fmul_rn(wy, m[9]);
+        float2* __restrict__ vp = vol + ((size_t)(zrel * R + y) * R + xb + lane);
+        const float xh = (float)(xb + lane) + 0.5f;             // x + 0.5, exact
+
+        float Z[INT_NC];
+        int idx[INT_NC];
+#pragma unroll
+        for (int c = 0; c < INT_NC; ++c) {
+            idx[c] = -1; Z[c] = 0.f;
+            if (mask & (1u << c)) {                              // warp-uniform
+                const float wx = __fmul_rn(xh + 32.0f * c, cell);
+                Z[c] = __fadd_rn(__fmaf_rn(wz, m[10], __fmaf_rn(wx, m[8], ty3)), m[11]);
+                const float X = __fadd_rn(__fmaf_rn(wz, m[2], __fmaf_rn(wx, m[0], ty1)), m[3]);
+                const float Y = __fadd_rn(__fmaf_rn(wz, m[6], __fmaf_rn(wx, m[4], ty2)), m[7]);
+                const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
+                bool in = ((unsigned)(rel + 32 * c) <= span) && (Z[c] > 0.f);
+                // approximate pixel coordinate (one MUFU.RCP shared by both axes, < 2e-4 px off) and its nearest
+                // integer = floor(p + 0.5), without leaving the FMA/ALU pipes
+                const float rz = hkf_rcp_approx(Z[c]);
+                const float pu = __fmaf_rn(ax, rz, A.cx), pv = __fmaf_rn(ay, rz, A.cy);
+                const float tu = __fadd_rn(pu, MAGIC), tv = __fadd_rn(pv, MAGIC);
+                int iu = __float_as_int(tu) - 0x4B400000;
+                int iv = __float_as_int(tv) - 0x4B400000;
+                const float eu = __fsub_rn(pu, __fsub_rn(tu, MAGIC)), ev = __fsub_rn(pv, __fsub_rn(tv, MAGIC));
+                if (in && !(fmaxf(fabsf(eu), fabsf(ev)) < edge)) {     // NaN-safe; ~0.2 % of voxels
+                    // the reference's exact sequence: mul, div.rn, add, f64 add, cvt.rzi
+                    iu = hkf_round_px(hkf_project1(X, A.fx, Z[c], A.cx));
+                    iv = hkf_round_px(hkf_project1(Y, A.fy, Z[c], A.cy));
+                }
+                in = in && ((unsigned)(iu - 1) < ulim) && ((unsigned)(iv - 1) < vlim);
+                if (in) idx[c] = iv * cols + iu;
+            }
         }
-        live = live && ((unsigned)(u - 1) < ulim) && ((unsigned)(v - 1) < vlim);
-        float d = 0.f;
-        if (live) d = __ldg(depth + v * cols + u);
-        const float sdf = __fsub_rn(d, Z);
-        live = live && (d != 0.f) && (d < A.maxdist) && (sdf > ntrunc);
+        float d[INT_NC];
+#pragma unroll
+        for (int c = 0; c < INT_NC; ++c) d[c] = (idx[c] >= 0) ? __ldg(depth + idx[c]) : 0.f;
+        float sdf[INT_NC];
+        bool live[INT_NC];
+#pragma unroll
+        for (int c = 0; c < INT_NC; ++c) {
+            sdf[c] = __fsub_rn(d[c], Z[c]);
+            live[c] = (d[c] != 0.f) && (d[c] < A.maxdist) && (sdf[c] > ntrunc);
+        }
         if (COUNT_ONLY) {
-            local_count += live ? 1u : 0u;
-        } else if (live) {
-            const float2 old = rowp[x];
-            // fminf(sdf/trunc, 1): the quotient is >= 1 for sure once sdf >= trunc*(1+2^-19): free space, no division
-            const float tsdf = (sdf >= thr_one) ? 1.0f : fminf(__fdiv_rn(sdf, A.trunc), 1.0f);
-            const float w1 = __fadd_rn(old.y, 1.0f);
-            // fma(1,w,1) == w+1 exactly, so the quotient is exactly 1 when t == tsdf == 1
-            const float tn = (old.x == 1.0f && tsdf == 1.0f) ? 1.0f : __fdiv_rn(__fmaf_rn(old.x, old.y, tsdf), w1);
-            const float wn = fminf(w1, A.wmax);
-            // a voxel whose bits do not change (saturated weight, unchanged tsdf) needs no store
-            if (tn != old.x || wn != old.y) rowp[x] = make_float2(tn, wn);
+#pragma unroll
+            for (int c = 0; c < INT_NC; ++c) local_count += live[c] ? 1u : 0u;
+        } else {
+            float2 old[INT_NC];
+#pragma unroll
+            for (int c = 0; c < INT_NC; ++c) {
+                old[c] = make_float2(0.f, 0.f);
+                if (live[c]) old[c] = vp[32 * c];
+            }
+#pragma unroll
+            for (int c = 0; c < INT_NC; ++c) {
+                const float w1 = __fadd_rn(old[c].y, 1.0f);
+                const float wn = fminf(w1, A.wmax);
+                // Free space seen as free space before: fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19),
+                // and fma(1,w,1)/(w+1) is exactly 1, so t' = 1 without a division.  Everything else (the band around
+                // the surface, first observations) takes the reference's two IEEE divisions.
+                float tn = 1.0f;
+                if (live[c] && !(sdf[c] >= thr_one && old[c].x == 1.0f)) {
+                    const float tsdf = (sdf[c] >= thr_one) ? 1.0f : fminf(__fdiv_rn(sdf[c], trunc), 1.0f);
+                    tn = __fdiv_rn(__fmaf_rn(old[c].x, old[c].y, tsdf), w1);
+                }
+                // a voxel whose bits do not change (saturated weight, unchanged tsdf) needs no store
+                if (live[c] && (tn != old[c].x || wn != old[c].y)) vp[32 * c] = make_float2(tn, wn);
+            }
         }
     }
     if (COUNT_ONLY) {
         for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xffffffffu, local_count, o);
         if (lane == 0 && local_count) atomicAdd(&st->upd_count, (unsigned long long)local_count);
     }
+}
+
+// both passes, on the context's stream
+template <bool FROM_STATE, bool COUNT_ONLY>
+static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
+{
+    const int nrows = (A.z_hi - A.z_lo) * A.R;
+    const int parity = c->int_parity;
+    c->int_parity ^= 1;
+    k_integrate_items<FROM_STATE><<<div_up(nrows, 256), 256, 0, c->stream>>>(A, c->st, c->int_items, parity);
+    HKF_LAUNCH_CHECK(c);
+    k_integrate<FROM_STATE, COUNT_ONLY><<<c->sm_count * 5, INT_THREADS, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st, c->int_items, parity);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
 }
 
 static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* ip, const HkfCameraParams* cam, IntegrateArgs* A)
@@ -212,20 +318,14 @@ extern "C" int hkf_integrate_volume(hkf_ctx* c, int has_color, int use_angle_wei
     float inv[16];
     hkf_mat44_inverse(transform->m, inv);      // host, float cofactors: cudaIntegrateVolume line 84
     IntegrateArgs A; fill_args(c, inv, ip, cam, &A);
-    int nrows = (A.z_hi - A.z_lo) * A.R;
-    k_integrate<false, false><<<div_up(nrows, 8), 256, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st);
-    HKF_LAUNCH_CHECK(c);
-    return HKF_OK;
+    return launch_integrate<false, false>(c, A);
 }
 
 extern "C" int hkf_integrate_tracked(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
     IntegrateArgs A; fill_args(c, nullptr, &fp->integrate, &c->ip.depth_camera, &A);
-    int nrows = (A.z_hi - A.z_lo) * A.R;
-    k_integrate<true, false><<<div_up(nrows, 8), 256, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st);
-    HKF_LAUNCH_CHECK(c);
-    return HKF_OK;
+    return launch_integrate<true, false>(c, A);
 }
 
 extern "C" int hkf_count_integrate_updates(hkf_ctx* c, const HkfMat44* transform, const HkfIntegrateParams* ip,
@@ -238,9 +338,8 @@ extern "C" int hkf_count_integrate_updates(hkf_ctx* c, const HkfMat44* transform
     // count over OWNED planes only
     A.z_lo = (int)c->own_z0; A.z_hi = (int)c->own_z1;
     HKF_CUDA(c, cudaMemsetAsync(&c->st->upd_count, 0, sizeof(unsigned long long), c->stream));
-    int nrows = (A.z_hi - A.z_lo) * A.R;
-    k_integrate<false, true><<<div_up(nrows, 8), 256, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st);
-    HKF_LAUNCH_CHECK(c);
+    int rc = launch_integrate<false, true>(c, A);
+    if (rc != HKF_OK) return rc;
     HKF_CUDA(c, cudaMemcpyAsync(n_upd, &c->st->upd_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     HKF_CUDA(c, cudaStreamSynchronize(c->stream));
     return HKF_OK;
