@@ -21,6 +21,22 @@
 
 struct DMat44 { float m[16]; };
 
+// Depth extrema of the current truncated depth map over pixel tiles of 8 rows x (32 << level) columns,
+// level = 0..3.  One unsigned array: [0] = float bits of the frame's largest valid depth, then per level the
+// largest valid depth of each tile (float bits; 0 = no valid pixel) and the INVERTED bits of the smallest depth
+// with invalid pixels counted as 0 (so that zero-initialised storage + atomicMax implements the minimum).
+// Level 0 tiles are owned by exactly one producer block (plain stores); coarser levels are merged with atomics
+// and therefore cleared before each frame.
+#define HKF_TILE_W 32
+#define HKF_TILE_H 8
+#define HKF_BOUND_LEVELS 4
+struct DepthBounds {
+    unsigned* base;
+    int tiles_y;
+    int tx[HKF_BOUND_LEVELS];
+    int off_max[HKF_BOUND_LEVELS], off_min[HKF_BOUND_LEVELS];
+};
+
 // device-resident per-frame state shared by the fused kernels
 struct HkfDeviceState {
     float pose[16];          // current camera pose (camera -> world)
@@ -55,6 +71,8 @@ struct hkf_ctx {
     float* raw_depth = nullptr;
     float* trunc_depth = nullptr;
     float* filtered_depth = nullptr;
+    DepthBounds bounds{};             // per-tile depth extrema of the current frame (integration chunk classification)
+    size_t bounds_zero_bytes = 0;     // prefix of bounds.base that is cleared before each frame
     float4* new_v[HKF_MAX_LEVELS]{};
     float4* new_n[HKF_MAX_LEVELS]{};
     float4* model_v[HKF_MAX_LEVELS]{};
@@ -105,9 +123,23 @@ static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; 
 // internal cross-file helpers (C++ linkage)
 void hkf_shard_release(hkf_ctx* c);
 int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn);
+int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 
 // ---------------------------------------------------------------- device arithmetic contract
 #ifdef __CUDACC__
+
+// a producer block publishes the extrema (float bits, mn with invalid = 0) of level-0 tile (tx0, ty)
+__device__ __forceinline__ void hkf_bounds_publish(const DepthBounds& B, int tx0, int ty, unsigned mx, unsigned mn)
+{
+    B.base[B.off_max[0] + ty * B.tx[0] + tx0] = mx;
+    B.base[B.off_min[0] + ty * B.tx[0] + tx0] = ~mn;
+#pragma unroll
+    for (int l = 1; l < HKF_BOUND_LEVELS; ++l) {
+        atomicMax(&B.base[B.off_max[l] + ty * B.tx[l] + (tx0 >> l)], mx);
+        atomicMax(&B.base[B.off_min[l] + ty * B.tx[l] + (tx0 >> l)], ~mn);
+    }
+    if (mx) atomicMax(&B.base[0], mx);
+}
 
 // (int)(p + 0.5) as the reference compiles it: the literal 0.5 is a double, so the add is in
 // fp64 and the cast truncates toward zero (src/cuda/DepthCamera.h:39-43;

@@ -53,6 +53,7 @@ struct IntegrateArgs {
     int R;
     int z_lo, z_hi;     // stored planes of this slab
     float size;         // S
+    DepthBounds B;      // depth extrema of this frame per pixel tile (hkf_internal.cuh)
 };
 
 // clip the world-x interval [lo,hi] with a*wx + b >= 0 (approximate division: the caller adds margins)
@@ -119,14 +120,11 @@ __device__ __forceinline__ void load_pose_inv(const IntegrateArgs& A, const HkfD
 }
 
 // work item: .x = y | zrel << 12 | segment << 24 ; .y = first | last << 8 (voxel offsets inside the 128-voxel
-// segment that can be updated) | chunk mask << 16
-__device__ __forceinline__ uint2 make_item(int y, int zrel, int seg, int lo_rel, int hi_rel)
+// segment that can be updated) | mask of chunks to project << 16 | mask of free-space chunks << 20
+__device__ __forceinline__ uint2 make_item(int y, int zrel, int seg, int lo_rel, int hi_rel, unsigned gen, unsigned fre)
 {
-    unsigned mask = 0;
-#pragma unroll
-    for (int c = 0; c < INT_NC; ++c) if (hi_rel >= 32 * c && lo_rel <= 32 * c + 31) mask |= 1u << c;
     return make_uint2((unsigned)y | ((unsigned)zrel << 12) | ((unsigned)seg << 24),
-                      (unsigned)lo_rel | ((unsigned)hi_rel << 8) | (mask << 16));
+                      (unsigned)lo_rel | ((unsigned)hi_rel << 8) | (gen << 16) | (fre << 20));
 }
 
 // Pass 1 (thread per voxel row, ~2 M warp instructions in total): the row's conservative interval, cut into
@@ -150,10 +148,70 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
         y = row - zrel * R;
         const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), A.cell);
         const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), A.cell);
-        if (!row_interval(A, m, wy, wz, __uint_as_float(st->dmax_bits), x_lo, x_hi)) { x_lo = 1; x_hi = 0; }
+        if (!row_interval(A, m, wy, wz, __uint_as_float(A.B.base[0]), x_lo, x_hi)) { x_lo = 1; x_hi = 0; }
     }
+    // Chunk classification (32 voxels).  A chunk's voxel centres project inside the bounding box of its two end
+    // voxels' projections (a 3D segment projects to a 2D segment while Z > 0); the box, grown by 1.5 px, touches at
+    // most 2 tiles per tile row at the level whose tile width covers it.  From the depth extrema of those tiles:
+    //   dead : the nearest voxel is farther than trunc behind the largest valid depth -> "sdf > -trunc"
+    //          (integrateVolume.cu:64) fails for every voxel, the chunk is dropped;
+    //   free : the box lies in the image interior, every pixel of the tiles is valid and < fMaxIntegrateDist, and
+    //          the farthest voxel is more than trunc in front of the smallest depth -> every voxel is updated with
+    //          tsdf = fminf(sdf/trunc, 1) = 1 exactly, so pass 2 needs no projection and no depth read for it;
+    //   else : general, decided voxel by voxel in pass 2.
+    unsigned long long gen_chunks = 0, free_chunks = 0;       // bit k: chunk k of this row (R <= 2048 -> <= 64 chunks)
+    if (x_lo <= x_hi) {
+        const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), A.cell);
+        const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), A.cell);
+        const float X0 = m[1] * wy + m[2] * wz + m[3], Y0 = m[5] * wy + m[6] * wz + m[7], Z0 = m[9] * wy + m[10] * wz + m[11];
+        const float thr_free = A.trunc * 1.000002f + 2e-4f, thr_dead = A.trunc + 2e-4f;
+        auto project = [&](int x, float& u, float& v, float& z) {
+            const float wx = ((float)x + 0.5f) * A.cell;
+            z = m[8] * wx + Z0;
+            const float rz = __fdividef(1.0f, z);
+            u = A.fx * (m[0] * wx + X0) * rz + A.cx;
+            v = A.fy * (m[4] * wx + Y0) * rz + A.cy;
+        };
+        float ua, va, za;
+        project(x_lo, ua, va, za);
+        for (int k = x_lo >> 5; k <= (x_hi >> 5); ++k) {
+            float ub, vb, zb;
+            project(min(x_hi, 32 * k + 31), ub, vb, zb);
+            int cls = 1;                                      // 0 dead, 1 general, 2 free
+            if (za >= 0.05f && zb >= 0.05f) {
+                const float u0 = fminf(ua, ub) - 1.5f, u1 = fmaxf(ua, ub) + 1.5f;
+                const float v0 = fminf(va, vb) - 1.5f, v1 = fmaxf(va, vb) + 1.5f;
+                const float w = u1 - u0;
+                const int lvl = w <= (float)HKF_TILE_W ? 0 : w <= 2.f * HKF_TILE_W ? 1 : w <= 4.f * HKF_TILE_W ? 2 : w <= 8.f * HKF_TILE_W ? 3 : -1;
+                const int ty0 = max((int)floorf(v0 * (1.0f / HKF_TILE_H)), 0);
+                const int ty1 = min((int)floorf(v1 * (1.0f / HKF_TILE_H)), A.B.tiles_y - 1);
+                if (lvl >= 0 && ty1 - ty0 <= 2) {
+                    const float inv_w = 1.0f / (float)(HKF_TILE_W << lvl);
+                    const int tx0 = max((int)floorf(u0 * inv_w), 0);
+                    const int tx1 = min((int)floorf(u1 * inv_w), A.B.tx[lvl] - 1);
+                    unsigned mx = 0, mninv = 0;
+                    for (int ty = ty0; ty <= ty1; ++ty)
+                        for (int tx = tx0; tx <= tx1; ++tx) {
+                            mx = max(mx, __ldg(A.B.base + A.B.off_max[lvl] + ty * A.B.tx[lvl] + tx));
+                            mninv = max(mninv, __ldg(A.B.base + A.B.off_min[lvl] + ty * A.B.tx[lvl] + tx));
+                        }
+                    const float dmx = __uint_as_float(mx), dmn = __uint_as_float(~mninv);   // NaN if no tile was read
+                    const bool interior = u0 >= 1.0f && u1 <= (float)(A.cols - 2) && v0 >= 1.0f && v1 <= (float)(A.rows - 2);
+                    if (fminf(za, zb) >= dmx + thr_dead) cls = 0;
+                    else if (interior && dmn > 0.f && dmx < A.maxdist && dmn - fmaxf(za, zb) >= thr_free) cls = 2;
+                }
+            }
+            if (cls == 1) gen_chunks |= 1ull << k;
+            if (cls == 2) free_chunks |= 1ull << k;
+            ua = ub; va = vb; za = zb;   // the next chunk starts one voxel after this end: [this end, next end] is a superset
+        }
+    }
+    const unsigned long long live_chunks = gen_chunks | free_chunks;
     const int seg0 = x_lo / INT_SEG, seg1 = x_hi / INT_SEG;
-    const int n = (x_lo <= x_hi) ? seg1 - seg0 + 1 : 0;
+    const unsigned segmask = (1u << INT_NC) - 1;
+    int n = 0;
+    if (x_lo <= x_hi)
+        for (int seg = seg0; seg <= seg1; ++seg) n += ((live_chunks >> (seg * INT_NC)) & segmask) ? 1 : 0;
     int incl = n;                                              // inclusive warp scan
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -162,9 +220,11 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
     unsigned base = 0;
     if (lane == 31) base = atomicAdd(&st->int_items[parity], (unsigned)total);
     base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - n);
-    for (int k = 0; k < n; ++k) {
-        const int seg = seg0 + k;
-        items[base + k] = make_item(y, zrel, seg, max(x_lo - seg * INT_SEG, 0), min(x_hi - seg * INT_SEG, INT_SEG - 1));
+    if (n) {
+        for (int seg = seg0; seg <= seg1; ++seg) {
+            const unsigned g = (unsigned)(gen_chunks >> (seg * INT_NC)) & segmask, f = (unsigned)(free_chunks >> (seg * INT_NC)) & segmask;
+            if (g | f) items[base++] = make_item(y, zrel, seg, max(x_lo - seg * INT_SEG, 0), min(x_hi - seg * INT_SEG, INT_SEG - 1), g, f);
+        }
     }
 }
 
@@ -201,7 +261,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
         const int xb = (int)(cur.x >> 24) * INT_SEG;
         const int rel = lane - (int)(cur.y & 0xffu);                          // voxel offset relative to the first live one
         const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
-        const unsigned mask = cur.y >> 16;
+        const unsigned gen = (cur.y >> 16) & 15u, fre = (cur.y >> 20) & 15u;
         const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
         const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
         const float ty1 = __fmul_rn(wy, m[1]), ty2 = __fmul_rn(wy, m[5]), ty3 = __fmul_rn(wy, m[9]);
@@ -213,7 +273,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
 #pragma unroll
         for (int c = 0; c < INT_NC; ++c) {
             idx[c] = -1; Z[c] = 0.f;
-            if (mask & (1u << c)) {                              // warp-uniform
+            if (gen & (1u << c)) {                               // warp-uniform
                 const float wx = __fmul_rn(xh + 32.0f * c, cell);
                 Z[c] = __fadd_rn(__fmaf_rn(wz, m[10], __fmaf_rn(wx, m[8], ty3)), m[11]);
                 const float X = __fadd_rn(__fmaf_rn(wz, m[2], __fmaf_rn(wx, m[0], ty1)), m[3]);
@@ -246,6 +306,10 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
         for (int c = 0; c < INT_NC; ++c) {
             sdf[c] = __fsub_rn(d[c], Z[c]);
             live[c] = (d[c] != 0.f) && (d[c] < A.maxdist) && (sdf[c] > ntrunc);
+            if (fre & (1u << c)) {                               // warp-uniform: free space for certain (pass 1), tsdf = 1
+                sdf[c] = 1e30f;
+                live[c] = (unsigned)(rel + 32 * c) <= span;
+            }
         }
         if (COUNT_ONLY) {
 #pragma unroll
@@ -306,6 +370,7 @@ static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* 
     A->R = (int)c->ip.volume_resolution;
     A->z_lo = (int)c->z_lo; A->z_hi = (int)c->z_hi;
     A->size = c->ip.volume_size;
+    A->B = c->bounds;
 }
 
 extern "C" int hkf_integrate_volume(hkf_ctx* c, int has_color, int use_angle_weight_color, const HkfMat44* transform,

@@ -115,15 +115,10 @@ __global__ void k_decode_mm(const uint16_t* __restrict__ mm, float* __restrict__
     if (i < n) raw[i] = decode_mm(mm[i]);
 }
 
-__global__ void k_trunc(const float* __restrict__ raw, float* __restrict__ out, unsigned n, float tmin, float tmax,
-                        unsigned* __restrict__ dmax_bits)
+__global__ void k_trunc(const float* __restrict__ raw, float* __restrict__ out, unsigned n, float tmin, float tmax)
 {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    float d = 0.f;
-    if (i < n) { d = trunc_depth(raw[i], tmin, tmax); out[i] = d; }
-    unsigned b = __float_as_uint(d);
-    b = __reduce_max_sync(0xffffffffu, b);
-    if ((threadIdx.x & 31) == 0 && b) atomicMax(dmax_bits, b);
+    if (i < n) out[i] = trunc_depth(raw[i], tmin, tmax);
 }
 
 __global__ void k_bilateral(const float* __restrict__ in, float* __restrict__ out, int cols, int rows, int radius,
@@ -178,9 +173,10 @@ __global__ void __launch_bounds__(TILE_W * TILE_H)
 k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, float* __restrict__ trunc_out,
                    float* __restrict__ filt_out, float4* __restrict__ v_out, float4* __restrict__ n_out,
                    int cols, int rows, int radius, float tmin, float tmax, float ss, float sd, float thresh,
-                   float cx, float cy, float fx, float fy, unsigned* __restrict__ dmax_bits)
+                   float cx, float cy, float fx, float fy, DepthBounds B)
 {
     extern __shared__ float smem[];
+    __shared__ unsigned s_tmax[TILE_W * TILE_H / 32], s_tmin[TILE_W * TILE_H / 32];
     const int ap = radius + 1;
     const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
     const int fw = TILE_W + 2, fh = TILE_H + 2;
@@ -189,7 +185,7 @@ k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out,
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
     const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * TILE_H;
 
-    unsigned local_max = 0;
+    unsigned local_max = 0, local_min = 0xffffffffu;
     for (int i = tid; i < tw * th; i += TILE_W * TILE_H) {
         int lx = i % tw, ly = i / tw;
         int gx = bx0 - ap + lx, gy = by0 - ap + ly;
@@ -201,13 +197,21 @@ k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out,
                 raw_out[(size_t)gy * cols + gx] = d;
                 trunc_out[(size_t)gy * cols + gx] = t;
                 local_max = max(local_max, __float_as_uint(t));
+                local_min = min(local_min, __float_as_uint(t));
             }
         }
         s_trunc[i] = t;
     }
+    // this block's tile is exactly one level-0 tile of the integration pass's depth bounds
     local_max = __reduce_max_sync(0xffffffffu, local_max);
-    if ((tid & 31) == 0 && local_max) atomicMax(dmax_bits, local_max);
+    local_min = __reduce_min_sync(0xffffffffu, local_min);
+    if ((tid & 31) == 0) { s_tmax[tid >> 5] = local_max; s_tmin[tid >> 5] = local_min; }
     __syncthreads();
+    if (tid == 0) {
+        unsigned mx = 0, mn = 0xffffffffu;
+        for (int i = 0; i < TILE_W * TILE_H / 32; ++i) { mx = max(mx, s_tmax[i]); mn = min(mn, s_tmin[i]); }
+        hkf_bounds_publish(B, blockIdx.x, blockIdx.y, mx, mn);
+    }
 
     auto at = [&](int gx, int gy) { return s_trunc[(gy - by0 + ap) * tw + (gx - bx0 + ap)]; };
     for (int i = tid; i < fw * fh; i += TILE_W * TILE_H) {
@@ -305,10 +309,9 @@ extern "C" int hkf_trunc_depth(hkf_ctx* c, float tmin, float tmax)
 {
     if (!c) return HKF_ERR_ARG;
     unsigned n = c->cols[0] * c->rows[0];
-    HKF_CUDA(c, cudaMemsetAsync(&c->st->dmax_bits, 0, sizeof(unsigned), c->stream));
-    k_trunc<<<div_up(n, 256), 256, 0, c->stream>>>(c->raw_depth, c->trunc_depth, n, tmin, tmax, &c->st->dmax_bits);
+    k_trunc<<<div_up(n, 256), 256, 0, c->stream>>>(c->raw_depth, c->trunc_depth, n, tmin, tmax);
     HKF_LAUNCH_CHECK(c);
-    return HKF_OK;
+    return hkf_depth_bounds(c);
 }
 
 extern "C" int hkf_bilateral_filter_depth(hkf_ctx* c, float sigma_pixel, float sigma_depth)
@@ -380,14 +383,15 @@ extern "C" int hkf_preprocess(hkf_ctx* c, const uint16_t* depth_mm, int is_devic
     int radius; float ss, sd, thresh;
     bilateral_consts(fp->sigma_pixel, fp->sigma_depth, &radius, &ss, &sd, &thresh);
     if (radius < 0 || radius > 12) { c->err = "hkf_preprocess: bilateral radius out of range for the fused kernel"; return HKF_ERR_ARG; }
-    HKF_CUDA(c, cudaMemsetAsync(&c->st->dmax_bits, 0, sizeof(unsigned), c->stream));
+    HKF_CUDA(c, cudaMemsetAsync(c->bounds.base, 0, c->bounds_zero_bytes, c->stream));
+    static_assert(TILE_W == HKF_TILE_W && TILE_H == HKF_TILE_H, "preprocess tile = integration culling tile");
     const int ap = radius + 1;
     size_t smem = ((TILE_W + 2 * ap) * (TILE_H + 2 * ap) + (TILE_W + 2) * (TILE_H + 2)) * sizeof(float);
     dim3 b(TILE_W, TILE_H), g(div_up(c->cols[0], TILE_W), div_up(c->rows[0], TILE_H));
     const HkfCameraParams& cam = c->ip.depth_camera;
     k_preprocess_fused<<<g, b, smem, c->stream>>>(src, c->raw_depth, c->trunc_depth, c->filtered_depth, c->new_v[0], c->new_n[0],
                                                   (int)c->cols[0], (int)c->rows[0], radius, fp->trunc_min, fp->trunc_max, ss, sd, thresh,
-                                                  cam.cx, cam.cy, cam.fx, cam.fy, &c->st->dmax_bits);
+                                                  cam.cx, cam.cy, cam.fx, cam.fy, c->bounds);
     HKF_LAUNCH_CHECK(c);
     return hkf_pyramids_fused(c, c->new_v, c->new_n);
 }
