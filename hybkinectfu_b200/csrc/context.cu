@@ -83,7 +83,7 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     if (!p || !out) return HKF_ERR_ARG;
     *out = nullptr;
     if (p->pyramid_levels < 1 || p->pyramid_levels > HKF_MAX_LEVELS) { g_create_err = "pyramid_levels must be 1..3 (CameraPoseFinderICP::initPoseFinder)"; return HKF_ERR_ARG; }
-    if (p->volume_resolution < 4 || (p->volume_resolution & 1) || p->volume_resolution > 2048) { g_create_err = "volume_resolution must be even and in 4..2048"; return HKF_ERR_ARG; }
+    if (p->volume_resolution < 4 || (p->volume_resolution & 3) || p->volume_resolution > 2048) { g_create_err = "volume_resolution must be a multiple of 4 in 4..2048"; return HKF_ERR_ARG; }
     if (p->depth_camera.cols == 0 || p->depth_camera.rows == 0) { g_create_err = "empty depth camera"; return HKF_ERR_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -146,8 +146,9 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * R * R;
     CREATE_CUDA(cudaMalloc(&c->vol, nvox * sizeof(float2)));
     CREATE_CUDA(cudaMemset(c->vol, 0, nvox * sizeof(float2)));
-    // one work item per 128 voxels of a row at most (integrate.cu)
-    CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)(c->z_hi - c->z_lo) * R * div_up(R, 128) * sizeof(uint2)));
+    // one work item per 4 x 128 voxel brick at most (integrate.cu)
+    c->int_capacity = (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
+    CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint2)));
     c->sm_count = prop.multiProcessorCount;
     if (p->max_triangles) CREATE_CUDA(cudaMalloc(&c->tris, (size_t)p->max_triangles * sizeof(HkfTriangle)));
     CREATE_CUDA(cudaMalloc(&c->st, sizeof(HkfDeviceState)));

@@ -52,7 +52,7 @@ struct HkfDeviceState {
     unsigned long long upd_count;
     float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
     int   sdf_done;          // SDF tracker: converged flag (|x| < 1e-3)
-    unsigned int_items[2];   // integration work-item counters (double-buffered: one is appended to while the other is cleared)
+    unsigned int_items[4];   // integration work-item counters [parity][free, general] (double-buffered: one pair is appended to while the other is cleared)
     long long dbg[8];        // development aid: SM-clock stamps of the last block of a tracking kernel
 };
 
@@ -84,6 +84,7 @@ struct hkf_ctx {
     // volume slab
     float2* vol = nullptr;
     uint2* int_items = nullptr;        // integration work items (row, 128-voxel segment, interval)
+    unsigned int_capacity = 0;
     int int_parity = 0;
     int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes

@@ -56,42 +56,50 @@ struct IntegrateArgs {
     DepthBounds B;      // depth extrema of this frame per pixel tile (hkf_internal.cuh)
 };
 
-// clip the world-x interval [lo,hi] with a*wx + b >= 0 (approximate division: the caller adds margins)
-__device__ __forceinline__ void clip_lin(float& lo, float& hi, float a, float b)
+#define INT_G 4                        // voxel rows (consecutive y, same z) per work item
+#define INT_NC 4                       // 32-voxel chunks per row of a work item: an item is a 4 x 128 voxel brick
+#define INT_SEG (32 * INT_NC)
+#define INT_THREADS 256
+
+// clip the world-x interval [lo,hi] with a*wx + b(row) >= 0 for the first and last row of a group: b is linear in
+// the row index, so the bound of every row in between lies between q0 and q1 (approximate divisions: the caller
+// adds margins)
+__device__ __forceinline__ void clip_lin2(float& lo, float& hi, float a, float b0, float b1)
 {
     const float eps = 1e-12f;
-    const float q = __fdividef(-b, a);
-    if (a > eps) lo = fmaxf(lo, q);
-    else if (a < -eps) hi = fminf(hi, q);
-    else if (b < 0.f) { lo = 1.f; hi = 0.f; }
+    const float q0 = __fdividef(-b0, a), q1 = __fdividef(-b1, a);
+    if (a > eps) lo = fmaxf(lo, fminf(q0, q1));
+    else if (a < -eps) hi = fminf(hi, fmaxf(q0, q1));
+    else if (b0 < 0.f && b1 < 0.f) { lo = 1.f; hi = 0.f; }
 }
 
-// Conservative voxel interval [x_lo, x_hi] of row (y, z) that can possibly be updated: the row is a straight
-// line in camera space, intersected analytically with the view frustum and the frame's depth range.  A superset
-// (1 px / 1 voxel margins); the per-voxel tests that decide an update are the reference's.  Returns false when empty.
-__device__ __forceinline__ bool row_interval(const IntegrateArgs& A, const float* m, float wy, float wz, float dmax,
-                                             int& x_lo, int& x_hi)
+// Conservative voxel interval [x_lo, x_hi] that can possibly be updated in ANY of the rows y0..y1 of plane z: a
+// row is a straight line in camera space, intersected analytically with the view frustum and the frame's depth
+// range.  A superset (1 px / 1 voxel margins); the per-voxel tests that decide an update are the reference's.
+__device__ __forceinline__ bool group_interval(const IntegrateArgs& A, const float* m, float wy0, float wy1, float wz, float dmax,
+                                               int& x_lo, int& x_hi)
 {
-    const float bx = m[1] * wy + m[2] * wz + m[3];
-    const float by = m[5] * wy + m[6] * wz + m[7];
-    const float bz = m[9] * wy + m[10] * wz + m[11];
+    const float bx0 = m[1] * wy0 + m[2] * wz + m[3], bx1 = m[1] * wy1 + m[2] * wz + m[3];
+    const float by0 = m[5] * wy0 + m[6] * wz + m[7], by1 = m[5] * wy1 + m[6] * wz + m[7];
+    const float bz0 = m[9] * wy0 + m[10] * wz + m[11], bz1 = m[9] * wy1 + m[10] * wz + m[11];
     const float zmax = fminf(dmax, A.maxdist) + A.trunc + 2e-3f;
     const float z_safe = 0.05f;
     // region A: Zc >= z_safe, pixel within [0.5-1, cols-1.5+1] x [0.5-1, rows-1.5+1], Zc <= zmax
     float loA = 0.f, hiA = A.size;
-    clip_lin(loA, hiA, m[8], bz - z_safe);
-    clip_lin(loA, hiA, -m[8], zmax - bz);
+    clip_lin2(loA, hiA, m[8], bz0 - z_safe, bz1 - z_safe);
+    clip_lin2(loA, hiA, -m[8], zmax - bz0, zmax - bz1);
     {
         const float pxmin = -0.5f, pxmax = (float)A.cols - 0.5f, pymin = -0.5f, pymax = (float)A.rows - 0.5f;
-        clip_lin(loA, hiA, A.fx * m[0] + (A.cx - pxmin) * m[8], A.fx * bx + (A.cx - pxmin) * bz);
-        clip_lin(loA, hiA, -(A.fx * m[0] + (A.cx - pxmax) * m[8]), -(A.fx * bx + (A.cx - pxmax) * bz));
-        clip_lin(loA, hiA, A.fy * m[4] + (A.cy - pymin) * m[8], A.fy * by + (A.cy - pymin) * bz);
-        clip_lin(loA, hiA, -(A.fy * m[4] + (A.cy - pymax) * m[8]), -(A.fy * by + (A.cy - pymax) * bz));
+        const float c0 = A.cx - pxmin, c1 = A.cx - pxmax, c2 = A.cy - pymin, c3 = A.cy - pymax;
+        clip_lin2(loA, hiA, A.fx * m[0] + c0 * m[8], A.fx * bx0 + c0 * bz0, A.fx * bx1 + c0 * bz1);
+        clip_lin2(loA, hiA, -(A.fx * m[0] + c1 * m[8]), -(A.fx * bx0 + c1 * bz0), -(A.fx * bx1 + c1 * bz1));
+        clip_lin2(loA, hiA, A.fy * m[4] + c2 * m[8], A.fy * by0 + c2 * bz0, A.fy * by1 + c2 * bz1);
+        clip_lin2(loA, hiA, -(A.fy * m[4] + c3 * m[8]), -(A.fy * by0 + c3 * bz0), -(A.fy * by1 + c3 * bz1));
     }
     // region B: -0.01 <= Zc <= z_safe (projection is ill-conditioned there: no pixel culling)
     float loB = 0.f, hiB = A.size;
-    clip_lin(loB, hiB, m[8], bz + 0.01f);
-    clip_lin(loB, hiB, -m[8], z_safe - bz);
+    clip_lin2(loB, hiB, m[8], bz0 + 0.01f, bz1 + 0.01f);
+    clip_lin2(loB, hiB, -m[8], z_safe - bz0, z_safe - bz1);
     float lo, hi;
     const bool hasA = loA <= hiA, hasB = loB <= hiB;
     if (hasA && hasB) { lo = fminf(loA, loB); hi = fmaxf(hiA, hiB); }
@@ -104,10 +112,6 @@ __device__ __forceinline__ bool row_interval(const IntegrateArgs& A, const float
     return x_lo <= x_hi;
 }
 
-#define INT_NC 4                       // 32-voxel chunks a warp has in flight: a work item is 128 voxels of one row
-#define INT_SEG (32 * INT_NC)
-#define INT_THREADS 256
-
 __device__ __forceinline__ void load_pose_inv(const IntegrateArgs& A, const HkfDeviceState* st, bool from_state, float* m)
 {
     if (from_state) {
@@ -119,223 +123,279 @@ __device__ __forceinline__ void load_pose_inv(const IntegrateArgs& A, const HkfD
     }
 }
 
-// work item: .x = y | zrel << 12 | segment << 24 ; .y = first | last << 8 (voxel offsets inside the 128-voxel
+// work item: .x = y/4 | zrel << 10 | segment << 22 ; .y = first | last << 8 (voxel offsets inside the 128-voxel
 // segment that can be updated) | mask of chunks to project << 16 | mask of free-space chunks << 20
-__device__ __forceinline__ uint2 make_item(int y, int zrel, int seg, int lo_rel, int hi_rel, unsigned gen, unsigned fre)
+__device__ __forceinline__ uint2 make_item(int yg, int zrel, int seg, int lo_rel, int hi_rel, unsigned gen, unsigned fre)
 {
-    return make_uint2((unsigned)y | ((unsigned)zrel << 12) | ((unsigned)seg << 24),
+    return make_uint2((unsigned)yg | ((unsigned)zrel << 10) | ((unsigned)seg << 22),
                       (unsigned)lo_rel | ((unsigned)hi_rel << 8) | (gen << 16) | (fre << 20));
 }
 
-// Pass 1 (thread per voxel row, ~2 M warp instructions in total): the row's conservative interval, cut into
-// 128-voxel work items and appended to a compact list (one warp-aggregated atomic per 32 rows), so that pass 2
-// is perfectly balanced and never looks at the ~60 % of rows that cannot be touched this frame.
+// Pass 1 (thread per group of 4 voxel rows): the group's conservative interval, cut into 32-voxel chunks that are
+// classified against the frame's per-tile depth extrema, and the surviving 4 x 128 voxel bricks appended to two
+// compact work lists (one warp-aggregated atomic per list per 32 groups): bricks made of free-space chunks only
+// grow from the front of `items`, bricks with chunks that need projecting grow from the back.
+//
+// Chunk classification.  The voxel centres of a 4-row x 32-voxel chunk form a planar rectangle; while Z > 0 its
+// image is the convex hull of its four projected corners, and depth along it is extremal at a corner.  The
+// bounding box of the corners, grown by 1.5 px, touches at most 2 tiles per tile row at the level whose tile width
+// covers it.  From the depth extrema of those tiles:
+//   dead : the nearest corner is farther than trunc behind the largest valid depth -> "sdf > -trunc"
+//          (integrateVolume.cu:64) fails for every voxel, the chunk is dropped;
+//   free : the box lies in the image interior, every pixel of the tiles is valid and < fMaxIntegrateDist, and the
+//          farthest corner is more than trunc in front of the smallest depth -> every voxel is updated with
+//          tsdf = fminf(sdf/trunc, 1) = 1 exactly, so pass 2 needs neither a projection nor a depth read for it;
+//   else : general, decided voxel by voxel in pass 2 with the reference's arithmetic.
+#define INT_GB 64                      // row groups per block of pass 1
 template <bool FROM_STATE>
 __global__ void __launch_bounds__(256)
-k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, int parity)
+k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity)
 {
+    __shared__ int s_lo[INT_GB], s_hi[INT_GB];
     const int lane = threadIdx.x & 31;
-    const int R = A.R;
-    const int nrows = (A.z_hi - A.z_lo) * R;                  // row = (z - z_lo) * R + y
-    const int row = blockIdx.x * 256 + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->int_items[parity ^ 1] = 0;   // the counter the NEXT call appends to
+    const int RG = A.R / INT_G;
+    const int ngroups = (A.z_hi - A.z_lo) * RG;
+    const int nseg = (A.R + INT_SEG - 1) / INT_SEG;
+    if (blockIdx.x == 0 && threadIdx.x < 2) st->int_items[(parity ^ 1) * 2 + threadIdx.x] = 0;   // the counters the NEXT call appends to
     if (FROM_STATE && st->track_status != HKF_TRACK_OK) return;   // "camera lost": no integration (HybKinectfu.cpp:123-147)
     float m[12];
     load_pose_inv(A, st, FROM_STATE, m);
-    int x_lo = 1, x_hi = 0, y = 0, zrel = 0;
-    if (row < nrows) {
-        zrel = row / R;
-        y = row - zrel * R;
-        const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), A.cell);
-        const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), A.cell);
-        if (!row_interval(A, m, wy, wz, __uint_as_float(A.B.base[0]), x_lo, x_hi)) { x_lo = 1; x_hi = 0; }
-    }
-    // Chunk classification (32 voxels).  A chunk's voxel centres project inside the bounding box of its two end
-    // voxels' projections (a 3D segment projects to a 2D segment while Z > 0); the box, grown by 1.5 px, touches at
-    // most 2 tiles per tile row at the level whose tile width covers it.  From the depth extrema of those tiles:
-    //   dead : the nearest voxel is farther than trunc behind the largest valid depth -> "sdf > -trunc"
-    //          (integrateVolume.cu:64) fails for every voxel, the chunk is dropped;
-    //   free : the box lies in the image interior, every pixel of the tiles is valid and < fMaxIntegrateDist, and
-    //          the farthest voxel is more than trunc in front of the smallest depth -> every voxel is updated with
-    //          tsdf = fminf(sdf/trunc, 1) = 1 exactly, so pass 2 needs no projection and no depth read for it;
-    //   else : general, decided voxel by voxel in pass 2.
-    unsigned long long gen_chunks = 0, free_chunks = 0;       // bit k: chunk k of this row (R <= 2048 -> <= 64 chunks)
-    if (x_lo <= x_hi) {
-        const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), A.cell);
-        const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), A.cell);
-        const float X0 = m[1] * wy + m[2] * wz + m[3], Y0 = m[5] * wy + m[6] * wz + m[7], Z0 = m[9] * wy + m[10] * wz + m[11];
-        const float thr_free = A.trunc * 1.000002f + 2e-4f, thr_dead = A.trunc + 2e-4f;
-        auto project = [&](int x, float& u, float& v, float& z) {
-            const float wx = ((float)x + 0.5f) * A.cell;
-            z = m[8] * wx + Z0;
-            const float rz = __fdividef(1.0f, z);
-            u = A.fx * (m[0] * wx + X0) * rz + A.cx;
-            v = A.fy * (m[4] * wx + Y0) * rz + A.cy;
-        };
-        float ua, va, za;
-        project(x_lo, ua, va, za);
-        for (int k = x_lo >> 5; k <= (x_hi >> 5); ++k) {
-            float ub, vb, zb;
-            project(min(x_hi, 32 * k + 31), ub, vb, zb);
-            int cls = 1;                                      // 0 dead, 1 general, 2 free
-            if (za >= 0.05f && zb >= 0.05f) {
-                const float u0 = fminf(ua, ub) - 1.5f, u1 = fmaxf(ua, ub) + 1.5f;
-                const float v0 = fminf(va, vb) - 1.5f, v1 = fmaxf(va, vb) + 1.5f;
-                const float w = u1 - u0;
-                const int lvl = w <= (float)HKF_TILE_W ? 0 : w <= 2.f * HKF_TILE_W ? 1 : w <= 4.f * HKF_TILE_W ? 2 : w <= 8.f * HKF_TILE_W ? 3 : -1;
-                const int ty0 = max((int)floorf(v0 * (1.0f / HKF_TILE_H)), 0);
-                const int ty1 = min((int)floorf(v1 * (1.0f / HKF_TILE_H)), A.B.tiles_y - 1);
-                if (lvl >= 0 && ty1 - ty0 <= 2) {
-                    const float inv_w = 1.0f / (float)(HKF_TILE_W << lvl);
-                    const int tx0 = max((int)floorf(u0 * inv_w), 0);
-                    const int tx1 = min((int)floorf(u1 * inv_w), A.B.tx[lvl] - 1);
-                    unsigned mx = 0, mninv = 0;
-                    for (int ty = ty0; ty <= ty1; ++ty)
-                        for (int tx = tx0; tx <= tx1; ++tx) {
-                            mx = max(mx, __ldg(A.B.base + A.B.off_max[lvl] + ty * A.B.tx[lvl] + tx));
-                            mninv = max(mninv, __ldg(A.B.base + A.B.off_min[lvl] + ty * A.B.tx[lvl] + tx));
-                        }
-                    const float dmx = __uint_as_float(mx), dmn = __uint_as_float(~mninv);   // NaN if no tile was read
-                    const bool interior = u0 >= 1.0f && u1 <= (float)(A.cols - 2) && v0 >= 1.0f && v1 <= (float)(A.rows - 2);
-                    if (fminf(za, zb) >= dmx + thr_dead) cls = 0;
-                    else if (interior && dmn > 0.f && dmx < A.maxdist && dmn - fmaxf(za, zb) >= thr_free) cls = 2;
-                }
-            }
-            if (cls == 1) gen_chunks |= 1ull << k;
-            if (cls == 2) free_chunks |= 1ull << k;
-            ua = ub; va = vb; za = zb;   // the next chunk starts one voxel after this end: [this end, next end] is a superset
+
+    // ---- phase A: one thread per row group computes the group's interval
+    if (threadIdx.x < INT_GB) {
+        const int g = blockIdx.x * INT_GB + threadIdx.x;
+        int x_lo = 1, x_hi = 0;
+        if (g < ngroups) {
+            const int zrel = g / RG, yg = g - zrel * RG;
+            const float wy0 = ((float)(yg * INT_G) + 0.5f) * A.cell;
+            const float wy1 = ((float)(yg * INT_G + INT_G - 1) + 0.5f) * A.cell;
+            const float wz = ((float)(zrel + A.z_lo) + 0.5f) * A.cell;
+            if (!group_interval(A, m, wy0, wy1, wz, __uint_as_float(A.B.base[0]), x_lo, x_hi)) { x_lo = 1; x_hi = 0; }
         }
+        s_lo[threadIdx.x] = x_lo; s_hi[threadIdx.x] = x_hi;
     }
-    const unsigned long long live_chunks = gen_chunks | free_chunks;
-    const int seg0 = x_lo / INT_SEG, seg1 = x_hi / INT_SEG;
-    const unsigned segmask = (1u << INT_NC) - 1;
-    int n = 0;
-    if (x_lo <= x_hi)
-        for (int seg = seg0; seg <= seg1; ++seg) n += ((live_chunks >> (seg * INT_NC)) & segmask) ? 1 : 0;
-    int incl = n;                                              // inclusive warp scan
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    unsigned base = 0;
-    if (lane == 31) base = atomicAdd(&st->int_items[parity], (unsigned)total);
-    base = __shfl_sync(0xffffffffu, base, 31) + (unsigned)(incl - n);
-    if (n) {
-        for (int seg = seg0; seg <= seg1; ++seg) {
-            const unsigned g = (unsigned)(gen_chunks >> (seg * INT_NC)) & segmask, f = (unsigned)(free_chunks >> (seg * INT_NC)) & segmask;
-            if (g | f) items[base++] = make_item(y, zrel, seg, max(x_lo - seg * INT_SEG, 0), min(x_hi - seg * INT_SEG, INT_SEG - 1), g, f);
+    __syncthreads();
+
+    // ---- phase B: one thread per (row group, 128-voxel segment) classifies the segment's four chunks
+    const float thr_free = A.trunc * 1.000002f + 2e-4f, thr_dead = A.trunc + 2e-4f;
+    for (int p = threadIdx.x; p < INT_GB * nseg; p += 256) {       // uniform trip count
+        const int gl = p / nseg, seg = p - gl * nseg;
+        const int g = blockIdx.x * INT_GB + gl;
+        const int x_lo = s_lo[gl], x_hi = s_hi[gl];
+        const int xa = max(x_lo, seg * INT_SEG), xe = min(x_hi, seg * INT_SEG + INT_SEG - 1);
+        unsigned gm = 0, fm = 0;
+        int zrel = 0, yg = 0;
+        if (xa <= xe) {
+            zrel = g / RG; yg = g - zrel * RG;
+            const float wy0 = ((float)(yg * INT_G) + 0.5f) * A.cell;
+            const float wy1 = ((float)(yg * INT_G + INT_G - 1) + 0.5f) * A.cell;
+            const float wz = ((float)(zrel + A.z_lo) + 0.5f) * A.cell;
+            const float Xa = m[1] * wy0 + m[2] * wz + m[3], Ya = m[5] * wy0 + m[6] * wz + m[7], Za = m[9] * wy0 + m[10] * wz + m[11];
+            const float Xb = m[1] * wy1 + m[2] * wz + m[3], Yb = m[5] * wy1 + m[6] * wz + m[7], Zb = m[9] * wy1 + m[10] * wz + m[11];
+            auto corners = [&](int x, float& u0, float& u1, float& v0, float& v1, float& z0, float& z1) {
+                const float wx = ((float)x + 0.5f) * A.cell;
+                const float za = m[8] * wx + Za, zb = m[8] * wx + Zb;
+                const float ra = __fdividef(1.0f, za), rb = __fdividef(1.0f, zb);
+                const float ua = A.fx * (m[0] * wx + Xa) * ra + A.cx, ub = A.fx * (m[0] * wx + Xb) * rb + A.cx;
+                const float va = A.fy * (m[4] * wx + Ya) * ra + A.cy, vb = A.fy * (m[4] * wx + Yb) * rb + A.cy;
+                u0 = fminf(ua, ub); u1 = fmaxf(ua, ub); v0 = fminf(va, vb); v1 = fmaxf(va, vb); z0 = fminf(za, zb); z1 = fmaxf(za, zb);
+            };
+            float pu0, pu1, pv0, pv1, pz0, pz1;                    // box of the two corners at the current chunk boundary
+            corners(xa, pu0, pu1, pv0, pv1, pz0, pz1);
+#pragma unroll 1
+            for (int c = (xa >> 5) & (INT_NC - 1); c <= ((xe >> 5) & (INT_NC - 1)); ++c) {
+                float qu0, qu1, qv0, qv1, qz0, qz1;
+                corners(min(xe, seg * INT_SEG + 32 * c + 31), qu0, qu1, qv0, qv1, qz0, qz1);
+                int cls = 1;                                      // 0 dead, 1 general, 2 free
+                const float zn = fminf(pz0, qz0), zf = fmaxf(pz1, qz1);
+                if (zn >= 0.05f) {
+                    const float u0 = fminf(pu0, qu0) - 1.5f, u1 = fmaxf(pu1, qu1) + 1.5f;
+                    const float v0 = fminf(pv0, qv0) - 1.5f, v1 = fmaxf(pv1, qv1) + 1.5f;
+                    const float w = u1 - u0;
+                    const int lvl = w <= (float)HKF_TILE_W ? 0 : w <= 2.f * HKF_TILE_W ? 1 : w <= 4.f * HKF_TILE_W ? 2 : w <= 8.f * HKF_TILE_W ? 3 : -1;
+                    const int ty0 = max((int)floorf(v0 * (1.0f / HKF_TILE_H)), 0);
+                    const int ty1 = min((int)floorf(v1 * (1.0f / HKF_TILE_H)), A.B.tiles_y - 1);
+                    if (lvl >= 0 && ty1 - ty0 <= 3) {
+                        const float inv_w = 1.0f / (float)(HKF_TILE_W << lvl);
+                        const int tx0 = max((int)floorf(u0 * inv_w), 0);
+                        const int tx1 = min((int)floorf(u1 * inv_w), A.B.tx[lvl] - 1);
+                        unsigned mx = 0, mninv = 0;
+                        for (int ty = ty0; ty <= ty1; ++ty)
+                            for (int tx = tx0; tx <= tx1; ++tx) {
+                                mx = max(mx, __ldg(A.B.base + A.B.off_max[lvl] + ty * A.B.tx[lvl] + tx));
+                                mninv = max(mninv, __ldg(A.B.base + A.B.off_min[lvl] + ty * A.B.tx[lvl] + tx));
+                            }
+                        const float dmx = __uint_as_float(mx), dmn = __uint_as_float(~mninv);   // NaN if no tile was read
+                        const bool interior = u0 >= 1.0f && u1 <= (float)(A.cols - 2) && v0 >= 1.0f && v1 <= (float)(A.rows - 2);
+                        if (zn >= dmx + thr_dead || dmn >= A.maxdist) cls = 0;     // behind everything / nothing integrable there
+                        else if (interior && dmn > 0.f && dmx < A.maxdist && dmn - zf >= thr_free) cls = 2;
+                    }
+                }
+                if (cls == 1) gm |= 1u << c;
+                if (cls == 2) fm |= 1u << c;
+                // the next chunk starts one voxel after this end: [this end, next end] is a superset
+                pu0 = qu0; pu1 = qu1; pv0 = qv0; pv1 = qv1; pz0 = qz0; pz1 = qz1;
+            }
+        }
+        // bricks made of free-space chunks only grow from the front of `items`, the others from the back
+        const bool isg = gm != 0, isf = !isg && fm != 0;
+        const unsigned bg = __ballot_sync(0xffffffffu, isg), bf = __ballot_sync(0xffffffffu, isf);
+        unsigned baseg = 0, basef = 0;
+        if (lane == 0) {
+            if (bg) baseg = atomicAdd(&st->int_items[parity * 2 + 1], (unsigned)__popc(bg));
+            if (bf) basef = atomicAdd(&st->int_items[parity * 2 + 0], (unsigned)__popc(bf));
+        }
+        baseg = __shfl_sync(0xffffffffu, baseg, 0); basef = __shfl_sync(0xffffffffu, basef, 0);
+        if (isg | isf) {
+            const uint2 it = make_item(yg, zrel, seg, xa - seg * INT_SEG, xe - seg * INT_SEG, gm, fm);
+            const unsigned below = (1u << lane) - 1;
+            if (isg) items[capacity - 1 - (baseg + __popc(bg & below))] = it;
+            else items[basef + __popc(bf & below)] = it;
         }
     }
 }
 
-// Pass 2: persistent warps stride over the work items; a lane owns voxels x = seg*128 + 32 c + lane, c = 0..3, so
-// every warp load/store instruction moves 256 contiguous bytes and a warp keeps 4 of them in flight.
+// t' and w' of one voxel (tsdfvolume::updateVoxel, tsdfVolume.h:57-74, weight 1) with the reference's two IEEE divisions
+// skipped where their result is known: fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19), and
+// fma(1,w,1)/(w+1) is exactly 1.  Stores only when the voxel's bits change (saturated free space needs no store).
+__device__ __forceinline__ void update_voxel(float2* p, const float2 old, float sdf, float trunc, float thr_one, float wmax)
+{
+    const float w1 = __fadd_rn(old.y, 1.0f);
+    const float wn = fminf(w1, wmax);
+    float tn = 1.0f;
+    if (!(sdf >= thr_one && old.x == 1.0f)) {
+        const float tsdf = (sdf >= thr_one) ? 1.0f : fminf(__fdiv_rn(sdf, trunc), 1.0f);
+        tn = __fdiv_rn(__fmaf_rn(old.x, old.y, tsdf), w1);
+    }
+    if (tn != old.x || wn != old.y) *p = make_float2(tn, wn);
+}
+
+// Pass 2: persistent warps stride over the work items; a lane owns voxels x = seg*128 + 32 c + lane of each row, so
+// every warp load/store instruction moves 256 contiguous bytes.
 template <bool FROM_STATE, bool COUNT_ONLY>
-__global__ void __launch_bounds__(INT_THREADS, 5)
+__global__ void __launch_bounds__(INT_THREADS, 4)
 k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict__ vol, HkfDeviceState* __restrict__ st,
-            const uint2* __restrict__ items, int parity)
+            const uint2* __restrict__ items, unsigned capacity, int parity)
 {
     const int lane = threadIdx.x & 31;
     const int R = A.R;
-    const unsigned n_items = st->int_items[parity];
+    const unsigned n_free = st->int_items[parity * 2 + 0], n_gen = st->int_items[parity * 2 + 1];
     const unsigned wid = (blockIdx.x * INT_THREADS + threadIdx.x) >> 5;
     const unsigned nwarps = (gridDim.x * INT_THREADS) >> 5;
-    if (wid >= n_items) return;
-    float m[12];
-    load_pose_inv(A, st, FROM_STATE, m);
     const float cell = A.cell;
-    const int cols = A.cols;
-    const unsigned ulim = (unsigned)(A.cols - 2), vlim = (unsigned)(A.rows - 2);
-    const float trunc = A.trunc, ntrunc = -A.trunc;
-    const float thr_one = A.trunc * 1.000002f;
-    const float MAGIC = 12582912.0f;              // 1.5 * 2^23: adding it leaves the nearest integer in the mantissa
-    const float edge = 0.5f - 0.00048828125f;     // within 2^-11 px of a rounding boundary -> the exact sequence decides
+    const float trunc = A.trunc, thr_one = A.trunc * 1.000002f, wmax = A.wmax;
     unsigned local_count = 0;
 
-    uint2 it = __ldg(items + wid);
+    // ---- bricks with chunks that need projecting (the heavier ones first)
+    if (wid < n_gen) {
+        float m[12];
+        load_pose_inv(A, st, FROM_STATE, m);
+        const int cols = A.cols;
+        const unsigned ulim = (unsigned)(A.cols - 2), vlim = (unsigned)(A.rows - 2);
+        const float ntrunc = -A.trunc;
+        const float MAGIC = 12582912.0f;              // 1.5 * 2^23: adding it leaves the nearest integer in the mantissa
+        const float edge = 0.5f - 0.00048828125f;     // within 2^-11 px of a rounding boundary -> the exact sequence decides
 #pragma unroll 1
-    for (unsigned item = wid; item < n_items; item += nwarps) {
-        const uint2 cur = it;
-        if (item + nwarps < n_items) it = __ldg(items + item + nwarps);      // prefetch the next item
-        const int y = (int)(cur.x & 0xfffu), zrel = (int)((cur.x >> 12) & 0xfffu);
-        const int xb = (int)(cur.x >> 24) * INT_SEG;
-        const int rel = lane - (int)(cur.y & 0xffu);                          // voxel offset relative to the first live one
-        const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
-        const unsigned gen = (cur.y >> 16) & 15u, fre = (cur.y >> 20) & 15u;
-        const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
-        const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
-        const float ty1 = __fmul_rn(wy, m[1]), ty2 = __fmul_rn(wy, m[5]), ty3 = __fmul_rn(wy, m[9]);
-        float2* __restrict__ vp = vol + ((size_t)(zrel * R + y) * R + xb + lane);
-        const float xh = (float)(xb + lane) + 0.5f;             // x + 0.5, exact
-
-        float Z[INT_NC];
-        int idx[INT_NC];
+        for (unsigned item = wid; item < n_gen; item += nwarps) {
+            const uint2 cur = __ldg(items + (capacity - 1 - item));
+            const int y0 = (int)(cur.x & 0x3ffu) * INT_G, zrel = (int)((cur.x >> 10) & 0xfffu);
+            const int xb = (int)(cur.x >> 22) * INT_SEG;
+            const int rel = lane - (int)(cur.y & 0xffu);                          // voxel offset relative to the first live one
+            const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
+            const unsigned gen = (cur.y >> 16) & 15u, fre = (cur.y >> 20) & 15u;
+            const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
+            const float xh = (float)(xb + lane) + 0.5f;             // x + 0.5, exact
+#pragma unroll 1
+            for (int r = 0; r < INT_G; ++r) {
+                const int y = y0 + r;
+                const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
+                const float ty1 = __fmul_rn(wy, m[1]), ty2 = __fmul_rn(wy, m[5]), ty3 = __fmul_rn(wy, m[9]);
+                float2* __restrict__ vp = vol + ((size_t)(zrel * R + y) * R + xb + lane);
+                // The voxels are requested first, for every in-range lane of a live chunk: the DRAM round trip then
+                // overlaps the projection arithmetic and the depth read instead of following them (a few voxels
+                // that turn out not to be updated are read in vain).
+                float2 old[INT_NC];
+                bool inr[INT_NC];
 #pragma unroll
-        for (int c = 0; c < INT_NC; ++c) {
-            idx[c] = -1; Z[c] = 0.f;
-            if (gen & (1u << c)) {                               // warp-uniform
-                const float wx = __fmul_rn(xh + 32.0f * c, cell);
-                Z[c] = __fadd_rn(__fmaf_rn(wz, m[10], __fmaf_rn(wx, m[8], ty3)), m[11]);
-                const float X = __fadd_rn(__fmaf_rn(wz, m[2], __fmaf_rn(wx, m[0], ty1)), m[3]);
-                const float Y = __fadd_rn(__fmaf_rn(wz, m[6], __fmaf_rn(wx, m[4], ty2)), m[7]);
-                const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
-                bool in = ((unsigned)(rel + 32 * c) <= span) && (Z[c] > 0.f);
-                // approximate pixel coordinate (one MUFU.RCP shared by both axes, < 2e-4 px off) and its nearest
-                // integer = floor(p + 0.5), without leaving the FMA/ALU pipes
-                const float rz = hkf_rcp_approx(Z[c]);
-                const float pu = __fmaf_rn(ax, rz, A.cx), pv = __fmaf_rn(ay, rz, A.cy);
-                const float tu = __fadd_rn(pu, MAGIC), tv = __fadd_rn(pv, MAGIC);
-                int iu = __float_as_int(tu) - 0x4B400000;
-                int iv = __float_as_int(tv) - 0x4B400000;
-                const float eu = __fsub_rn(pu, __fsub_rn(tu, MAGIC)), ev = __fsub_rn(pv, __fsub_rn(tv, MAGIC));
-                if (in && !(fmaxf(fabsf(eu), fabsf(ev)) < edge)) {     // NaN-safe; ~0.2 % of voxels
-                    // the reference's exact sequence: mul, div.rn, add, f64 add, cvt.rzi
-                    iu = hkf_round_px(hkf_project1(X, A.fx, Z[c], A.cx));
-                    iv = hkf_round_px(hkf_project1(Y, A.fy, Z[c], A.cy));
+                for (int c = 0; c < INT_NC; ++c) {
+                    inr[c] = ((gen | fre) & (1u << c)) && ((unsigned)(rel + 32 * c) <= span);
+                    old[c] = make_float2(0.f, 0.f);
+                    if (!COUNT_ONLY && inr[c]) old[c] = vp[32 * c];
                 }
-                in = in && ((unsigned)(iu - 1) < ulim) && ((unsigned)(iv - 1) < vlim);
-                if (in) idx[c] = iv * cols + iu;
+                float Z[INT_NC];
+                int idx[INT_NC];
+#pragma unroll
+                for (int c = 0; c < INT_NC; ++c) {
+                    idx[c] = -1; Z[c] = 0.f;
+                    if (gen & (1u << c)) {                               // warp-uniform
+                        const float wx = __fmul_rn(xh + 32.0f * c, cell);
+                        Z[c] = __fadd_rn(__fmaf_rn(wz, m[10], __fmaf_rn(wx, m[8], ty3)), m[11]);
+                        const float X = __fadd_rn(__fmaf_rn(wz, m[2], __fmaf_rn(wx, m[0], ty1)), m[3]);
+                        const float Y = __fadd_rn(__fmaf_rn(wz, m[6], __fmaf_rn(wx, m[4], ty2)), m[7]);
+                        const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
+                        bool in = inr[c] && (Z[c] > 0.f);
+                        // approximate pixel coordinate (one MUFU.RCP shared by both axes, < 2e-4 px off) and its nearest
+                        // integer = floor(p + 0.5), without leaving the FMA/ALU pipes
+                        const float rz = hkf_rcp_approx(Z[c]);
+                        const float pu = __fmaf_rn(ax, rz, A.cx), pv = __fmaf_rn(ay, rz, A.cy);
+                        const float tu = __fadd_rn(pu, MAGIC), tv = __fadd_rn(pv, MAGIC);
+                        int iu = __float_as_int(tu) - 0x4B400000;
+                        int iv = __float_as_int(tv) - 0x4B400000;
+                        const float eu = __fsub_rn(pu, __fsub_rn(tu, MAGIC)), ev = __fsub_rn(pv, __fsub_rn(tv, MAGIC));
+                        if (in && !(fmaxf(fabsf(eu), fabsf(ev)) < edge)) {     // NaN-safe; ~0.2 % of voxels
+                            // the reference's exact sequence: mul, div.rn, add, f64 add, cvt.rzi
+                            iu = hkf_round_px(hkf_project1(X, A.fx, Z[c], A.cx));
+                            iv = hkf_round_px(hkf_project1(Y, A.fy, Z[c], A.cy));
+                        }
+                        in = in && ((unsigned)(iu - 1) < ulim) && ((unsigned)(iv - 1) < vlim);
+                        if (in) idx[c] = iv * cols + iu;
+                    }
+                }
+                float d[INT_NC];
+#pragma unroll
+                for (int c = 0; c < INT_NC; ++c) d[c] = (idx[c] >= 0) ? __ldg(depth + idx[c]) : 0.f;
+#pragma unroll
+                for (int c = 0; c < INT_NC; ++c) {
+                    float sdf = __fsub_rn(d[c], Z[c]);
+                    bool live = (d[c] != 0.f) && (d[c] < A.maxdist) && (sdf > ntrunc);
+                    if (fre & (1u << c)) { sdf = 1e30f; live = inr[c]; }   // warp-uniform: free space for certain (pass 1), tsdf = 1
+                    if (COUNT_ONLY) local_count += live ? 1u : 0u;
+                    else if (live) update_voxel(vp + 32 * c, old[c], sdf, trunc, thr_one, wmax);
+                }
             }
         }
-        float d[INT_NC];
-#pragma unroll
-        for (int c = 0; c < INT_NC; ++c) d[c] = (idx[c] >= 0) ? __ldg(depth + idx[c]) : 0.f;
-        float sdf[INT_NC];
+    }
+
+    // ---- free-space bricks: a pure streaming read-modify-write, 16 x 256 B in flight per warp
+#pragma unroll 1
+    for (unsigned item = wid; item < n_free; item += nwarps) {
+        const uint2 cur = __ldg(items + item);
+        const int y0 = (int)(cur.x & 0x3ffu) * INT_G, zrel = (int)((cur.x >> 10) & 0xfffu);
+        const int xb = (int)(cur.x >> 22) * INT_SEG;
+        const int rel = lane - (int)(cur.y & 0xffu);
+        const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
+        const unsigned fre = (cur.y >> 20) & 15u;
+        float2* __restrict__ vp = vol + ((size_t)(zrel * R + y0) * R + xb + lane);
         bool live[INT_NC];
 #pragma unroll
-        for (int c = 0; c < INT_NC; ++c) {
-            sdf[c] = __fsub_rn(d[c], Z[c]);
-            live[c] = (d[c] != 0.f) && (d[c] < A.maxdist) && (sdf[c] > ntrunc);
-            if (fre & (1u << c)) {                               // warp-uniform: free space for certain (pass 1), tsdf = 1
-                sdf[c] = 1e30f;
-                live[c] = (unsigned)(rel + 32 * c) <= span;
-            }
-        }
+        for (int c = 0; c < INT_NC; ++c) live[c] = (fre & (1u << c)) && ((unsigned)(rel + 32 * c) <= span);
         if (COUNT_ONLY) {
 #pragma unroll
-            for (int c = 0; c < INT_NC; ++c) local_count += live[c] ? 1u : 0u;
+            for (int c = 0; c < INT_NC; ++c) local_count += live[c] ? (unsigned)INT_G : 0u;
         } else {
-            float2 old[INT_NC];
+            float2 old[INT_G][INT_NC];
 #pragma unroll
-            for (int c = 0; c < INT_NC; ++c) {
-                old[c] = make_float2(0.f, 0.f);
-                if (live[c]) old[c] = vp[32 * c];
-            }
+            for (int r = 0; r < INT_G; ++r)
 #pragma unroll
-            for (int c = 0; c < INT_NC; ++c) {
-                const float w1 = __fadd_rn(old[c].y, 1.0f);
-                const float wn = fminf(w1, A.wmax);
-                // Free space seen as free space before: fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19),
-                // and fma(1,w,1)/(w+1) is exactly 1, so t' = 1 without a division.  Everything else (the band around
-                // the surface, first observations) takes the reference's two IEEE divisions.
-                float tn = 1.0f;
-                if (live[c] && !(sdf[c] >= thr_one && old[c].x == 1.0f)) {
-                    const float tsdf = (sdf[c] >= thr_one) ? 1.0f : fminf(__fdiv_rn(sdf[c], trunc), 1.0f);
-                    tn = __fdiv_rn(__fmaf_rn(old[c].x, old[c].y, tsdf), w1);
+                for (int c = 0; c < INT_NC; ++c) {
+                    old[r][c] = make_float2(0.f, 0.f);
+                    if (live[c]) old[r][c] = vp[(size_t)r * R + 32 * c];
                 }
-                // a voxel whose bits do not change (saturated weight, unchanged tsdf) needs no store
-                if (live[c] && (tn != old[c].x || wn != old[c].y)) vp[32 * c] = make_float2(tn, wn);
-            }
+#pragma unroll
+            for (int r = 0; r < INT_G; ++r)
+#pragma unroll
+                for (int c = 0; c < INT_NC; ++c)
+                    if (live[c]) update_voxel(vp + (size_t)r * R + 32 * c, old[r][c], 1e30f, trunc, thr_one, wmax);
         }
     }
     if (COUNT_ONLY) {
@@ -348,12 +408,13 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
 template <bool FROM_STATE, bool COUNT_ONLY>
 static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
 {
-    const int nrows = (A.z_hi - A.z_lo) * A.R;
+    const int ngroups = (A.z_hi - A.z_lo) * (A.R / INT_G);
     const int parity = c->int_parity;
     c->int_parity ^= 1;
-    k_integrate_items<FROM_STATE><<<div_up(nrows, 256), 256, 0, c->stream>>>(A, c->st, c->int_items, parity);
+    k_integrate_items<FROM_STATE><<<div_up(ngroups, INT_GB), 256, 0, c->stream>>>(A, c->st, c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
-    k_integrate<FROM_STATE, COUNT_ONLY><<<c->sm_count * 5, INT_THREADS, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st, c->int_items, parity);
+    k_integrate<FROM_STATE, COUNT_ONLY><<<c->sm_count * 4, INT_THREADS, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st, c->int_items,
+                                                                                       c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
