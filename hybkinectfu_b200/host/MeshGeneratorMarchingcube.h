@@ -1,0 +1,29 @@
+// MeshGeneratorMarchingcube — marching-cubes driver (src/MeshGeneratorMarchingcube.{h,cpp}): generateMesh() launches
+// the extraction with threshold 300*S/R (never binds since |tsdf| <= 1), copyTrianglesToCPU() downloads the soup,
+// saveMesh() turns it into an indexed mesh and writes Wavefront OBJ.  The reference welds vertices closer than 1e-4
+// with mLib's hash grid (order dependent on the nondeterministic triangle order); here the soup is first put in
+// canonical order and vertices are welded exactly (marching cubes emits bit-identical positions for a shared edge),
+// which makes the file a deterministic function of the volume.  saveMesh returns true on success (the reference
+// always returns 0).
+#pragma once
+#include <array>
+#include <vector>
+#include "MeshGenerator.h"
+#include "../../include/hkf.h"
+
+class MeshGeneratorMarchingcube : public MeshGenerator {
+public:
+    void generateMesh() override;
+    bool saveMesh(const std::string& filename) override;
+    unsigned triangleCount() const { return (unsigned)_soup.size(); }
+    size_t vertexCount() const { return _vertices.size(); }
+    size_t faceCount() const { return _faces.size(); }
+    // soup -> canonical indexed mesh (exposed for tests)
+    static void weld(std::vector<HkfTriangle> soup, std::vector<std::array<float, 3>>& vertices, std::vector<std::array<unsigned, 3>>& faces);
+    static bool writeObj(const std::string& filename, const std::vector<std::array<float, 3>>& vertices, const std::vector<std::array<unsigned, 3>>& faces);
+protected:
+    bool copyTrianglesToCPU();
+    std::vector<HkfTriangle> _soup;
+    std::vector<std::array<float, 3>> _vertices;
+    std::vector<std::array<unsigned, 3>> _faces;
+};

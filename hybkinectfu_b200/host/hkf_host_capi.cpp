@@ -1,0 +1,124 @@
+// extern "C" facade over the host classes, for the ctypes-driven tests and tools (tests/test_host_classes.py).
+// Not part of the drop-in boundary (that is include/hkf.h); it only lets Python drive the C++ classes.
+#include <cstring>
+#include <string>
+#include "AppParamsProducer.h"
+#include "CameraPoseFinderFromFile.h"
+#include "CudaDeviceDataMan.h"
+#include "DataSourceProducerSynthetic.h"
+#include "MainController.h"
+#include "TrajectoryRecorder.h"
+
+static std::string g_err;
+
+extern "C" {
+
+const char* hkfhost_last_error() { return g_err.c_str(); }
+
+// ---- parameters
+int hkfhost_read_params(const char* path) { return AppParamsProducer::readParams(path) ? 0 : 1; }
+const char* hkfhost_missing_keys() { static std::string s; s = AppParamsProducer::lastMissingKeys(); return s.c_str(); }
+void hkfhost_get_frame_params(HkfFrameParams* fp, HkfInitParams* ip)
+{
+    if (fp) *fp = AppParams::instance()->frameParams();
+    if (ip) *ip = AppParams::instance()->initParams();
+}
+int hkfhost_switches()
+{
+    const SwitchParams& s = AppParams::instance()->_switch_params;
+    return (s.useRGBData ? 1 : 0) | (s.useTrajFromFile ? 2 : 0) | (s.useSdfTracker ? 4 : 0) | (s.recordTrajectory ? 8 : 0) |
+           (s.useSyntheticData ? 16 : 0) | (s.stepwiseTracking ? 32 : 0);
+}
+
+// ---- synthetic producer (pure host)
+void hkfhost_synth_pose(unsigned i, unsigned n, double phase, double volume_size, double trunc_min, double* out16)
+{
+    DataSourceProducerSynthetic::trajectoryPose(i, n, phase, volume_size, trunc_min, out16);
+}
+void hkfhost_synth_render(const double* pose16, unsigned cols, unsigned rows, float cx, float cy, float fx, float fy, uint16_t* out)
+{
+    CameraParams cam; cam.cols = cols; cam.rows = rows; cam.cx = cx; cam.cy = cy; cam.fx = fx; cam.fy = fy;
+    DataSourceProducerSynthetic::renderDepthMm(pose16, cam, out);
+}
+int hkfhost_write_tum(const char* path, unsigned n, double phase, double volume_size, double trunc_min)
+{
+    return DataSourceProducerSynthetic::writeTumTrajectory(path, n, phase, volume_size, trunc_min) ? 0 : 1;
+}
+
+// ---- trajectory file round trip (pure host): record poses, then replay them through CameraPoseFinderFromFile
+int hkfhost_record_trajectory(const char* path, const float* poses16, const double* timestamps, unsigned n)
+{
+    TrajectoryRecorder rec(path);
+    for (unsigned i = 0; i < n; ++i) {
+        Mat44 m; std::memcpy(m.m, poses16 + 16 * i, 64);
+        if (!rec.recordCameraPose(m, timestamps[i])) return 1;
+    }
+    return 0;
+}
+int hkfhost_replay_trajectory(const char* path, const float* pose0_16, const double* timestamps, unsigned n, float* poses_out16)
+{
+    AppParams::instance()->_io_params.trajReadFilename = path;
+    CameraPoseFinderFromFile f;
+    Mat44 p0; std::memcpy(p0.m, pose0_16, 64);
+    if (!f.init(p0)) { g_err = "cannot open trajectory"; return 1; }
+    ColorFrameData rgb;
+    for (unsigned i = 0; i < n; ++i) {
+        DepthFrameData d(i);
+        uint16_t px = 0;
+        d.setFrameData(&px, 1, 1, timestamps[i]);
+        if (!f.findCameraPose(d, rgb)) { g_err = "no record for timestamp"; return 2; }
+        std::memcpy(poses_out16 + 16 * i, f.getCameraPose().m, 64);
+    }
+    return 0;
+}
+
+// ---- mesh post-processing (pure host)
+int hkfhost_weld(const HkfTriangle* soup, unsigned n, const char* obj_path, unsigned* n_vertices, unsigned* n_faces)
+{
+    std::vector<HkfTriangle> s(soup, soup + n);
+    std::vector<std::array<float, 3>> v;
+    std::vector<std::array<unsigned, 3>> f;
+    MeshGeneratorMarchingcube::weld(s, v, f);
+    if (n_vertices) *n_vertices = (unsigned)v.size();
+    if (n_faces) *n_faces = (unsigned)f.size();
+    if (obj_path && *obj_path) return MeshGeneratorMarchingcube::writeObj(obj_path, v, f) ? 0 : 1;
+    return 0;
+}
+
+// ---- the whole pipeline through MainController / HybKinectfu (needs a B200)
+int hkfhost_init(const char* config_path, int device)
+{
+    if (!MainController::instance()->init(config_path, device)) { g_err = MainController::instance()->lastError(); return 1; }
+    return 0;
+}
+// process one externally supplied frame through HybKinectfu::processNewFrame
+int hkfhost_process(const uint16_t* depth_mm, unsigned cols, unsigned rows, unsigned frame_id, double timestamp, float* pose_out16, int* status)
+{
+    HybKinectfu* k = MainController::instance()->fusioner();
+    if (!k) { g_err = "not initialised"; return 1; }
+    DepthFrameData d(frame_id);
+    ColorFrameData rgb(frame_id);
+    d.setFrameData(depth_mm, (int)cols, (int)rows, timestamp);
+    rgb.setFrameData(nullptr, 0, 0, timestamp);
+    if (!k->processNewFrame(d, rgb)) { g_err = std::string("processNewFrame: ") + hkf_last_error(CudaDeviceDataMan::instance()->ctx()); return 2; }
+    if (pose_out16) std::memcpy(pose_out16, k->cameraPose().m, 64);
+    if (status) *status = k->lastTrackingStatus();
+    return 0;
+}
+// pull `n` frames from the configured data source (MainController::mainLoop)
+int hkfhost_run(unsigned n, int save_mesh) { return MainController::instance()->mainLoop(n, save_mesh != 0, false); }
+int hkfhost_mesh(const char* obj_path, unsigned* n_tri, unsigned* n_vertices, unsigned* n_faces)
+{
+    MeshGeneratorMarchingcube* m = MainController::instance()->meshGenerator();
+    if (!m) return 1;
+    m->generateMesh();
+    if (!m->saveMesh(obj_path)) return 2;
+    if (n_tri) *n_tri = m->triangleCount();
+    if (n_vertices) *n_vertices = (unsigned)m->vertexCount();
+    if (n_faces) *n_faces = (unsigned)m->faceCount();
+    return 0;
+}
+void* hkfhost_ctx() { return CudaDeviceDataMan::instance()->ctx(); }
+void hkfhost_release() { MainController::instance()->release(); }
+
+}  // extern "C"

@@ -96,7 +96,8 @@ enum {
 enum {
     HKF_TRACK_OK = 0,
     HKF_TRACK_SINGULAR = 1, /* det(AtA) < 1e-10, src/CameraPoseFinderICP.cpp:138 */
-    HKF_TRACK_SHAKE = 2     /* "camera shaking detected", src/CameraPoseFinderICP.cpp:104 */
+    HKF_TRACK_SHAKE = 2,    /* "camera shaking detected", src/CameraPoseFinderICP.cpp:104 */
+    HKF_TRACK_NO_POSE = 3   /* CameraPoseFinderFromFile found no record for the frame, src/CameraPoseFinderFromFile.cpp:32-65 */
 };
 
 /* buffers named in src/cuda/CudaDeviceDataMan.h:54-67, in the REFERENCE layouts */

@@ -1,0 +1,287 @@
+"""The retained host classes (hybkinectfu_b200/host: HybKinectfu, CameraPoseFinder{ICP,SDF,FromFile},
+MeshGeneratorMarchingcube, DataSourceProducerSynthetic, TrajectoryRecorder, AppParams / INI) driven through the small
+extern "C" facade of libhkf_host.so.
+
+CPU part: parameter parsing (config.ini keys of the reference), the synthetic producer against synth.py, the
+TUM trajectory write -> nearest-timestamp replay round trip, mesh welding + OBJ.  GPU part: the whole
+HybKinectfu::processNewFrame loop in the three tracker modes against the Python/C-ABI path and the golden
+reference poses, fused and stepwise (reference control flow) modes.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, bits_equal
+from hybkinectfu_b200 import capi, synth
+
+LIB = os.path.join(ROOT, "hybkinectfu_b200", "libhkf_host.so")
+
+
+@pytest.fixture(scope="module")
+def host():
+    lib = C.CDLL(LIB)
+    lib.hkfhost_last_error.restype = C.c_char_p
+    lib.hkfhost_missing_keys.restype = C.c_char_p
+    lib.hkfhost_ctx.restype = C.c_void_p
+    lib.hkfhost_synth_pose.argtypes = [C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.hkfhost_synth_render.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.hkfhost_write_tum.argtypes = [C.c_char_p, C.c_uint, C.c_double, C.c_double, C.c_double]
+    lib.hkfhost_process.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def write_ini(path, cols=192, rows=144, res=128, levels=3, sdf=0, fromfile=0, stepwise=0, record=0, traj_in="", traj_out="", mesh="", frames=200):
+    cam = synth.Camera().scaled(cols, rows)
+    open(path, "w").write(f"""[switch]
+use_color=0
+record_rgbd=0
+read_rgbd_from_rgbddataset=0
+record_trajectory={record}
+read_trajactory_from_file={fromfile}
+color_angle_weight=0
+use_sdf_tracker={sdf}
+use_synthetic_data=1
+stepwise_tracking={stepwise}
+[camera]
+rgb_cols={cols}
+rgb_rows={rows}
+rgb_cx={cam.cx}
+rgb_cy={cam.cy}
+rgb_fx={cam.fx}
+rgb_fy={cam.fy}
+depth_cols={cols}
+depth_rows={rows}
+depth_cx={cam.cx!r}
+depth_cy={cam.cy!r}
+depth_fx={cam.fx!r}
+depth_fy={cam.fy!r}
+[kinectfusion]
+depth_trunc_max=4
+depth_trunc_min=0.3
+filter_sigma_pixel=2
+filter_sigma_depth=0.02
+volume_resolution={res}
+volume_size_meter=2
+volume_max_weight=128
+integrate_sdf_trunc=0.04
+integrate_depth_trunc=2
+raycast_increment_factor=0.8
+[icp]
+icp_pyramid_level={levels}
+icp_thre_dist=0.1
+icp_thre_sin_angle=0.2
+camera_shake_dist=0.4
+camera_shake_angle=0.4
+[sdfTracker]
+max_iter_nums=6
+camera_shake_dist=0.4
+camera_shake_angle=0.4
+[mesh]
+max_triangle_num=400000
+[IO]
+rgbd_record_filename=
+rgbd_source_filename=
+trajectory_record_filename={traj_out}
+trajectory_source_filename={traj_in}
+mesh_filename={mesh}
+[synthetic]
+frames={frames}
+phase=0
+""")
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+def test_params_from_reference_style_ini(host, tmp_path):
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), cols=640, rows=480, res=512)
+    assert host.hkfhost_read_params(str(ini).encode()) == 0
+    fp, ip = capi.FrameParams(), capi.InitParams()
+    host.hkfhost_get_frame_params(C.byref(fp), C.byref(ip))
+    assert (ip.depth_camera.cols, ip.depth_camera.rows, ip.pyramid_levels, ip.volume_resolution) == (640, 480, 3, 512)
+    assert ip.depth_camera.fx == 525.0 and ip.depth_camera.cx == 319.5 and ip.volume_size == 2.0 and ip.weight_max == 128.0
+    # fRayIncrement = raycast_increment_factor * integrate_sdf_trunc as a FLOAT product (src/AppParamsProducer.cpp:113-117)
+    assert np.float32(fp.raycast.fRayIncrement) == np.float32(0.8) * np.float32(0.04)
+    assert (fp.trunc_min, fp.trunc_max, fp.sdf_max_iter) == (np.float32(0.3), 4.0, 6)
+    assert fp.icp_dist_thres == np.float32(0.1) and fp.icp_norm_sin_thres == np.float32(0.2)
+    assert host.hkfhost_switches() & 16 and not host.hkfhost_switches() & 1
+
+
+def test_reference_root_config_ini_quirks(host, tmp_path):
+    """the reference's root config.ini lacks max_iter_nums and would crash its parser; sections must
+    not inherit keys from earlier sections"""
+    ini = tmp_path / "c.ini"
+    ini.write_text("[switch]\nuse_color=0\n[icp]\ncamera_shake_dist=0.25\n[sdfTracker]\ncamera_shake_angle=0.5\n; comment\n# comment\n")
+    assert host.hkfhost_read_params(str(ini).encode()) == 0
+    fp = capi.FrameParams()
+    host.hkfhost_get_frame_params(C.byref(fp), None)
+    assert fp.sdf_max_iter == 6                                  # default kept
+    assert fp.icp_dist_shake == np.float32(0.25)
+    assert fp.sdf_dist_shake != np.float32(0.25)                 # [sdfTracker] did not inherit [icp]'s key
+    assert b"max_iter_nums" in host.hkfhost_missing_keys()
+    assert host.hkfhost_read_params(b"/nonexistent.ini") == 1
+
+
+def test_synthetic_producer_equals_python_synth(host):
+    cam = synth.Camera().scaled(96, 72)
+    for i, phase in ((0, 0.0), (7, 0.0), (33, 0.7)):
+        p = np.zeros(16)
+        host.hkfhost_synth_pose(i, 50, phase, 2.0, 0.3, p.ctypes.data)
+        want = synth.trajectory(50, phase)[i]
+        assert np.abs(p.reshape(4, 4) - want).max() < 1e-12
+        out = np.zeros((72, 96), np.uint16)
+        host.hkfhost_synth_render(want.ctypes.data, 96, 72, cam.cx, cam.cy, cam.fx, cam.fy, out.ctypes.data)
+        ref = synth.render_depth_mm(want, cam)
+        # camera intrinsics cross the facade as float32: allow the last millimetre to differ on a few pixels
+        d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() < 0.01
+    assert np.array_equal(synth.trajectory(50)[0], synth.pose0())
+
+
+def test_trajectory_record_and_replay_round_trip(host, tmp_path):
+    """TrajectoryRecorder -> file -> CameraPoseFinderFromFile: pose_i = (pose0 * file0^-1) * file_i, nearest timestamp"""
+    n = 12
+    poses = synth.trajectory(60)[::5].astype(np.float32)
+    ts = np.arange(n) / 30.0
+    path = str(tmp_path / "traj.txt").encode()
+    assert host.hkfhost_record_trajectory(path, poses.ctypes.data, ts.ctypes.data, n) == 0
+    lines = open(path).read().splitlines()
+    assert lines[0].startswith("#") and lines[2] == "# timestamp tx ty tz qx qy qz qw" and len(lines) == 3 + n
+    assert len(lines[3].split()) == 8
+    out = np.zeros((n, 4, 4), np.float32)
+    query = ts + 0.004 * np.sin(np.arange(n))                   # jittered timestamps still pick the nearest record
+    assert host.hkfhost_replay_trajectory(path, poses[0].ctypes.data, query.ctypes.data, n, out.ctypes.data) == 0
+    assert bits_equal(out[0], poses[0])                          # frame 0 keeps the initial pose
+    assert np.abs(out - poses).max() < 5e-6                      # 6 significant digits in the file
+    # the synthetic ground-truth writer uses 9 decimals
+    gt = str(tmp_path / "gt.txt").encode()
+    assert host.hkfhost_write_tum(gt, 60, 0.0, 2.0, 0.3) == 0
+    ts60 = np.arange(60) / 30.0
+    out60 = np.zeros((60, 4, 4), np.float32)
+    assert host.hkfhost_replay_trajectory(gt, synth.pose0().astype(np.float32).ctypes.data, ts60.ctypes.data, 60, out60.ctypes.data) == 0
+    assert np.abs(out60 - synth.trajectory(60)).max() < 2e-6
+
+
+def test_weld_and_obj(host, tmp_path):
+    # two triangles sharing an edge + one exact duplicate + one degenerate
+    tri = np.zeros((4, 3, 6), np.float32)
+    tri[0, :, :3] = [[0, 0, 0], [1, 0, 0], [0, 1, 0]]
+    tri[1, :, :3] = [[1, 0, 0], [1, 1, 0], [0, 1, 0]]
+    tri[2] = tri[0]
+    tri[3, :, :3] = [[2, 2, 2], [2, 2, 2], [3, 3, 3]]
+    nv, nf = C.c_uint(), C.c_uint()
+    obj = str(tmp_path / "m.obj")
+    assert host.hkfhost_weld(tri.ctypes.data, 4, obj.encode(), C.byref(nv), C.byref(nf)) == 0
+    assert (nv.value, nf.value) == (6, 2)                        # 4 mesh vertices + the 2 of the degenerate triangle
+    txt = open(obj).read().splitlines()
+    assert sum(l.startswith("v ") for l in txt) == 6 and sum(l.startswith("f ") for l in txt) == 2
+    # order independence: shuffling the soup gives the same file
+    obj2 = str(tmp_path / "m2.obj")
+    assert host.hkfhost_weld(np.ascontiguousarray(tri[::-1]).ctypes.data, 4, obj2.encode(), None, None) == 0
+    assert open(obj).read() == open(obj2).read()
+
+
+def test_init_without_gpu_reports_no_fallback(host, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini))
+    assert host.hkfhost_init(str(ini).encode(), 0) == 1
+    assert b"no CPU fallback" in host.hkfhost_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _run_host(host, ini, frames, ts=None):
+    assert host.hkfhost_init(str(ini).encode(), 0) == 0, host.hkfhost_last_error()
+    poses, sts = [], []
+    for i, mm in enumerate(frames):
+        p = np.zeros((4, 4), np.float32)
+        st = C.c_int()
+        mm = np.ascontiguousarray(mm)
+        rc = host.hkfhost_process(mm.ctypes.data, mm.shape[1], mm.shape[0], i, float(i / 30.0 if ts is None else ts[i]), p.ctypes.data, C.byref(st))
+        assert rc == 0, host.hkfhost_last_error()
+        poses.append(p); sts.append(st.value)
+    return np.stack(poses), np.array(sts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sdf", [0, 1])
+def test_hybkinectfu_fused_equals_c_abi_path_and_reference(host, pipeline, tmp_path, sdf):
+    from test_gpu_pipeline import run_fused, pose_err, ROT_TOL, TRANS_TOL
+    from conftest import small_config
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), sdf=sdf, mesh=str(tmp_path / "mesh.obj"))
+    poses, sts = _run_host(host, ini, pipeline["frames"])
+    want, wsts, c = run_fused(small_config(128), pipeline["frames"], sdf)
+    assert (sts == wsts).all() and bits_equal(poses, want)       # the C++ classes add nothing to the arithmetic
+    gold = pipeline["sdf_poses" if sdf else "icp_poses"]
+    rot, trans = pose_err(poses, gold)
+    assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+    # same volume as the python-driven context, and the mesh export works on it
+    h = capi.Context.__new__(capi.Context)
+    vol_host = np.zeros((128, 128, 128, 2), np.float32)
+    lib = capi.load()
+    assert lib.hkf_download(C.c_void_p(host.hkfhost_ctx()), capi.BUF_VOLUME, 0, vol_host.ctypes.data, vol_host.nbytes) == vol_host.nbytes
+    assert bits_equal(vol_host, c.download(capi.BUF_VOLUME))
+    ntri, nv, nf = C.c_uint(), C.c_uint(), C.c_uint()
+    assert host.hkfhost_mesh(str(tmp_path / "mesh.obj").encode(), C.byref(ntri), C.byref(nv), C.byref(nf)) == 0
+    assert ntri.value == c.marching_cubes() and 0 < nv.value < 3 * ntri.value and nf.value <= ntri.value
+    c.close()
+    host.hkfhost_release()
+
+
+@pytest.mark.gpu
+def test_hybkinectfu_stepwise_reference_control_flow(host, pipeline, tmp_path):
+    """per-iteration wrapper calls + host solves (the reference's loop) give the fused path's poses"""
+    from test_gpu_pipeline import pose_err, ROT_TOL, TRANS_TOL
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), stepwise=1)
+    poses, sts = _run_host(host, ini, pipeline["frames"])
+    host.hkfhost_release()
+    assert (sts == pipeline["icp_status"]).all()
+    rot, trans = pose_err(poses, pipeline["icp_poses"])
+    assert rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+    write_ini(str(ini), stepwise=1, sdf=1)
+    poses, sts = _run_host(host, ini, pipeline["frames"])
+    host.hkfhost_release()
+    rot, trans = pose_err(poses, pipeline["sdf_poses"])
+    assert (sts == pipeline["sdf_status"]).all() and rot <= ROT_TOL and trans <= TRANS_TOL, (rot, trans)
+
+
+@pytest.mark.gpu
+def test_hybkinectfu_poses_from_file(host, pipeline, tmp_path):
+    """C1 shape: CameraPoseFinderFromFile replaying the ground-truth trajectory; the volume must equal integration
+    with the very poses the finder produced"""
+    n = len(pipeline["frames"])
+    traj = tmp_path / "gt.txt"
+    synth.write_tum_trajectory(str(traj), pipeline["gt_poses"].astype(np.float64))
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), fromfile=1, traj_in=str(traj), record=1, traj_out=str(tmp_path / "rec.txt"))
+    # the file holds 6-decimal timestamps; a frame stamped later than the last record is "camera lost" in the reference too
+    ts = np.round(np.arange(n) / 30.0, 6)
+    poses, sts = _run_host(host, ini, pipeline["frames"], ts)
+    assert (sts == 0).all()
+    assert np.abs(poses - pipeline["gt_poses"]).max() < 2e-6
+    vol_host = np.zeros((128, 128, 128, 2), np.float32)
+    lib = capi.load()
+    assert lib.hkf_download(C.c_void_p(host.hkfhost_ctx()), capi.BUF_VOLUME, 0, vol_host.ctypes.data, vol_host.nbytes) == vol_host.nbytes
+    host.hkfhost_release()
+    from conftest import small_config
+    from test_gpu_pipeline import run_fused
+    _, _, c = run_fused(small_config(128), pipeline["frames"], 2, poses)
+    assert bits_equal(vol_host, c.download(capi.BUF_VOLUME))
+    c.close()
+    rec = open(tmp_path / "rec.txt").read().splitlines()
+    assert len(rec) == 3 + n
+
+
+@pytest.mark.gpu
+def test_main_controller_loop_with_synthetic_source(host, tmp_path):
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), frames=40, mesh=str(tmp_path / "m.obj"))
+    assert host.hkfhost_init(str(ini).encode(), 0) == 0, host.hkfhost_last_error()
+    assert host.hkfhost_run(6, 1) == 6
+    host.hkfhost_release()
+    assert os.path.getsize(tmp_path / "m.obj") > 1000
