@@ -122,7 +122,7 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
         CREATE_CUDA(cudaMalloc(&B.base, (size_t)off * sizeof(unsigned)));
         CREATE_CUDA(cudaMemset(B.base, 0, (size_t)off * sizeof(unsigned)));
     }
-    CREATE_CUDA(cudaMalloc(&c->ray_keys, n0 * sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMalloc(&c->ray_keys, 2 * n0 * sizeof(unsigned long long)));   // own keys | composited keys
     CREATE_CUDA(cudaMalloc(&c->ray_payload, n0 * 8 * sizeof(float)));
     for (int l = 0; l < c->levels; ++l) {
         size_t nb = (size_t)c->cols[l] * c->rows[l] * sizeof(float4);

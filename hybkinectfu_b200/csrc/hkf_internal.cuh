@@ -123,6 +123,7 @@ static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; 
 
 // internal cross-file helpers (C++ linkage)
 void hkf_shard_release(hkf_ctx* c);
+int hkf_shard_allreduce_sums(hkf_ctx* c);
 int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn);
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 

@@ -49,7 +49,9 @@ struct IcpArgs {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <bool FROM_STATE>
+// FROM_STATE: pose/status from device state; SOLVE: the last block also solves and advances the pose (single GPU).
+// Sharded ranks run <true,false> over their pixel-row band, allreduce st->sums, then k_icp_solve.
+template <bool FROM_STATE, bool SOLVE>
 __global__ void __launch_bounds__(ICP_THREADS, 2)
 k_icp(IcpArgs A, HkfDeviceState* st)
 {
@@ -148,7 +150,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     const long long t3 = clock64();
     if (threadIdx.x >= 64 && threadIdx.x < 64 + HKF_SUMS) st->sums[threadIdx.x - 64] = s_sums[threadIdx.x - 64];
     if (threadIdx.x == 64) st->ticket = 0;
-    if (!FROM_STATE) {
+    if (!SOLVE) {
         if (threadIdx.x == 0) { st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3; }
         return;
     }
@@ -212,7 +214,7 @@ extern "C" int hkf_cal_point_to_plane_err_solver_params(hkf_ctx* c, unsigned lev
     if (cam->cols != c->cols[level] || cam->rows != c->rows[level]) { c->err = "level camera size mismatch"; return HKF_ERR_ARG; }
     IcpArgs A; fill_icp_args(c, (int)level, cam, dist_thres, norm_sin_thres, &A);
     memcpy(A.cur, cur->m, 64); memcpy(A.last_inv, last_inv->m, 64);
-    k_icp<false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+    k_icp<false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -233,6 +235,39 @@ static const int* icp_schedule(int levels)
     return levels == 1 ? s1 : levels == 2 ? s2 : s3;
 }
 
+// sharded mode: the solve of one iteration on the allreduced sums (every rank computes the same bits)
+__global__ void k_icp_solve(HkfDeviceState* st, float angle_shake, float dist_shake, int is_last)
+{
+    __shared__ float s_sums[HKF_SUMS];
+    __shared__ int s_flag[2];
+    if (st->track_status != HKF_TRACK_OK) return;
+    if (threadIdx.x < HKF_SUMS) s_sums[threadIdx.x] = st->sums[threadIdx.x];
+    __syncthreads();
+    float c2[16];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c2[i] = st->cur[i];
+        s_flag[1] = hkf_icp_step(s_sums, angle_shake, dist_shake, c2);
+    } else if (threadIdx.x == 32) {
+        s_flag[0] = hkf_icp_singular(s_sums) ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_flag[0]) st->track_status = HKF_TRACK_SINGULAR;
+        else if (s_flag[1] != HKF_SOLVE_OK) st->track_status = HKF_TRACK_SHAKE;
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) st->cur[i] = c2[i];
+            if (is_last) {
+                float inv[16];
+                hkf_mat44_inverse(c2, inv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { st->pose[i] = c2[i]; st->pose_inv[i] = inv[i]; }
+            }
+        }
+    }
+}
+
 extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
@@ -242,12 +277,26 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
     k_track_begin<<<1, 32, 0, c->stream>>>(c->st);
     HKF_LAUNCH_CHECK(c);
     const int* iters = icp_schedule(c->levels);
+    const bool sharded = c->nranks > 1;
     for (int l = c->levels - 1; l >= 0; --l) {
         HkfCameraParams cam; hkf_level_camera(&c->ip.depth_camera, l, &cam);
         IcpArgs A; fill_icp_args(c, l, &cam, fp->icp_dist_thres, fp->icp_norm_sin_thres, &A);
         A.angle_shake = fp->icp_angle_shake; A.dist_shake = fp->icp_dist_shake;
+        if (sharded) {      // this rank's band of pixel rows
+            A.y0 = (int)((long long)A.rows * c->rank / c->nranks);
+            A.y1 = (int)((long long)A.rows * (c->rank + 1) / c->nranks);
+        }
         for (int it = 0; it < iters[l]; ++it) {
             A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
+            if (sharded) {
+                k_icp<true, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+                HKF_LAUNCH_CHECK(c);
+                rc = hkf_shard_allreduce_sums(c);
+                if (rc != HKF_OK) return rc;
+                k_icp_solve<<<1, 64, 0, c->stream>>>(c->st, A.angle_shake, A.dist_shake, A.is_last);
+                HKF_LAUNCH_CHECK(c);
+                continue;
+            }
             // programmatic dependent launch: the next iteration's blocks become resident and issue their
             // pose-independent loads while this iteration's last block is still reducing and solving
             cudaLaunchConfig_t cfg = {};
@@ -256,7 +305,7 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, k_icp<true>, A, c->st);
+            cudaLaunchKernelEx(&cfg, k_icp<true, true>, A, c->st);
             HKF_LAUNCH_CHECK(c);
         }
     }

@@ -175,5 +175,7 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     if (is_slab(c)) k_raycast<true, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
     else k_raycast<true, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
     HKF_LAUNCH_CHECK(c);
+    // sharded volume: nearest-hit compositing of the per-slab partial raycasts -> full model maps on every rank
+    if (c->nranks > 1) return hkf_shard_composite_raycast(c);
     return HKF_OK;
 }

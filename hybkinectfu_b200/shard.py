@@ -1,0 +1,109 @@
+"""z-slab sharding of one TSDF volume across the GPUs of a box (BASELINE.json configs[3]).
+
+Host-side logic only: how the volume is cut into slabs with halos, which pixel rows of an ICP level a rank
+evaluates, the nearest-hit compositing rule, and the torch.distributed plumbing that distributes the NCCL unique
+id of the C library's own communicator.  The device work is csrc/shard.cu, icp.cu and raycast.cu.
+
+The functions here are backend-agnostic (they are exercised with gloo on CPU in tests/test_shard_cpu.py); the
+only NCCL calls the data path makes are the ones inside libhkf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+
+import numpy as np
+
+NO_HIT = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def halo_planes(ray_increment: float, volume_size: float, resolution: int) -> int:
+    """Planes a slab must replicate per interior side: a crossing is owned by the slab of its LATER sample, its
+    earlier sample lies up to one ray increment before it, the two trilinear refinements reach one more voxel and
+    the central-difference gradient one cell plus one voxel beyond that (src/cuda/raycastingVolume.cu:15-43,65-119)."""
+    cell = volume_size / resolution
+    return int(math.ceil(ray_increment / cell)) + 3
+
+
+def slab_ranges(resolution: int, nranks: int, halo: int):
+    """[(own_z0, own_z1, stored_z0, stored_z1)] per rank: owned planes partition [0, R), stored = owned + halo"""
+    out = []
+    for r in range(nranks):
+        z0 = resolution * r // nranks
+        z1 = resolution * (r + 1) // nranks
+        out.append((z0, z1, max(z0 - halo, 0), min(z1 + halo, resolution)))
+    return out
+
+
+def icp_band(rows: int, rank: int, nranks: int):
+    """pixel rows [y0, y1) of an ICP level evaluated by `rank` (csrc/icp.cu, hkf_icp_track)"""
+    return rows * rank // nranks, rows * (rank + 1) // nranks
+
+
+def pack_key(t: np.ndarray, ok: np.ndarray, rank: int) -> np.ndarray:
+    """(t | ok | rank) compositing key of csrc/raycast.cu: float bits of the crossing's sample parameter in the high
+    word (positive floats order like their bit patterns), refinement success in bit 8, rank in the low byte"""
+    bits = np.asarray(t, np.float32).view(np.uint32).astype(np.uint64)
+    return (bits << np.uint64(32)) | (np.asarray(ok, np.uint64) << np.uint64(8)) | np.uint64(rank)
+
+
+def composite(keys: np.ndarray, vertices: np.ndarray, normals: np.ndarray):
+    """Single-process statement of the compositing rule: keys [G][H][W] (NO_HIT where a rank reports nothing),
+    payloads [G][H][W][4].  The minimum key wins, also when its refinement failed (the reference's ray ends at its
+    first crossing, src/cuda/raycastingVolume.cu:96-108); a failed winner's payload is zero."""
+    best = keys.min(axis=0)
+    win = (keys == best[None]) & (keys != NO_HIT)
+    assert (win.sum(axis=0) <= 1).all(), "two ranks claim the same crossing"
+    v = (vertices * win[..., None]).sum(axis=0, dtype=np.float32)
+    n = (normals * win[..., None]).sum(axis=0, dtype=np.float32)
+    return best, v, n
+
+
+def composite_distributed(keys: np.ndarray, vertices: np.ndarray, normals: np.ndarray):
+    """The same rule with collectives, as csrc/shard.cu does it: all_reduce(MIN) on the keys, losers zero their
+    payload, all_reduce(SUM) on the payload.  Works on any torch.distributed backend (gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    k = torch.from_numpy(keys.view(np.int64).copy())          # keys < 2^63 except NO_HIT, which maps to -1
+    k[k < 0] = torch.iinfo(torch.int64).max
+    best = k.clone()
+    dist.all_reduce(best, op=dist.ReduceOp.MIN)
+    win = (k == best) & (k != torch.iinfo(torch.int64).max)
+    pay = torch.from_numpy(np.concatenate([vertices, normals], axis=-1).astype(np.float32)) * win[..., None]
+    dist.all_reduce(pay, op=dist.ReduceOp.SUM)
+    out = best.numpy().copy()
+    out[out == np.iinfo(np.int64).max] = -1
+    return out.view(np.uint64), pay.numpy()[..., :4], pay.numpy()[..., 4:]
+
+
+def broadcast_unique_id(make_id, src: int = 0) -> bytes:
+    """rank `src` creates the 128-byte NCCL unique id (hkf_shard_unique_id), everybody receives it"""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if dist.get_rank() == src:
+        buf = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        buf = buf.cuda()
+    dist.broadcast(buf, src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def sharded_context(cfg, rank: int, nranks: int, device: int):
+    """hkf context of `rank`'s slab, joined to the library's own NCCL communicator.  Needs an initialised
+    torch.distributed process group (any backend) to hand the unique id round."""
+    from . import capi
+    halo = halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
+    z0, z1, _, _ = slab_ranges(cfg.resolution, nranks, halo)[rank]
+    c = dataclasses.replace(cfg, slab_z0=z0, slab_z1=z1, slab_halo=halo)
+    ctx = capi.Context(c, device=device)
+
+    def make_id():
+        b = (C.c_char * 128)()
+        ctx._ck(ctx.lib.hkf_shard_unique_id(b), "hkf_shard_unique_id")
+        return bytes(b)
+
+    uid = broadcast_unique_id(make_id)
+    ctx._ck(ctx.lib.hkf_shard_init(ctx._h, rank, nranks, uid), "hkf_shard_init")
+    return ctx

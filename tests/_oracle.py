@@ -178,6 +178,14 @@ def marching_cubes(vol, cfg, max_tris=None):
     return n, tris[:min(n, max_tris)]
 
 
+def solve_icp(s27):
+    """det gate + LLT solve of the restated host part (oracle/host_math.h); returns (ok, x[6])"""
+    a = np.ascontiguousarray(s27, np.float32).reshape(27)
+    x = np.zeros(6, np.float32)
+    ok = int(cpu().orc_solve_icp(_fp(a), _fp(x)))
+    return ok, x
+
+
 def mat44_inverse(m):
     a = np.ascontiguousarray(m, np.float32).reshape(16)
     out = np.empty(16, np.float32)
