@@ -5,8 +5,9 @@ A step = one depth frame through preprocess -> 3-level projective ICP -> TSDF in
 Workload at N=1 = BASELINE.json configs[1]: 640x480 synthetic sequence into a 512^3 / 2 m volume.
 N>1 (torchrun, one rank per GPU): N independent replicas of that workload with phase-shifted
 trajectories ("scaling": "weak", aggregate frames/s; the path shards by sequence with no data-path
-collective), plus — in the same JSON line under "c4_sharded" — the 1024^3 z-slab-sharded single
-sequence with nearest-hit raycast compositing and the NCCL allreduce of the ICP sums.
+collective).  `--workload c4` instead runs BASELINE configs[3]: ONE sequence into a 1024^3 volume that is
+z-slab-sharded over the N GPUs ("scaling": "strong"), with nearest-hit raycast compositing and the NCCL
+allreduce of the ICP sums.
 
   value      frames/s with every input frame already resident in HBM, CUDA-event timed on the
              context's stream
@@ -266,6 +267,87 @@ def cpu_baseline(cfg, frames, nframes):
             "stage_seconds": {"preprocess": times[0], "track": times[1], "integrate": times[2], "raycast": times[3]}}
 
 
+# ---------------------------------------------------------------------------------------------- C4: z-slab sharded
+def run_c4(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: ONE 640x480 sequence into a 1024^3 volume, z-slab-sharded over `world` GPUs
+    (strong scaling): banded ICP + NCCL allreduce of the 27 sums, slab-local integration (halo planes integrated
+    redundantly, no volume exchange), nearest-hit compositing of the per-slab raycasts."""
+    import dataclasses
+    import torch
+    from hybkinectfu_b200 import capi, shard, synth
+    torch.cuda.set_device(local_rank)
+    cfg = dataclasses.replace(bench_cfg(args.c4_resolution), max_triangles=1)
+    W, K = args.warmup, args.steps
+    frames, gt = make_sequence(W + K)
+    if world > 1:
+        ctx = shard.sharded_context(cfg, rank, world, local_rank)
+    else:
+        ctx = capi.Context(cfg, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.lib.hkf_stream(ctx._h), device=local_rank)
+    dev_frames = torch.from_numpy(frames.view(np.int16)).to(f"cuda:{local_rank}")
+    fbytes = frames[0].nbytes
+    ctx.set_pose(synth.pose0().astype(np.float32))
+
+    def frame(i):
+        ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev_frames.data_ptr() + i * fbytes, 1, ctx.fp), "hkf_preprocess")
+        if i:
+            ctx.icp_track()
+        ctx.integrate_tracked()
+        ctx.raycast_tracked()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    for i in range(W):
+        frame(i)
+    ctx.sync(); barrier(); torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches()
+    ev0.record(stream)
+    est = []
+    for k in range(K):
+        frame(W + k)
+    ev1.record(stream)
+    ctx.sync(); torch.cuda.synchronize(); barrier()
+    t = ev0.elapsed_time(ev1) * 1e-3
+    launches = ctx.launches() - l0
+    pose, st = ctx.frame_result()
+    # per-stage CUDA-event times of this rank (a few extra frames of the periodic sequence, untimed above)
+    stage = np.zeros(4)
+    nst = min(10, W + K - 1)
+    for j in range(nst):
+        i = 1 + j
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(stream)
+        ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev_frames.data_ptr() + i * fbytes, 1, ctx.fp), "hkf_preprocess")
+        ev[1].record(stream)
+        ctx.icp_track(); ev[2].record(stream)
+        ctx.integrate_tracked(); ev[3].record(stream)
+        ctx.raycast_tracked(); ev[4].record(stream)
+        ctx.sync()
+        stage += np.array([ev[a].elapsed_time(ev[a + 1]) * 1e3 for a in range(4)])
+    stage /= max(nst, 1)
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([t], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
+    slabs = shard.balanced_slab_ranges(cfg, world, halo) if world > 1 else shard.slab_ranges(cfg.resolution, 1, 0)
+    out = {"metric": f"fused frames/s at 640x480 into {cfg.resolution}^3 TSDF, z-slab-sharded (ICP + integrate + raycast)", "value": K / t,
+           "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t * 1e3 / K, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic analytic scene, 16-bit mm depth",
+           "config": {"workload": f"C4: one 640x480 sequence, {cfg.resolution}^3 volume over 2 m, z-slabs over {world} GPU(s), halo {halo if world > 1 else 0} planes",
+                      "owned_planes_per_rank": [s[1] - s[0] for s in slabs], "stored_planes_per_rank": [s[3] - s[2] for s in slabs], "track_status_last": int(st),
+                      "rank0_stage_us": {"preprocess": float(stage[0]), "icp": float(stage[1]), "integrate": float(stage[2]), "raycast+composite": float(stage[3])},
+                      "pose_err_vs_gt_m": float(np.abs(pose[:3, 3] - gt[W + K - 1][:3, 3]).max())},
+           "gpu_launches": int(launches)}
+    ctx.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -331,6 +413,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2: BASELINE configs[1] (replicas at N>1); c4: z-slab-sharded single sequence")
+    ap.add_argument("--c4-resolution", type=int, default=1024)
     args = ap.parse_args()
     if args.warmup < 1:
         args.warmup = 1
@@ -347,7 +431,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    out = run_ours(args, rank, world, local_rank)
+    out = run_c4(args, rank, world, local_rank) if args.workload == "c4" else run_ours(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

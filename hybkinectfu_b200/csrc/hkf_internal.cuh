@@ -56,6 +56,26 @@ struct HkfDeviceState {
     long long dbg[8];        // development aid: SM-clock stamps of the last block of a tracking kernel
 };
 
+// ---- z-slab sharding over peer memory (csrc/shard.cu).  Every rank owns one mailbox that its peers write into
+// through NVLink (cudaIpc-mapped pointers); flags are monotonically increasing sequence numbers, so nothing is
+// ever reset.
+#define HKF_MAX_RANKS 8
+struct ShardMailbox {
+    // [iteration parity][source rank][27 partial sums + padding]: every 8-byte word carries (float bits, iteration
+    // number), stored with ONE 64-bit store, so the reader needs no separate flag and the writer no fence (the
+    // low-latency protocol NCCL calls LL)
+    unsigned long long sums[2][HKF_MAX_RANKS][32];
+    unsigned ready[HKF_MAX_RANKS];         // raycast epoch whose keys/payload the source rank has finished writing
+    unsigned done[HKF_MAX_RANKS];          // raycast epoch the source rank has finished compositing (= reading its peers)
+};
+struct ShardPeers {
+    ShardMailbox* mail[HKF_MAX_RANKS];                 // mail[r] = rank r's mailbox as mapped in this process
+    const unsigned long long* keys[HKF_MAX_RANKS];     // rank r's raycast keys
+    const float4* v[HKF_MAX_RANKS];                    // rank r's level-0 model vertices / normals
+    const float4* n[HKF_MAX_RANKS];
+    int rank, nranks;
+};
+
 struct hkf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -98,6 +118,11 @@ struct hkf_ctx {
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
     float* ray_payload = nullptr;
+    ShardMailbox* mailbox = nullptr;   // this rank's mailbox (device memory, IPC-exported)
+    ShardPeers peers{};
+    bool p2p = false;                  // peers mapped: exchanges go over peer memory instead of NCCL
+    unsigned shard_seq = 0, shard_epoch = 0;
+    void* ipc_opened[HKF_MAX_RANKS][4]{};
 };
 
 #define HKF_CUDA(ctx, call)                                                        \
@@ -196,6 +221,21 @@ __device__ __forceinline__ float hkf_row4(float m1, float m2, float m3, float m4
 }
 
 __device__ __forceinline__ float4 ld_f4(const float4* p) { return __ldg(p); }
+
+// flag plumbing of the peer-memory exchanges: release-store / acquire-spin at system scope, bounded
+__device__ __forceinline__ void shard_signal(unsigned* p, unsigned v)
+{
+    __threadfence_system();
+    *(volatile unsigned*)p = v;
+}
+__device__ __forceinline__ bool shard_wait_ge(const unsigned* p, unsigned v)
+{
+    const long long t0 = clock64();
+    while ((int)(*(volatile const unsigned*)p - v) < 0)
+        if (clock64() - t0 > 4000000000ll) return false;            // ~2 s: a peer died; do not hang the GPU
+    __threadfence_system();
+    return true;
+}
 
 // raw MUFU.RCP (1 ulp): only ever used to PRE-classify a value whose exact IEEE result is then either
 // provably implied or recomputed with div.rn

@@ -40,6 +40,7 @@ struct IcpArgs {
     float* partials;           // [27][ntiles]
     int is_last;               // last iteration of the schedule: commit cur -> pose
     float cur[16], last_inv[16];   // only used when !FROM_STATE
+    ShardPeers peers; unsigned seq;   // peer-memory sharded mode (P2P): exchange of the partial sums inside this kernel
 };
 
 #define ICP_TILES 2
@@ -51,7 +52,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // FROM_STATE: pose/status from device state; SOLVE: the last block also solves and advances the pose (single GPU).
 // Sharded ranks run <true,false> over their pixel-row band, allreduce st->sums, then k_icp_solve.
-template <bool FROM_STATE, bool SOLVE>
+template <bool FROM_STATE, bool SOLVE, bool P2P>
 __global__ void __launch_bounds__(ICP_THREADS, 2)
 k_icp(IcpArgs A, HkfDeviceState* st)
 {
@@ -147,6 +148,36 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     __threadfence();
     second_stage_all<ICP_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
     __syncthreads();
+    if (P2P) {
+        // All-reduce of the 27 partial sums over peer memory: this rank's sums go into slot [seq & 1][rank] of every
+        // rank's mailbox as (value, iteration) words (one 64-bit P2P store each over NVLink), every rank polls its own
+        // mailbox until all words of the iteration have arrived and adds them in RANK ORDER, so all ranks continue
+        // with bit-identical sums and poses.
+        const int par = (int)(A.seq & 1u);
+        if (warp == 0) {
+            if (lane < HKF_SUMS) {
+                const unsigned long long word = ((unsigned long long)A.seq << 32) | __float_as_uint(s_sums[lane]);
+                for (int r = 0; r < A.peers.nranks; ++r)
+                    *(volatile unsigned long long*)&A.peers.mail[r]->sums[par][A.peers.rank][lane] = word;
+            }
+            const ShardMailbox* mine = A.peers.mail[A.peers.rank];
+            bool ok = true;
+            float acc = 0.f;
+            if (lane < HKF_SUMS) {
+                const long long tw = clock64();
+                for (int r = 0; r < A.peers.nranks && ok; ++r) {
+                    unsigned long long word;
+                    while ((unsigned)((word = *(volatile const unsigned long long*)&mine->sums[par][r][lane]) >> 32) != A.seq)
+                        if (clock64() - tw > 4000000000ll) { ok = false; break; }     // ~2 s: a peer died; do not hang the GPU
+                    const float v = __uint_as_float((unsigned)word);
+                    acc = r == 0 ? v : __fadd_rn(acc, v);
+                }
+            }
+            ok = __all_sync(0xffffffffu, ok);
+            if (lane < HKF_SUMS) s_sums[lane] = ok ? acc : __int_as_float(0x7fc00000);   // NaN sums -> tracking fails
+        }
+        __syncthreads();
+    }
     const long long t3 = clock64();
     if (threadIdx.x >= 64 && threadIdx.x < 64 + HKF_SUMS) st->sums[threadIdx.x - 64] = s_sums[threadIdx.x - 64];
     if (threadIdx.x == 64) st->ticket = 0;
@@ -204,6 +235,7 @@ static void fill_icp_args(hkf_ctx* c, int level, const HkfCameraParams* cam, flo
     A->angle_shake = 0.f; A->dist_shake = 0.f;
     A->partials = c->partials;
     A->is_last = 0;
+    A->peers = ShardPeers{}; A->seq = 0;
 }
 
 extern "C" int hkf_cal_point_to_plane_err_solver_params(hkf_ctx* c, unsigned level, const HkfMat44* cur, const HkfMat44* last_inv,
@@ -214,7 +246,7 @@ extern "C" int hkf_cal_point_to_plane_err_solver_params(hkf_ctx* c, unsigned lev
     if (cam->cols != c->cols[level] || cam->rows != c->rows[level]) { c->err = "level camera size mismatch"; return HKF_ERR_ARG; }
     IcpArgs A; fill_icp_args(c, (int)level, cam, dist_thres, norm_sin_thres, &A);
     memcpy(A.cur, cur->m, 64); memcpy(A.last_inv, last_inv->m, 64);
-    k_icp<false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+    k_icp<false, false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -288,8 +320,8 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
         }
         for (int it = 0; it < iters[l]; ++it) {
             A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
-            if (sharded) {
-                k_icp<true, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+            if (sharded && !c->p2p) {
+                k_icp<true, false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
                 HKF_LAUNCH_CHECK(c);
                 rc = hkf_shard_allreduce_sums(c);
                 if (rc != HKF_OK) return rc;
@@ -305,7 +337,8 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, k_icp<true, true>, A, c->st);
+            if (sharded) { A.peers = c->peers; A.seq = ++c->shard_seq; cudaLaunchKernelEx(&cfg, k_icp<true, true, true>, A, c->st); }
+            else cudaLaunchKernelEx(&cfg, k_icp<true, true, false>, A, c->st);
             HKF_LAUNCH_CHECK(c);
         }
     }

@@ -31,6 +31,7 @@ struct RaycastArgs {
     float inc, near_plane, far_plane;
     float pose[16];
     int own_z0, own_z1, rank;
+    const ShardMailbox* mailbox; int nranks; unsigned epoch;   // peer-memory mode: epoch of this raycast
 };
 
 template <bool FROM_STATE, bool SLAB>
@@ -38,6 +39,13 @@ __global__ void __launch_bounds__(256)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
 {
+    if (SLAB && A.mailbox != nullptr) {
+        // peers read this rank's keys / payload of the previous epoch straight from its memory: do not overwrite
+        // them before every peer has finished compositing that epoch
+        if (threadIdx.x == 0)
+            for (int r = 0; r < A.nranks; ++r) shard_wait_ge(&A.mailbox->done[r], A.epoch - 1u);
+        __syncthreads();
+    }
     // 16x16 pixel block, warps as 8x4 patches
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -80,7 +88,22 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         const int R = V.R;
         float t = tmin, last_sdf = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
         bool last_known = true;
-        while (t < tmax) {
+        float t_leave = 3.0e38f;
+        if (SLAB) {
+            // Samples before the ray enters the stored planes (minus two cells of slack) cannot be read by this rank:
+            // advance t through them with the same repeated float addition (the sample sequence is part of parity),
+            // skipping the voxel arithmetic; past the far side of the slab nothing more can be detected.
+            const float zl = V.z_lo == 0 ? -1.0e30f : ((float)V.z_lo - 2.0f) * V.cell;
+            const float zh = V.z_hi == R ? 1.0e30f : ((float)V.z_hi + 2.0f) * V.cell;
+            const float ta = (zl - oz) / dz, tb = (zh - oz) / dz;
+            const float t_enter = fminf(ta, tb) - A.inc;
+            t_leave = fmaxf(ta, tb) + A.inc;
+            if (t < t_enter) {
+                while (t < t_enter && t < tmax) t = __fadd_rn(A.inc, t);
+                last_known = false;
+            }
+        }
+        while (t < tmax && t < t_leave) {
             const float px = __fmaf_rn(dx, t, ox), py = __fmaf_rn(dy, t, oy), pz = __fmaf_rn(dz, t, oz);
             const int gx = max(0, min(vol_w2v(V, px), R - 1));
             const int gy = max(0, min(vol_w2v(V, py), R - 1));
@@ -149,6 +172,8 @@ static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParam
     A->inc = rp->fRayIncrement; A->near_plane = near_plane; A->far_plane = far_plane;
     if (pose) memcpy(A->pose, pose, 64); else memset(A->pose, 0, 64);
     A->own_z0 = (int)c->own_z0; A->own_z1 = (int)c->own_z1; A->rank = c->rank;
+    A->mailbox = nullptr; A->nranks = c->nranks; A->epoch = 0;
+    if (c->p2p) { A->mailbox = c->mailbox; A->epoch = ++c->shard_epoch; }
 }
 
 static inline bool is_slab(const hkf_ctx* c) { return !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution); }

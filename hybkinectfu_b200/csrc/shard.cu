@@ -86,7 +86,102 @@ extern "C" int hkf_shard_init(hkf_ctx* c, int rank, int nranks, const void* uniq
 
 void hkf_shard_release(hkf_ctx* c)
 {
-    if (c && c->nccl_comm) { nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
+    if (!c) return;
+    for (int r = 0; r < HKF_MAX_RANKS; ++r)
+        for (int k = 0; k < 4; ++k)
+            if (c->ipc_opened[r][k]) { cudaIpcCloseMemHandle(c->ipc_opened[r][k]); c->ipc_opened[r][k] = nullptr; }
+    c->p2p = false;
+    if (c->mailbox) { cudaFree(c->mailbox); c->mailbox = nullptr; }
+    if (c->nccl_comm) { nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
+}
+
+// ---------------------------------------------------------------- peer-memory fast path
+extern "C" int hkf_shard_ipc_handles(hkf_ctx* c, void* out)
+{
+    if (!c || !out) return HKF_ERR_ARG;
+    static_assert(4 * sizeof(cudaIpcMemHandle_t) == HKF_SHARD_IPC_BYTES, "handle block size");
+    HKF_CUDA(c, cudaSetDevice(c->device));
+    if (!c->mailbox) {
+        HKF_CUDA(c, cudaMalloc(&c->mailbox, sizeof(ShardMailbox)));
+        HKF_CUDA(c, cudaMemset(c->mailbox, 0, sizeof(ShardMailbox)));
+    }
+    cudaIpcMemHandle_t h[4];
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[0], c->mailbox));
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[1], c->ray_keys));
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[2], c->model_v[0]));
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[3], c->model_n[0]));
+    memcpy(out, h, sizeof(h));
+    return HKF_OK;
+}
+
+extern "C" int hkf_shard_connect(hkf_ctx* c, const void* all_handles, int nranks)
+{
+    if (!c || !all_handles) return HKF_ERR_ARG;
+    if (nranks != c->nranks || nranks > HKF_MAX_RANKS) { c->err = "hkf_shard_connect: rank count mismatch (or > 8 ranks)"; return HKF_ERR_ARG; }
+    if (!c->mailbox) { c->err = "hkf_shard_connect: call hkf_shard_ipc_handles first"; return HKF_ERR_STATE; }
+    HKF_CUDA(c, cudaSetDevice(c->device));
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+    ShardPeers P{};
+    P.rank = c->rank; P.nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+        void* ptr[4];
+        if (r == c->rank) {
+            ptr[0] = c->mailbox; ptr[1] = c->ray_keys; ptr[2] = c->model_v[0]; ptr[3] = c->model_n[0];
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                HKF_CUDA(c, cudaIpcOpenMemHandle(&ptr[k], h[r * 4 + k], cudaIpcMemLazyEnablePeerAccess));
+                c->ipc_opened[r][k] = ptr[k];
+            }
+        }
+        P.mail[r] = (ShardMailbox*)ptr[0]; P.keys[r] = (const unsigned long long*)ptr[1];
+        P.v[r] = (const float4*)ptr[2]; P.n[r] = (const float4*)ptr[3];
+    }
+    c->peers = P;
+    c->p2p = true;
+    return HKF_OK;
+}
+
+// One kernel composites the per-slab raycasts: a barrier over mailbox flags (every rank's keys and payload of this
+// epoch are complete), then per pixel the minimum key over ranks read straight from peer memory and, where another
+// rank won with a successful refinement, that rank's vertex/normal.  In place: a rank only overwrites pixels it did
+// not win, and nobody reads a loser's payload.
+__global__ void __launch_bounds__(256)
+k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ out_n, unsigned npix, unsigned epoch, HkfDeviceState* st)
+{
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        bool ok = true;
+        if (blockIdx.x == 0)
+            for (int r = 0; r < P.nranks; ++r) shard_signal(&P.mail[r]->ready[P.rank], epoch);
+        for (int r = 0; r < P.nranks; ++r) ok = shard_wait_ge(&P.mail[P.rank]->ready[r], epoch) && ok;
+        s_ok = ok;
+    }
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_ok && i < npix) {
+        unsigned long long best = ~0ull;
+        for (int r = 0; r < P.nranks; ++r) {
+            const unsigned long long k = __ldcv(P.keys[r] + i);       // peer memory: never from a stale cache line
+            best = k < best ? k : best;
+        }
+        const int w = (int)(best & 0xffu);
+        if (best == ~0ull || !((best >> 8) & 1ull)) {
+            out_v[i] = make_float4(0.f, 0.f, 0.f, 0.f); out_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (w != P.rank) {
+            out_v[i] = __ldcv(P.v[w] + i); out_n[i] = __ldcv(P.n[w] + i);
+        }
+    }
+    // everything this rank reads from its peers for this epoch has been read
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned t = atomicAdd(&st->ticket, 1u);
+        if (t == gridDim.x - 1) {
+            st->ticket = 0;
+            if (!s_ok) st->track_status = HKF_TRACK_SINGULAR;
+            for (int r = 0; r < P.nranks; ++r) shard_signal(&P.mail[r]->done[P.rank], epoch);
+        }
+    }
 }
 
 // sum the 27 per-rank partial sums in place (st->sums), enqueued on the context's stream
@@ -115,6 +210,11 @@ extern "C" int hkf_shard_composite_raycast(hkf_ctx* c)
     if (!c->nccl_comm) { c->err = "hkf_shard_composite_raycast: hkf_shard_init has not been called"; return HKF_ERR_STATE; }
     NcclApi* a = nccl_api();
     const unsigned npix = c->cols[0] * c->rows[0];
+    if (c->p2p) {
+        k_composite_p2p<<<div_up(npix, 256), 256, 0, c->stream>>>(c->peers, c->model_v[0], c->model_n[0], npix, c->shard_epoch, c->st);
+        HKF_LAUNCH_CHECK(c);
+        return HKF_OK;
+    }
     unsigned long long* best = c->ray_keys + npix;            // second half of the key buffer
     HKF_NCCL(c, a->AllReduce(c->ray_keys, best, npix, ncclUint64, ncclMin, (ncclComm_t)c->nccl_comm, c->stream));
     k_composite_select<<<div_up(npix, 256), 256, 0, c->stream>>>(c->ray_keys, best, c->model_v[0], c->model_n[0], (float4*)c->ray_payload, npix);

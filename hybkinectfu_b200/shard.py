@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import os
 
 import numpy as np
 
@@ -34,6 +35,43 @@ def slab_ranges(resolution: int, nranks: int, halo: int):
         z1 = resolution * (r + 1) // nranks
         out.append((z0, z1, max(z0 - halo, 0), min(z1 + halo, resolution)))
     return out
+
+
+def plane_work(cfg, pose=None, samples: int = 48) -> np.ndarray:
+    """Relative integration + raycast work of each z plane for a camera at `pose` (default: HybKinectfu's initial
+    pose): the fraction of the plane inside the view frustum and the integration depth range, plus a constant."""
+    from . import synth
+    pose = synth.pose0(cfg.volume_size, cfg.trunc_min) if pose is None else np.asarray(pose, np.float64)
+    inv = np.linalg.inv(pose)
+    R, S = cfg.resolution, cfg.volume_size
+    g = (np.arange(samples) + 0.5) * (S / samples)
+    xx, yy = np.meshgrid(g, g)
+    w = np.zeros(R)
+    for z in range(R):
+        wz = (z + 0.5) * S / R
+        p = np.stack([xx, yy, np.full_like(xx, wz), np.ones_like(xx)], -1) @ inv.T
+        Z = p[..., 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = p[..., 0] * cfg.fx / Z + cfg.cx
+            v = p[..., 1] * cfg.fy / Z + cfg.cy
+        inside = (Z > 0) & (Z < cfg.max_integrate_dist + cfg.sdf_trunc) & (u >= 0) & (u < cfg.cols) & (v >= 0) & (v < cfg.rows)
+        w[z] = inside.mean()
+    # measured on B200 (1024^3, integrate + raycast per plane): cost grows like the square root of the covered
+    # fraction (free-space bricks are cheap, the per-row and near-surface work is not) plus a small constant
+    return np.sqrt(w) + 0.05
+
+
+def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int = 8):
+    """slab_ranges with boundaries chosen so that every rank gets the same share of plane_work (the view frustum
+    widens with depth: equal-thickness slabs are not equal work)"""
+    R = cfg.resolution
+    cum = np.concatenate([[0.0], np.cumsum(plane_work(cfg, pose))])
+    cuts = [0]
+    for r in range(1, nranks):
+        z = int(np.searchsorted(cum, cum[-1] * r / nranks))
+        cuts.append(min(max(z, cuts[-1] + min_planes), R - min_planes * (nranks - r)))
+    cuts.append(R)
+    return [(cuts[r], cuts[r + 1], max(cuts[r] - halo, 0), min(cuts[r + 1] + halo, R)) for r in range(nranks)]
 
 
 def icp_band(rows: int, rank: int, nranks: int):
@@ -77,6 +115,21 @@ def composite_distributed(keys: np.ndarray, vertices: np.ndarray, normals: np.nd
     return out.view(np.uint64), pay.numpy()[..., :4], pay.numpy()[..., 4:]
 
 
+IPC_BYTES = 256          # HKF_SHARD_IPC_BYTES
+
+
+def all_gather_bytes(mine: bytes) -> bytes:
+    """concatenation, in rank order, of every rank's equally sized byte string"""
+    import torch
+    import torch.distributed as dist
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+
 def broadcast_unique_id(make_id, src: int = 0) -> bytes:
     """rank `src` creates the 128-byte NCCL unique id (hkf_shard_unique_id), everybody receives it"""
     import torch
@@ -90,12 +143,13 @@ def broadcast_unique_id(make_id, src: int = 0) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def sharded_context(cfg, rank: int, nranks: int, device: int):
+def sharded_context(cfg, rank: int, nranks: int, device: int, p2p=None, balanced: bool = True):
     """hkf context of `rank`'s slab, joined to the library's own NCCL communicator.  Needs an initialised
     torch.distributed process group (any backend) to hand the unique id round."""
     from . import capi
     halo = halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
-    z0, z1, _, _ = slab_ranges(cfg.resolution, nranks, halo)[rank]
+    ranges = balanced_slab_ranges(cfg, nranks, halo) if balanced else slab_ranges(cfg.resolution, nranks, halo)
+    z0, z1, _, _ = ranges[rank]
     c = dataclasses.replace(cfg, slab_z0=z0, slab_z1=z1, slab_halo=halo)
     ctx = capi.Context(c, device=device)
 
@@ -106,4 +160,11 @@ def sharded_context(cfg, rank: int, nranks: int, device: int):
 
     uid = broadcast_unique_id(make_id)
     ctx._ck(ctx.lib.hkf_shard_init(ctx._h, rank, nranks, uid), "hkf_shard_init")
+    if p2p is None:
+        p2p = os.environ.get("HKF_SHARD_P2P", "1") != "0" and nranks <= 8
+    if p2p:
+        h = (C.c_char * IPC_BYTES)()
+        ctx._ck(ctx.lib.hkf_shard_ipc_handles(ctx._h, h), "hkf_shard_ipc_handles")
+        allh = all_gather_bytes(bytes(h))
+        ctx._ck(ctx.lib.hkf_shard_connect(ctx._h, allh, nranks), "hkf_shard_connect")
     return ctx

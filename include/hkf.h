@@ -209,6 +209,15 @@ int hkf_shard_init(hkf_ctx* ctx, int rank, int nranks, const void* unique_id_128
 /* nearest-hit compositing of per-slab partial raycasts (min over ranks of (t, ok, rank) keys,
  * then payload from the winner) -> full model maps on every rank */
 int hkf_shard_composite_raycast(hkf_ctx* ctx);
+/* Peer-memory fast path (optional, after hkf_shard_init): each rank exports HKF_SHARD_IPC_BYTES bytes of cudaIpc
+ * handles (its mailbox, raycast keys and level-0 model maps); the caller gathers them from all ranks (rank order)
+ * and hands the concatenation to hkf_shard_connect.  Afterwards the ICP sums are exchanged by the tracking kernel
+ * itself (P2P stores + flags over NVLink, summed in rank order so every rank holds the same bits) and the raycast is
+ * composited by one kernel that reads its peers' keys and the winner's payload directly; NCCL is no longer on the
+ * per-frame path.  Without it the same exchanges use ncclAllReduce. */
+#define HKF_SHARD_IPC_BYTES 256
+int hkf_shard_ipc_handles(hkf_ctx* ctx, void* out_handles);
+int hkf_shard_connect(hkf_ctx* ctx, const void* all_handles, int nranks);
 
 #ifdef __cplusplus
 }

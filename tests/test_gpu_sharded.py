@@ -110,7 +110,7 @@ def test_sharded_equals_single_gpu(world, res):
     for r in range(world):
         assert bits_equal(got[r]["given_v"], v1), f"composited vertices differ on rank {r}"
         assert bits_equal(got[r]["given_n"], n1), f"composited normals differ on rank {r}"
-        z0, z1, s0, s1 = shard.slab_ranges(res, world, halo)[r]
+        z0, z1, s0, s1 = shard.balanced_slab_ranges(cfg, world, halo)[r]
         assert got[r]["slab"] == (z0, z1, halo)
         assert bits_equal(got[r]["given_vol"], vol1[s0:s1]), f"slab {r} differs from planes [{s0},{s1}) of the whole volume"
     c.reset_volume(); c.set_pose(synth.pose0().astype(np.float32))

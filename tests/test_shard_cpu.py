@@ -21,6 +21,15 @@ def test_slabs_partition_the_volume_with_halos():
         assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))              # owned planes tile [0, R)
         assert all(s0 == max(z0 - halo, 0) and s1 == min(z1 + halo, R) for z0, z1, s0, s1 in rs)
     assert shard.halo_planes(0.032, 2.0, 1024) == 20
+    # work-balanced slabs: still a partition, thinner where the frustum is wide
+    cfg = small_config(128)
+    for G in (2, 4, 8):
+        rs = shard.balanced_slab_ranges(cfg, G, 7)
+        assert rs[0][0] == 0 and rs[-1][1] == 128 and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert all(z1 - z0 >= 8 for z0, z1, _, _ in rs)
+        w = shard.plane_work(cfg)
+        share = [w[z0:z1].sum() / w.sum() for z0, z1, _, _ in rs]
+        assert max(share) < 1.3 / G
     bands = [shard.icp_band(120, r, 8) for r in range(8)]
     assert bands[0][0] == 0 and bands[-1][1] == 120 and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
 
