@@ -86,7 +86,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
 
     if (tmin < tmax) {
         const int R = V.R;
-        float t = tmin, last_sdf = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
+        float t = tmin, last_sdf = 0.f, last_t = tmin;
         bool last_known = true;
         float t_leave = 3.0e38f;
         if (SLAB) {
@@ -103,26 +103,54 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 last_known = false;
             }
         }
-        while (t < tmax && t < t_leave) {
-            const float px = __fmaf_rn(dx, t, ox), py = __fmaf_rn(dy, t, oy), pz = __fmaf_rn(dz, t, oz);
-            const int gx = max(0, min(vol_w2v(V, px), R - 1));
-            const int gy = max(0, min(vol_w2v(V, py), R - 1));
-            const int gz = max(0, min(vol_w2v(V, pz), R - 1));
-            bool known = true;
-            float sdf = 0.f;
-            if (SLAB && (gz < V.z_lo || gz >= V.z_hi)) known = false;
-            else sdf = __ldg(&V.vol[vol_index(V, gx, gy, gz)].x);
-            if (known && last_known && last_sdf > 0.0f && sdf < 0.0f) {
-                // first zero crossing: the ray ends here whatever happens next
-                const bool mine = !SLAB || (gz >= A.own_z0 && gz < A.own_z1);
-                if (mine) {
+        // Nearest-voxel index of a sample, (int)((p*R)/S) clamped: the quotient is first taken with a multiplication by
+        // 1/S (within 2 ulp of the IEEE quotient); only when that lands within 1e-3 of an integer does the reference's
+        // div.rn decide.  The samples of a ray do not depend on each other, so they are taken four at a time: four
+        // independent loads in flight, then the crossing test in order.
+        const float rS = __frcp_rn(S);
+        const unsigned Rm1 = (unsigned)(R - 1);
+        auto voxel = [&](float p) -> int {
+            const float q = __fmul_rn(p, V.Rf);
+            const float qa = __fmul_rn(q, rS);
+            int g = __float2int_rz(qa);
+            if (fabsf(qa - rintf(qa)) < 1.0e-3f) g = __float2int_rz(__fdiv_rn(q, S));
+            return (int)min((unsigned)max(g, 0), Rm1);
+        };
+        bool done = false;
+        while (!done && t < tmax && t < t_leave) {
+            float ts[4], sd[4];
+            int gzs[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                ts[b] = t;
+                const int gx = voxel(__fmaf_rn(dx, t, ox)), gy = voxel(__fmaf_rn(dy, t, oy)), gz = voxel(__fmaf_rn(dz, t, oz));
+                gzs[b] = gz;
+                const int gzc = SLAB ? min(max(gz, V.z_lo), V.z_hi - 1) : gz;      // keep the speculative read inside the slab
+                sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gzc)].x);
+                t = __fadd_rn(A.inc, t);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (done) break;
+                if (!(ts[b] < tmax)) { done = true; break; }
+                const int gz = gzs[b];
+                const bool known = !SLAB || (gz >= V.z_lo && gz < V.z_hi);
+                const float sdf = known ? sd[b] : 0.f;
+                if (known && last_known && last_sdf > 0.0f && sdf < 0.0f) {
+                    // first zero crossing: the ray ends here whatever happens next
+                    done = true;
+                    const bool mine = !SLAB || (gz >= A.own_z0 && gz < A.own_z1);
+                    if (!mine) break;          // another rank owns this crossing and reports it; nothing later can win
+                    const float tc = ts[b];
+                    const float px = __fmaf_rn(dx, tc, ox), py = __fmaf_rn(dy, tc, oy), pz = __fmaf_rn(dz, tc, oz);
+                    const float lx = __fmaf_rn(dx, last_t, ox), ly = __fmaf_rn(dy, last_t, oy), lz = __fmaf_rn(dz, last_t, oz);
                     bool ok = false;
                     float ftdt, ft;
                     float wx = 0.f, wy = 0.f, wz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
                     do {
                         if (vol_interp_sdf<SLAB>(V, px, py, pz, ftdt) != 1) break;
                         if (vol_interp_sdf<SLAB>(V, lx, ly, lz, ft) != 1) break;
-                        const float alpha = __fsub_rn(t, __fdiv_rn(__fmul_rn(A.inc, ftdt), __fsub_rn(ftdt, ft)));
+                        const float alpha = __fsub_rn(tc, __fdiv_rn(__fmul_rn(A.inc, ftdt), __fsub_rn(ftdt, ft)));
                         wx = __fmaf_rn(dx, alpha, ox); wy = __fmaf_rn(dy, alpha, oy); wz = __fmaf_rn(dz, alpha, oz);
                         // gradientForPoint(volume, last_world_pos, vertex)
                         const int hx = vol_w2v(V, lx), hy = vol_w2v(V, ly), hz = vol_w2v(V, lz);
@@ -147,15 +175,11 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                         ok = true;
                     } while (0);
                     if (ok) { ov = make_float4(wx, wy, wz, 1.0f); on = make_float4(nx, ny, nz, 0.f); }
-                    key = ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)(ok ? 1u : 0u) << 8) | (unsigned)A.rank;
+                    key = ((unsigned long long)__float_as_uint(tc) << 32) | ((unsigned long long)(ok ? 1u : 0u) << 8) | (unsigned)A.rank;
                     break;
                 }
-                if (!SLAB) break;
-                // another rank owns this crossing and the ray ends there; nothing later can win
-                break;
+                last_sdf = sdf; last_known = known; last_t = ts[b];
             }
-            last_sdf = sdf; last_known = known; lx = px; ly = py; lz = pz;
-            t = __fadd_rn(A.inc, t);
         }
     }
     out_v[pix] = ov;
