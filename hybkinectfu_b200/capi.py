@@ -77,7 +77,7 @@ EXPORTS = [
     "hkf_integrate_volume", "hkf_raycasting_volume", "hkf_marchingcube", "hkf_triangle_count", "hkf_preprocess",
     "hkf_set_pose", "hkf_icp_track", "hkf_sdf_track", "hkf_integrate_tracked", "hkf_raycast_tracked",
     "hkf_frame_result", "hkf_count_integrate_updates", "hkf_shard_unique_id", "hkf_shard_init",
-    "hkf_shard_composite_raycast", "hkf_shard_ipc_handles", "hkf_shard_connect",
+    "hkf_shard_composite_raycast", "hkf_shard_ipc_handles", "hkf_shard_connect", "hkf_preprocess_next", "hkf_swap_frame",
 ]
 
 _lib = None
@@ -127,6 +127,8 @@ def load() -> C.CDLL:
     lib.hkf_marchingcube.argtypes = [P, C.c_int, C.c_float]
     lib.hkf_triangle_count.argtypes = [P, C.POINTER(C.c_uint)]
     lib.hkf_preprocess.argtypes = [P, C.c_void_p, C.c_int, C.POINTER(FrameParams)]
+    lib.hkf_preprocess_next.argtypes = [P, C.c_void_p, C.c_int, C.POINTER(FrameParams)]
+    lib.hkf_swap_frame.argtypes = [P]
     lib.hkf_set_pose.argtypes = [P, C.POINTER(Mat44)]
     for n in ("hkf_icp_track", "hkf_sdf_track", "hkf_integrate_tracked", "hkf_raycast_tracked"):
         getattr(lib, n).argtypes = [P, C.POINTER(FrameParams)]
@@ -358,6 +360,13 @@ class Context:
 
     def preprocess_host_async(self, host_ptr: int):
         self._ck(self.lib.hkf_preprocess(self._h, C.c_void_p(host_ptr), 0, C.byref(self.fp)), "hkf_preprocess")
+
+    def preprocess_next(self, ptr: int, is_device: bool):
+        """upload + preprocess the NEXT frame on the side stream (hkf_preprocess_next); swap_frame() makes it current"""
+        self._ck(self.lib.hkf_preprocess_next(self._h, C.c_void_p(ptr), 1 if is_device else 0, C.byref(self.fp)), "hkf_preprocess_next")
+
+    def swap_frame(self):
+        self._ck(self.lib.hkf_swap_frame(self._h), "hkf_swap_frame")
 
     def set_pose(self, pose):
         m = Mat44.from_np(pose)

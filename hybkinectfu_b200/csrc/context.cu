@@ -61,6 +61,11 @@ static void free_all(hkf_ctx* c)
 {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_pre_done) cudaEventDestroy(c->ev_pre_done);
+    if (c->ev_swap) cudaEventDestroy(c->ev_swap);
+    cudaFree(c->back.depth_mm); cudaFree(c->back.raw_depth); cudaFree(c->back.trunc_depth); cudaFree(c->back.filtered_depth); cudaFree(c->back.bounds.base);
+    for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->back.new_v[l]); cudaFree(c->back.new_n[l]); }
     cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
     cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->st);
@@ -98,7 +103,11 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     c->ip = *p;
     c->levels = (int)p->pyramid_levels;
     CREATE_CUDA(cudaSetDevice(device));
-    CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // the per-frame chain runs at the highest priority; the side stream that prepares the next frame at the lowest
+        int lo = 0, hi = 0;
+        CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CREATE_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+    }
     unsigned cols = p->depth_camera.cols, rows = p->depth_camera.rows;
     for (int l = 0; l < c->levels; ++l) { c->cols[l] = cols; c->rows[l] = rows; cols >>= 1; rows >>= 1; }
     size_t n0 = (size_t)c->cols[0] * c->rows[0];
@@ -172,6 +181,7 @@ extern "C" void hkf_destroy(hkf_ctx* c)
 extern "C" int hkf_sync(hkf_ctx* c)
 {
     if (!c) return HKF_ERR_ARG;
+    if (c->stream2) HKF_CUDA(c, cudaStreamSynchronize(c->stream2));
     HKF_CUDA(c, cudaStreamSynchronize(c->stream));
     return HKF_OK;
 }

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -76,6 +77,15 @@ struct ShardPeers {
     int rank, nranks;
 };
 
+// one set of per-frame input buffers (the context keeps two when frames are pipelined, preprocess.cu)
+struct HkfFrameSet {
+    uint16_t* depth_mm = nullptr;
+    float *raw_depth = nullptr, *trunc_depth = nullptr, *filtered_depth = nullptr;
+    float4* new_v[HKF_MAX_LEVELS]{};
+    float4* new_n[HKF_MAX_LEVELS]{};
+    DepthBounds bounds{};
+};
+
 struct hkf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -98,6 +108,13 @@ struct hkf_ctx {
     float4* model_v[HKF_MAX_LEVELS]{};
     float4* model_n[HKF_MAX_LEVELS]{};
     unsigned long long* ray_keys = nullptr;
+    // frame pipelining (hkf_preprocess_next / hkf_swap_frame)
+    HkfFrameSet back;
+    bool back_allocated = false, back_valid = false, pipe_compute = false;
+    const uint16_t* back_src = nullptr;
+    HkfFrameParams back_fp{};
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_pre_done = nullptr, ev_swap = nullptr;
     // solver scratch: [27][nblocks] partials for the largest level
     float* partials = nullptr;
     unsigned max_blocks = 0;
@@ -149,7 +166,7 @@ static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; 
 // internal cross-file helpers (C++ linkage)
 void hkf_shard_release(hkf_ctx* c);
 int hkf_shard_allreduce_sums(hkf_ctx* c);
-int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn);
+int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream = nullptr);
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 
 // ---------------------------------------------------------------- device arithmetic contract

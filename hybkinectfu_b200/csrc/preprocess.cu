@@ -359,39 +359,137 @@ extern "C" int hkf_downsample_model_vertices(hkf_ctx* c) { return c ? downsample
 extern "C" int hkf_downsample_model_normals(hkf_ctx* c) { return c ? downsample<true>(c, c->model_n) : HKF_ERR_ARG; }
 
 // all coarser levels of one (vertices, normals) pyramid pair in a single launch
-int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn)
+int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream)
 {
+    if (stream == nullptr) stream = c->stream;
     if (c->levels < 2) return HKF_OK;
     bool three = c->levels >= 3;
     unsigned gx = div_up(c->cols[1], 2), gy = div_up(c->rows[1], 2);
     dim3 b(32, 4), g(div_up(gx, 32), div_up(gy, 4));
-    k_pyramids_fused<<<g, b, 0, c->stream>>>(pv[0], pn[0], pv[1], pn[1], three ? pv[2] : nullptr, three ? pn[2] : nullptr,
+    k_pyramids_fused<<<g, b, 0, stream>>>(pv[0], pn[0], pv[1], pn[1], three ? pv[2] : nullptr, three ? pn[2] : nullptr,
                                              c->cols[0], c->cols[1], c->rows[1], three ? c->cols[2] : 0, three ? c->rows[2] : 0);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
 
-extern "C" int hkf_preprocess(hkf_ctx* c, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp)
+// the fused preprocess of one frame into a given set of per-frame buffers, on a given stream
+static int run_preprocess(hkf_ctx* c, cudaStream_t stream, HkfFrameSet& F, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp)
 {
-    if (!c || !depth_mm || !fp) return HKF_ERR_ARG;
     unsigned n = c->cols[0] * c->rows[0];
     const uint16_t* src = depth_mm;
     if (!is_device) {
-        HKF_CUDA(c, cudaMemcpyAsync(c->depth_mm, depth_mm, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-        src = c->depth_mm;
+        HKF_CUDA(c, cudaMemcpyAsync(F.depth_mm, depth_mm, n * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+        src = F.depth_mm;
     }
     int radius; float ss, sd, thresh;
     bilateral_consts(fp->sigma_pixel, fp->sigma_depth, &radius, &ss, &sd, &thresh);
     if (radius < 0 || radius > 12) { c->err = "hkf_preprocess: bilateral radius out of range for the fused kernel"; return HKF_ERR_ARG; }
-    HKF_CUDA(c, cudaMemsetAsync(c->bounds.base, 0, c->bounds_zero_bytes, c->stream));
+    HKF_CUDA(c, cudaMemsetAsync(F.bounds.base, 0, c->bounds_zero_bytes, stream));
     static_assert(TILE_W == HKF_TILE_W && TILE_H == HKF_TILE_H, "preprocess tile = integration culling tile");
     const int ap = radius + 1;
     size_t smem = ((TILE_W + 2 * ap) * (TILE_H + 2 * ap) + (TILE_W + 2) * (TILE_H + 2)) * sizeof(float);
     dim3 b(TILE_W, TILE_H), g(div_up(c->cols[0], TILE_W), div_up(c->rows[0], TILE_H));
     const HkfCameraParams& cam = c->ip.depth_camera;
-    k_preprocess_fused<<<g, b, smem, c->stream>>>(src, c->raw_depth, c->trunc_depth, c->filtered_depth, c->new_v[0], c->new_n[0],
-                                                  (int)c->cols[0], (int)c->rows[0], radius, fp->trunc_min, fp->trunc_max, ss, sd, thresh,
-                                                  cam.cx, cam.cy, cam.fx, cam.fy, c->bounds);
+    k_preprocess_fused<<<g, b, smem, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, F.new_v[0], F.new_n[0],
+                                               (int)c->cols[0], (int)c->rows[0], radius, fp->trunc_min, fp->trunc_max, ss, sd, thresh,
+                                               cam.cx, cam.cy, cam.fx, cam.fy, F.bounds);
     HKF_LAUNCH_CHECK(c);
-    return hkf_pyramids_fused(c, c->new_v, c->new_n);
+    return hkf_pyramids_fused(c, F.new_v, F.new_n, stream);
+}
+
+static void current_set(hkf_ctx* c, HkfFrameSet* F)
+{
+    F->depth_mm = c->depth_mm; F->raw_depth = c->raw_depth; F->trunc_depth = c->trunc_depth; F->filtered_depth = c->filtered_depth;
+    for (int l = 0; l < HKF_MAX_LEVELS; ++l) { F->new_v[l] = c->new_v[l]; F->new_n[l] = c->new_n[l]; }
+    F->bounds = c->bounds;
+}
+static void make_current(hkf_ctx* c, const HkfFrameSet& F)
+{
+    c->depth_mm = F.depth_mm; c->raw_depth = F.raw_depth; c->trunc_depth = F.trunc_depth; c->filtered_depth = F.filtered_depth;
+    for (int l = 0; l < HKF_MAX_LEVELS; ++l) { c->new_v[l] = F.new_v[l]; c->new_n[l] = F.new_n[l]; }
+    c->bounds = F.bounds;
+}
+
+extern "C" int hkf_preprocess(hkf_ctx* c, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp)
+{
+    if (!c || !depth_mm || !fp) return HKF_ERR_ARG;
+    HkfFrameSet F; current_set(c, &F);
+    return run_preprocess(c, c->stream, F, depth_mm, is_device, fp);
+}
+
+// ---- frame pipelining: the NEXT frame is uploaded and preprocessed on a second stream into a second set of
+// per-frame buffers while the current frame is still being tracked / integrated / raycast (tracking is latency-bound
+// and leaves most SMs idle; the bilateral filter is arithmetic-bound and fills them).  hkf_swap_frame makes it current.
+static int alloc_back(hkf_ctx* c)
+{
+    if (c->back_allocated) return HKF_OK;
+    HkfFrameSet& B = c->back;
+    size_t n0 = (size_t)c->cols[0] * c->rows[0];
+    HKF_CUDA(c, cudaMalloc(&B.depth_mm, n0 * sizeof(uint16_t)));
+    HKF_CUDA(c, cudaMalloc(&B.raw_depth, n0 * sizeof(float)));
+    HKF_CUDA(c, cudaMalloc(&B.trunc_depth, n0 * sizeof(float)));
+    HKF_CUDA(c, cudaMalloc(&B.filtered_depth, n0 * sizeof(float)));
+    for (int l = 0; l < c->levels; ++l) {
+        size_t nb = (size_t)c->cols[l] * c->rows[l] * sizeof(float4);
+        HKF_CUDA(c, cudaMalloc(&B.new_v[l], nb)); HKF_CUDA(c, cudaMalloc(&B.new_n[l], nb));
+    }
+    B.bounds = c->bounds;
+    size_t nb = ((size_t)c->bounds.off_min[0] + (size_t)c->bounds.tiles_y * c->bounds.tx[0]) * sizeof(unsigned);
+    HKF_CUDA(c, cudaMalloc(&B.bounds.base, nb));
+    HKF_CUDA(c, cudaMemset(B.bounds.base, 0, nb));
+    {
+        int lo = 0, hi = 0;
+        HKF_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        HKF_CUDA(c, cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+    }
+    HKF_CUDA(c, cudaEventCreateWithFlags(&c->ev_pre_done, cudaEventDisableTiming));
+    HKF_CUDA(c, cudaEventCreateWithFlags(&c->ev_swap, cudaEventDisableTiming));
+    HKF_CUDA(c, cudaEventRecord(c->ev_swap, c->stream));
+    // HKF_PIPE_COMPUTE=1: run the next frame's kernels on the side stream as well (measured slower on B200: the
+    // bilateral blocks take the register file the tracking blocks need); default: upload only
+    const char* e = getenv("HKF_PIPE_COMPUTE");
+    c->pipe_compute = e && e[0] == '1';
+    c->back_allocated = true;
+    return HKF_OK;
+}
+
+extern "C" int hkf_preprocess_next(hkf_ctx* c, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp)
+{
+    if (!c || !depth_mm || !fp) return HKF_ERR_ARG;
+    int rc = alloc_back(c);
+    if (rc != HKF_OK) return rc;
+    // the back set was the current one until the last swap: everything enqueued before that swap may still read it
+    HKF_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_swap, 0));
+    c->back_src = depth_mm;
+    if (c->pipe_compute) {
+        rc = run_preprocess(c, c->stream2, c->back, depth_mm, is_device, fp);
+        if (rc != HKF_OK) return rc;
+    } else if (!is_device) {
+        // copy engine only: the upload overlaps the current frame, the kernels run on the main stream at the swap
+        unsigned n = c->cols[0] * c->rows[0];
+        HKF_CUDA(c, cudaMemcpyAsync(c->back.depth_mm, depth_mm, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream2));
+        c->back_src = c->back.depth_mm;
+    }
+    c->back_fp = *fp;
+    HKF_CUDA(c, cudaEventRecord(c->ev_pre_done, c->stream2));
+    c->back_valid = true;
+    return HKF_OK;
+}
+
+extern "C" int hkf_swap_frame(hkf_ctx* c)
+{
+    if (!c) return HKF_ERR_ARG;
+    if (!c->back_valid) { c->err = "hkf_swap_frame: no frame was prepared with hkf_preprocess_next"; return HKF_ERR_STATE; }
+    HKF_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_pre_done, 0));
+    HkfFrameSet cur; current_set(c, &cur);
+    make_current(c, c->back);
+    c->back = cur;
+    c->back_valid = false;
+    if (!c->pipe_compute) {
+        HkfFrameSet F; current_set(c, &F);
+        int rc = run_preprocess(c, c->stream, F, c->back_src, 1, &c->back_fp);
+        if (rc != HKF_OK) return rc;
+    }
+    HKF_CUDA(c, cudaEventRecord(c->ev_swap, c->stream));
+    return HKF_OK;
 }

@@ -182,6 +182,12 @@ int hkf_triangle_count(hkf_ctx* ctx, unsigned* n);
 /* decode + trunc + bilateral + vertices + normals + new-frame pyramids in two launches.
  * depth_mm: host (pinned or pageable) or device pointer, see hkf_upload_depth_mm. */
 int hkf_preprocess(hkf_ctx* ctx, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp);
+/* Frame pipelining: upload + preprocess the NEXT frame on a second stream into a second set of per-frame buffers
+ * while the current frame is still being tracked / integrated / raycast, then make it the current frame.  Same
+ * results as hkf_preprocess; hkf_swap_frame orders the main stream after the prepared frame.  A host buffer must
+ * stay valid until the swap. */
+int hkf_preprocess_next(hkf_ctx* ctx, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp);
+int hkf_swap_frame(hkf_ctx* ctx);
 /* set / get the device-resident pose (HKF_TRACK_OK is restored by set) */
 int hkf_set_pose(hkf_ctx* ctx, const HkfMat44* pose);
 /* whole CameraPoseFinderICP::estimateCameraPose (src/CameraPoseFinderICP.cpp:50-86) on the device:

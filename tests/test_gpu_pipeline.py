@@ -120,3 +120,35 @@ def test_tracking_failure_is_reported_and_skips_integration(pipeline):
     assert bits_equal(c.download(capi.BUF_VOLUME), vol0)
     assert c.download(capi.BUF_MODEL_NORMALS).any()
     c.close()
+
+
+def test_pipelined_frames_equal_sequential(pipeline):
+    """hkf_preprocess_next / hkf_swap_frame (next frame prepared on the side stream) changes nothing in the results"""
+    cfg = small_config(128)
+    want, wsts, c0 = run_fused(cfg, pipeline["frames"], 0)
+    vol0 = c0.download(capi.BUF_VOLUME)
+    c0.close()
+    from hybkinectfu_b200 import synth
+    frames = np.ascontiguousarray(pipeline["frames"], dtype=np.uint16)
+    c = capi.Context(cfg)
+    c.set_pose(synth.pose0(cfg.volume_size, cfg.trunc_min).astype(np.float32))
+    poses, sts = [], []
+    fb = frames[0].nbytes
+    for i in range(len(frames)):
+        if i == 0:
+            c.preprocess(frames[0])
+        else:
+            c.swap_frame()
+        if i + 1 < len(frames):
+            c.preprocess_next(frames.ctypes.data + (i + 1) * fb, False)
+        if i:
+            c.icp_track()
+        c.integrate_tracked(); c.raycast_tracked()
+        p, st = c.frame_result()
+        poses.append(p); sts.append(st)
+    assert (np.array(sts) == wsts).all() and bits_equal(np.stack(poses), want)
+    assert bits_equal(c.download(capi.BUF_VOLUME), vol0)
+    # a swap without a prepared frame is an error, not a silent no-op
+    with pytest.raises(capi.HkfError):
+        c.swap_frame()
+    c.close()
