@@ -50,6 +50,80 @@ struct IcpArgs {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// All-reduce of the 27 partial sums over peer memory (call from all threads of the block): this rank's sums go into
+// slot [seq & 1][rank] of every rank's mailbox as (value, iteration) words (one 64-bit P2P store each over NVLink),
+// every rank polls its own mailbox until all words of the iteration have arrived and adds them in RANK ORDER, so all
+// ranks continue with bit-identical sums and poses.
+__device__ __forceinline__ void icp_p2p_allreduce(const ShardPeers& peers, unsigned seq, float* s_sums, int warp, int lane)
+{
+    const int par = (int)(seq & 1u);
+    if (warp == 0) {
+        if (lane < HKF_SUMS) {
+            const unsigned long long word = ((unsigned long long)seq << 32) | __float_as_uint(s_sums[lane]);
+            for (int r = 0; r < peers.nranks; ++r)
+                *(volatile unsigned long long*)&peers.mail[r]->sums[par][peers.rank][lane] = word;
+        }
+        const ShardMailbox* mine = peers.mail[peers.rank];
+        bool ok = true;
+        float acc = 0.f;
+        if (lane < HKF_SUMS) {
+            const long long tw = clock64();
+            for (int r = 0; r < peers.nranks && ok; ++r) {
+                unsigned long long word;
+                while ((unsigned)((word = *(volatile const unsigned long long*)&mine->sums[par][r][lane]) >> 32) != seq)
+                    if (clock64() - tw > 4000000000ll) { ok = false; break; }     // ~2 s: a peer died; do not hang the GPU
+                const float v = __uint_as_float((unsigned)word);
+                acc = r == 0 ? v : __fadd_rn(acc, v);
+            }
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (lane < HKF_SUMS) s_sums[lane] = ok ? acc : __int_as_float(0x7fc00000);   // NaN sums -> tracking fails
+    }
+    __syncthreads();
+}
+
+// findCorrs + buildPointToPlaneSolverRows for one pixel (new-frame vertex v / normal n already loaded); the 7-float
+// solver row goes to shared memory, zero when there is no correspondence
+__device__ __forceinline__ void icp_pixel_row(const IcpArgs& A, const float* __restrict__ cur, const float* __restrict__ li,
+                                              const float4 n, const float4 v, bool ok, float (*s_row)[256], int t)
+{
+    // findCorrs + buildPointToPlaneSolverRows; r = 0 when there is no correspondence
+    ok = ok && !hkf_is_zero4(n);
+    // v_input_g = cur * v (lead-first), n_input_g = cur * n (lead-second): as contracted in the reference PTX
+    const float qx = hkf_row4<true>(cur[0], cur[1], cur[2], cur[3], v.x, v.y, v.z, v.w);
+    const float qy = hkf_row4<true>(cur[4], cur[5], cur[6], cur[7], v.x, v.y, v.z, v.w);
+    const float qz = hkf_row4<true>(cur[8], cur[9], cur[10], cur[11], v.x, v.y, v.z, v.w);
+    const float qw = hkf_row4<true>(cur[12], cur[13], cur[14], cur[15], v.x, v.y, v.z, v.w);
+    const float nix = hkf_row4<false>(cur[0], cur[1], cur[2], cur[3], n.x, n.y, n.z, n.w);
+    const float niy = hkf_row4<false>(cur[4], cur[5], cur[6], cur[7], n.x, n.y, n.z, n.w);
+    const float niz = hkf_row4<false>(cur[8], cur[9], cur[10], cur[11], n.x, n.y, n.z, n.w);
+    // v_cp = last_inv * v_input_g (lead-second); projective association, no z > 0 test (SURVEY.md quirk 5)
+    const float px = hkf_row4<false>(li[0], li[1], li[2], li[3], qx, qy, qz, qw);
+    const float py = hkf_row4<false>(li[4], li[5], li[6], li[7], qx, qy, qz, qw);
+    const float pz = hkf_row4<false>(li[8], li[9], li[10], li[11], qx, qy, qz, qw);
+    const int u = hkf_round_px(hkf_project1(px, A.fx, pz, A.cx));
+    const int w = hkf_round_px(hkf_project1(py, A.fy, pz, A.cy));
+    ok = ok && !(u < 0 || u >= A.cols || w < 0 || w >= A.rows);
+    const size_t midx = ok ? (size_t)w * A.cols + u : 0;
+    const float4 nt = ld_f4(A.model_n + midx);
+    const float4 p = ld_f4(A.model_v + midx);
+    ok = ok && !hkf_is_zero4(nt);
+    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
+    const float d = __fsqrt_rn(hkf_dot3(dx, dy, dz, dx, dy, dz));
+    const float sx = hkf_det2(nt.y, niz, nt.z, niy);
+    const float sy = hkf_det2(nt.z, nix, nt.x, niz);
+    const float sz = hkf_det2(nt.x, niy, nt.y, nix);
+    const float sn = __fsqrt_rn(hkf_dot3(sx, sy, sz, sx, sy, sz));
+    ok = ok && !(d > A.dist_thres || sn > A.sin_thres);
+    s_row[0][t] = ok ? hkf_det2(qy, nt.z, qz, nt.y) : 0.f;
+    s_row[1][t] = ok ? hkf_det2(qz, nt.x, qx, nt.z) : 0.f;
+    s_row[2][t] = ok ? hkf_det2(qx, nt.y, qy, nt.x) : 0.f;
+    s_row[3][t] = ok ? nt.x : 0.f;
+    s_row[4][t] = ok ? nt.y : 0.f;
+    s_row[5][t] = ok ? nt.z : 0.f;
+    s_row[6][t] = ok ? hkf_dot3(nt.x, nt.y, nt.z, dx, dy, dz) : 0.f;
+}
+
 // FROM_STATE: pose/status from device state; SOLVE: the last block also solves and advances the pose (single GPU).
 // Sharded ranks run <true,false> over their pixel-row band, allreduce st->sums, then k_icp_solve.
 template <bool FROM_STATE, bool SOLVE, bool P2P>
@@ -87,41 +161,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     if (!s_flag[0]) return;                    // a failed iteration ends the frame's tracking
     const float* cur = s_m; const float* li = s_m + 16;
 
-    // findCorrs + buildPointToPlaneSolverRows; r = 0 when there is no correspondence
-    ok = ok && !hkf_is_zero4(n);
-    // v_input_g = cur * v (lead-first), n_input_g = cur * n (lead-second): as contracted in the reference PTX
-    const float qx = hkf_row4<true>(cur[0], cur[1], cur[2], cur[3], v.x, v.y, v.z, v.w);
-    const float qy = hkf_row4<true>(cur[4], cur[5], cur[6], cur[7], v.x, v.y, v.z, v.w);
-    const float qz = hkf_row4<true>(cur[8], cur[9], cur[10], cur[11], v.x, v.y, v.z, v.w);
-    const float qw = hkf_row4<true>(cur[12], cur[13], cur[14], cur[15], v.x, v.y, v.z, v.w);
-    const float nix = hkf_row4<false>(cur[0], cur[1], cur[2], cur[3], n.x, n.y, n.z, n.w);
-    const float niy = hkf_row4<false>(cur[4], cur[5], cur[6], cur[7], n.x, n.y, n.z, n.w);
-    const float niz = hkf_row4<false>(cur[8], cur[9], cur[10], cur[11], n.x, n.y, n.z, n.w);
-    // v_cp = last_inv * v_input_g (lead-second); projective association, no z > 0 test (SURVEY.md quirk 5)
-    const float px = hkf_row4<false>(li[0], li[1], li[2], li[3], qx, qy, qz, qw);
-    const float py = hkf_row4<false>(li[4], li[5], li[6], li[7], qx, qy, qz, qw);
-    const float pz = hkf_row4<false>(li[8], li[9], li[10], li[11], qx, qy, qz, qw);
-    const int u = hkf_round_px(hkf_project1(px, A.fx, pz, A.cx));
-    const int w = hkf_round_px(hkf_project1(py, A.fy, pz, A.cy));
-    ok = ok && !(u < 0 || u >= A.cols || w < 0 || w >= A.rows);
-    const size_t midx = ok ? (size_t)w * A.cols + u : 0;
-    const float4 nt = ld_f4(A.model_n + midx);
-    const float4 p = ld_f4(A.model_v + midx);
-    ok = ok && !hkf_is_zero4(nt);
-    const float dx = __fsub_rn(p.x, qx), dy = __fsub_rn(p.y, qy), dz = __fsub_rn(p.z, qz);
-    const float d = __fsqrt_rn(hkf_dot3(dx, dy, dz, dx, dy, dz));
-    const float sx = hkf_det2(nt.y, niz, nt.z, niy);
-    const float sy = hkf_det2(nt.z, nix, nt.x, niz);
-    const float sz = hkf_det2(nt.x, niy, nt.y, nix);
-    const float sn = __fsqrt_rn(hkf_dot3(sx, sy, sz, sx, sy, sz));
-    ok = ok && !(d > A.dist_thres || sn > A.sin_thres);
-    s_r[tl][0][t] = ok ? hkf_det2(qy, nt.z, qz, nt.y) : 0.f;
-    s_r[tl][1][t] = ok ? hkf_det2(qz, nt.x, qx, nt.z) : 0.f;
-    s_r[tl][2][t] = ok ? hkf_det2(qx, nt.y, qy, nt.x) : 0.f;
-    s_r[tl][3][t] = ok ? nt.x : 0.f;
-    s_r[tl][4][t] = ok ? nt.y : 0.f;
-    s_r[tl][5][t] = ok ? nt.z : 0.f;
-    s_r[tl][6][t] = ok ? hkf_dot3(nt.x, nt.y, nt.z, dx, dy, dz) : 0.f;
+    icp_pixel_row(A, cur, li, n, v, ok, s_r[tl], t);
     __syncthreads();
 
     // ---- first stage: 2 x 27 (tile, sum) jobs over 16 warps
@@ -148,36 +188,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     __threadfence();
     second_stage_all<ICP_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
     __syncthreads();
-    if (P2P) {
-        // All-reduce of the 27 partial sums over peer memory: this rank's sums go into slot [seq & 1][rank] of every
-        // rank's mailbox as (value, iteration) words (one 64-bit P2P store each over NVLink), every rank polls its own
-        // mailbox until all words of the iteration have arrived and adds them in RANK ORDER, so all ranks continue
-        // with bit-identical sums and poses.
-        const int par = (int)(A.seq & 1u);
-        if (warp == 0) {
-            if (lane < HKF_SUMS) {
-                const unsigned long long word = ((unsigned long long)A.seq << 32) | __float_as_uint(s_sums[lane]);
-                for (int r = 0; r < A.peers.nranks; ++r)
-                    *(volatile unsigned long long*)&A.peers.mail[r]->sums[par][A.peers.rank][lane] = word;
-            }
-            const ShardMailbox* mine = A.peers.mail[A.peers.rank];
-            bool ok = true;
-            float acc = 0.f;
-            if (lane < HKF_SUMS) {
-                const long long tw = clock64();
-                for (int r = 0; r < A.peers.nranks && ok; ++r) {
-                    unsigned long long word;
-                    while ((unsigned)((word = *(volatile const unsigned long long*)&mine->sums[par][r][lane]) >> 32) != A.seq)
-                        if (clock64() - tw > 4000000000ll) { ok = false; break; }     // ~2 s: a peer died; do not hang the GPU
-                    const float v = __uint_as_float((unsigned)word);
-                    acc = r == 0 ? v : __fadd_rn(acc, v);
-                }
-            }
-            ok = __all_sync(0xffffffffu, ok);
-            if (lane < HKF_SUMS) s_sums[lane] = ok ? acc : __int_as_float(0x7fc00000);   // NaN sums -> tracking fails
-        }
-        __syncthreads();
-    }
+    if (P2P) icp_p2p_allreduce(A.peers, A.seq, s_sums, warp, lane);
     const long long t3 = clock64();
     if (threadIdx.x >= 64 && threadIdx.x < 64 + HKF_SUMS) st->sums[threadIdx.x - 64] = s_sums[threadIdx.x - 64];
     if (threadIdx.x == 64) st->ticket = 0;
@@ -213,6 +224,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     }
 }
 
+
 // start of a frame's tracking: cur = pose, last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63)
 __global__ void k_track_begin(HkfDeviceState* st)
 {
@@ -220,7 +232,7 @@ __global__ void k_track_begin(HkfDeviceState* st)
         st->cur[threadIdx.x] = st->pose[threadIdx.x];
         st->last_inv[threadIdx.x] = st->pose_inv[threadIdx.x];
     }
-    if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->sdf_done = 0; }
+    if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->gen = 0; st->sdf_done = 0; }
 }
 
 static void fill_icp_args(hkf_ctx* c, int level, const HkfCameraParams* cam, float dist_thres, float sin_thres, IcpArgs* A)
@@ -310,35 +322,49 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
     HKF_LAUNCH_CHECK(c);
     const int* iters = icp_schedule(c->levels);
     const bool sharded = c->nranks > 1;
+    if (!sharded || c->p2p) {
+        // One launch per iteration, chained with programmatic dependent launch: the next iteration's blocks become
+        // resident and issue their pose-independent loads while this iteration's last block is still reducing and
+        // solving.  (A single persistent cooperative kernel with a ticket/generation grid barrier was measured slower:
+        // 17.4 vs 13.7 us per iteration.)
+        for (int l = c->levels - 1; l >= 0; --l) {
+            HkfCameraParams cam; hkf_level_camera(&c->ip.depth_camera, l, &cam);
+            IcpArgs A; fill_icp_args(c, l, &cam, fp->icp_dist_thres, fp->icp_norm_sin_thres, &A);
+            A.angle_shake = fp->icp_angle_shake; A.dist_shake = fp->icp_dist_shake;
+            if (sharded) {      // this rank's band of pixel rows
+                A.y0 = (int)((long long)A.rows * c->rank / c->nranks);
+                A.y1 = (int)((long long)A.rows * (c->rank + 1) / c->nranks);
+                A.peers = c->peers;
+            }
+            for (int it = 0; it < iters[l]; ++it) {
+                A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(div_up(A.ntiles, ICP_TILES)); cfg.blockDim = dim3(ICP_THREADS); cfg.stream = c->stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                if (sharded) { A.seq = ++c->shard_seq; cudaLaunchKernelEx(&cfg, k_icp<true, true, true>, A, c->st); }
+                else cudaLaunchKernelEx(&cfg, k_icp<true, true, false>, A, c->st);
+                HKF_LAUNCH_CHECK(c);
+            }
+        }
+        return HKF_OK;
+    }
+    // sharded without peer memory: per-iteration launches with an NCCL allreduce in between
     for (int l = c->levels - 1; l >= 0; --l) {
         HkfCameraParams cam; hkf_level_camera(&c->ip.depth_camera, l, &cam);
         IcpArgs A; fill_icp_args(c, l, &cam, fp->icp_dist_thres, fp->icp_norm_sin_thres, &A);
         A.angle_shake = fp->icp_angle_shake; A.dist_shake = fp->icp_dist_shake;
-        if (sharded) {      // this rank's band of pixel rows
-            A.y0 = (int)((long long)A.rows * c->rank / c->nranks);
-            A.y1 = (int)((long long)A.rows * (c->rank + 1) / c->nranks);
-        }
+        A.y0 = (int)((long long)A.rows * c->rank / c->nranks);
+        A.y1 = (int)((long long)A.rows * (c->rank + 1) / c->nranks);
         for (int it = 0; it < iters[l]; ++it) {
             A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
-            if (sharded && !c->p2p) {
-                k_icp<true, false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
-                HKF_LAUNCH_CHECK(c);
-                rc = hkf_shard_allreduce_sums(c);
-                if (rc != HKF_OK) return rc;
-                k_icp_solve<<<1, 64, 0, c->stream>>>(c->st, A.angle_shake, A.dist_shake, A.is_last);
-                HKF_LAUNCH_CHECK(c);
-                continue;
-            }
-            // programmatic dependent launch: the next iteration's blocks become resident and issue their
-            // pose-independent loads while this iteration's last block is still reducing and solving
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(div_up(A.ntiles, ICP_TILES)); cfg.blockDim = dim3(ICP_THREADS); cfg.stream = c->stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            if (sharded) { A.peers = c->peers; A.seq = ++c->shard_seq; cudaLaunchKernelEx(&cfg, k_icp<true, true, true>, A, c->st); }
-            else cudaLaunchKernelEx(&cfg, k_icp<true, true, false>, A, c->st);
+            k_icp<true, false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+            HKF_LAUNCH_CHECK(c);
+            rc = hkf_shard_allreduce_sums(c);
+            if (rc != HKF_OK) return rc;
+            k_icp_solve<<<1, 64, 0, c->stream>>>(c->st, A.angle_shake, A.dist_shake, A.is_last);
             HKF_LAUNCH_CHECK(c);
         }
     }
