@@ -282,6 +282,98 @@ def cpu_baseline(cfg, frames, nframes):
             "stage_seconds": {"preprocess": times[0], "track": times[1], "integrate": times[2], "raycast": times[3]}}
 
 
+# ---------------------------------------------------------------------------------------------- C1 / C3 / C5
+def run_config(args, rank, world, local_rank):
+    """The other BASELINE.json configs on one GPU (per rank), device-resident frames, CUDA-event timed:
+    c1  integration-only, 100 frames 640x480, poses from file (ground truth), 256^3
+    c3  SDF direct tracking (CameraPoseFinderSDF) + integrate + raycast on 512^3, then marching-cubes export
+    c5  1280x960 sequences into 512^3, ICP pipeline, one independent sequence per GPU"""
+    import dataclasses
+    import torch
+    from hybkinectfu_b200 import capi, synth
+    torch.cuda.set_device(local_rank)
+    wl = args.workload
+    W, K = args.warmup, args.steps
+    if wl == "c1":
+        cfg = dataclasses.replace(bench_cfg(256), max_triangles=1)
+        W, K = 0, min(K, 100) if K != 200 else 100
+        frames, gt = make_sequence(100)
+    elif wl == "c3":
+        cfg = dataclasses.replace(bench_cfg(512), max_triangles=4000000)
+        frames, gt = make_sequence(W + K)
+    else:
+        cam = synth.Camera().scaled(1280, 960)
+        cfg = dataclasses.replace(bench_cfg(512), cols=1280, rows=960, cx=cam.cx, cy=cam.cy, fx=cam.fx, fy=cam.fy, max_triangles=1)
+        frames, gt = make_sequence(W + K, phase=2 * np.pi * rank / 8.0, cols=1280, rows=960)
+    ctx = capi.Context(cfg, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.lib.hkf_stream(ctx._h), device=local_rank)
+    dev = torch.from_numpy(frames.view(np.int16)).to(f"cuda:{local_rank}")
+    fb = frames[0].nbytes
+    ctx.set_pose(synth.pose0().astype(np.float32))
+    gt32 = gt.astype(np.float32)
+
+    def frame(i):
+        ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev.data_ptr() + i * fb, 1, ctx.fp), "hkf_preprocess")
+        if wl == "c1":
+            ctx.set_pose(gt32[i])
+        elif i:
+            ctx.sdf_track() if wl == "c3" else ctx.icp_track()
+        ctx.integrate_tracked()
+        if wl != "c1":
+            ctx.raycast_tracked()
+
+    for i in range(W):
+        frame(i)
+    ctx.sync(); torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches()
+    n_upd = 0
+    if wl == "c1":
+        # hkf_set_pose synchronises (host-provided poses): time the integration launches themselves
+        tot = 0.0
+        for i in range(K):
+            ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev.data_ptr() + i * fb, 1, ctx.fp), "hkf_preprocess")
+            ctx.set_pose(gt32[i])
+            n_upd += ctx.count_updates(gt32[i])
+            ev0.record(stream); ctx.integrate_tracked(); ev1.record(stream); ctx.sync()
+            tot += ev0.elapsed_time(ev1) * 1e-3
+        t = tot
+    else:
+        ev0.record(stream)
+        for k in range(K):
+            frame(W + k)
+        ev1.record(stream)
+        ctx.sync(); torch.cuda.synchronize()
+        t = ev0.elapsed_time(ev1) * 1e-3
+    launches = ctx.launches() - l0
+    pose, st = ctx.frame_result()
+    extra = {"track_status_last": int(st), "pose_err_vs_gt_m": float(np.abs(pose[:3, 3] - gt[(W + K - 1) % len(gt)][:3, 3]).max())}
+    if wl == "c1":
+        peak, _ = measured_hbm_peak()
+        gbs = (16.0 * n_upd + 4.0 * cfg.cols * cfg.rows * K) / t / 1e9
+        extra.update({"integration_GBps_algorithmic": gbs, "frac_of_hbm_peak": gbs / peak, "n_upd_mean": n_upd / K})
+    if wl == "c3":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); ntri = ctx.marching_cubes(); e1.record(stream); ctx.sync()
+        extra.update({"marching_cubes_triangles": int(ntri), "marching_cubes_ms": e0.elapsed_time(e1)})
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([t], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    names = {"c1": "C1 integration-only: 100 frames 640x480, poses from file, 256^3 (metric = integrations/s)",
+             "c3": "C3 SDF direct tracking (<= 6 Gauss-Newton iterations) + integrate + raycast, 512^3, marching-cubes export at the end",
+             "c5": f"C5 1280x960 sequences into 512^3, ICP pipeline, {world} independent replica(s)"}
+    out = {"metric": "fused frames/s" if wl != "c1" else "TSDF integrations/s", "value": world * K / t, "unit": "frames/s", "n_gpus": world, "steps": K,
+           "warmup": W, "ms_per_step": t * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic analytic scene, 16-bit mm depth", "config": dict({"workload": names[wl]}, **extra), "gpu_launches": int(launches)}
+    ctx.close()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- C4: z-slab sharded
 def run_c4(args, rank, world, local_rank):
     """BASELINE.json configs[3]: ONE 640x480 sequence into a 1024^3 volume, z-slab-sharded over `world` GPUs
@@ -428,7 +520,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"], help="c2: BASELINE configs[1] (replicas at N>1); c4: z-slab-sharded single sequence")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c2 (default): BASELINE configs[1], replicas at N>1; c4: z-slab-sharded single sequence; c1/c3/c5: the other BASELINE configs")
     ap.add_argument("--c4-resolution", type=int, default=1024)
     args = ap.parse_args()
     if args.warmup < 1:
@@ -446,7 +539,12 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    out = run_c4(args, rank, world, local_rank) if args.workload == "c4" else run_ours(args, rank, world, local_rank)
+    if args.workload == "c4":
+        out = run_c4(args, rank, world, local_rank)
+    elif args.workload in ("c1", "c3", "c5"):
+        out = run_config(args, rank, world, local_rank)
+    else:
+        out = run_ours(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
