@@ -436,11 +436,15 @@ def run_c4(args, rank, world, local_rank):
         ctx.sync()
         stage += np.array([ev[a].elapsed_time(ev[a + 1]) * 1e3 for a in range(4)])
     stage /= max(nst, 1)
+    all_stage = [stage.tolist()]
     if world > 1:
         import torch.distributed as dist
         tt = torch.tensor([t], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t = float(tt[0])
+        g = [torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}") for _ in range(world)]
+        dist.all_gather(g, torch.tensor(stage, dtype=torch.float64, device=f"cuda:{local_rank}"))
+        all_stage = [x.cpu().tolist() for x in g]
     halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
     slabs = shard.balanced_slab_ranges(cfg, world, halo) if world > 1 else shard.slab_ranges(cfg.resolution, 1, 0)
     out = {"metric": f"fused frames/s at 640x480 into {cfg.resolution}^3 TSDF, z-slab-sharded (ICP + integrate + raycast)", "value": K / t,
@@ -449,6 +453,8 @@ def run_c4(args, rank, world, local_rank):
            "config": {"workload": f"C4: one 640x480 sequence, {cfg.resolution}^3 volume over 2 m, z-slabs over {world} GPU(s), halo {halo if world > 1 else 0} planes",
                       "owned_planes_per_rank": [s[1] - s[0] for s in slabs], "stored_planes_per_rank": [s[3] - s[2] for s in slabs], "track_status_last": int(st),
                       "rank0_stage_us": {"preprocess": float(stage[0]), "icp": float(stage[1]), "integrate": float(stage[2]), "raycast+composite": float(stage[3])},
+                      "integrate_us_per_rank": [round(x[2], 1) for x in all_stage],
+                      "note": "per-stage times include waiting for the slowest rank at the next exchange (ICP sums, raycast compositing)",
                       "pose_err_vs_gt_m": float(np.abs(pose[:3, 3] - gt[W + K - 1][:3, 3]).max())},
            "gpu_launches": int(launches)}
     ctx.close()
@@ -535,6 +541,7 @@ def main():
             print(json.dumps(out), flush=True)
         return
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("HKF_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

@@ -62,15 +62,38 @@ def plane_work(cfg, pose=None, samples: int = 48) -> np.ndarray:
 
 
 def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int = 8):
-    """slab_ranges with boundaries chosen so that every rank gets the same share of plane_work (the view frustum
-    widens with depth: equal-thickness slabs are not equal work)"""
+    """slab_ranges with boundaries chosen so that every rank gets the same share of plane_work over the planes it
+    STORES (owned + halo: the halo is integrated and marched redundantly, so thin slabs cost more than they own).
+    The view frustum widens with depth: equal-thickness slabs are not equal work."""
     R = cfg.resolution
-    cum = np.concatenate([[0.0], np.cumsum(plane_work(cfg, pose))])
-    cuts = [0]
-    for r in range(1, nranks):
-        z = int(np.searchsorted(cum, cum[-1] * r / nranks))
-        cuts.append(min(max(z, cuts[-1] + min_planes), R - min_planes * (nranks - r)))
-    cuts.append(R)
+    if nranks == 1:
+        return [(0, R, 0, R)]
+    w = plane_work(cfg, pose)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+
+    def stored_cost(z0, z1):
+        return cum[min(z1 + halo, R)] - cum[max(z0 - halo, 0)]
+
+    def greedy(limit):
+        cuts, z0 = [0], 0
+        for r in range(nranks - 1):
+            z1 = z0 + min_planes
+            while z1 < R - min_planes * (nranks - 1 - r) and stored_cost(z0, z1 + 1) <= limit:
+                z1 += 1
+            cuts.append(z1)
+            z0 = z1
+        cuts.append(R)
+        return cuts
+
+    lo, hi = 0.0, float(cum[-1])
+    for _ in range(40):                      # smallest per-rank budget for which the last slab fits too
+        mid = 0.5 * (lo + hi)
+        c = greedy(mid)
+        if stored_cost(c[-2], R) <= mid:
+            hi = mid
+        else:
+            lo = mid
+    cuts = greedy(hi)
     return [(cuts[r], cuts[r + 1], max(cuts[r] - halo, 0), min(cuts[r + 1] + halo, R)) for r in range(nranks)]
 
 
