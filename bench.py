@@ -401,6 +401,8 @@ def run_c4(args, rank, world, local_rank):
             ctx.icp_track()
         ctx.integrate_tracked()
         ctx.raycast_tracked()
+        if world > 1 and os.environ.get("HKF_SHARD_MANUAL_COMPOSITE") == "1":
+            ctx._ck(ctx.lib.hkf_shard_composite_raycast(ctx._h), "composite")
 
     def barrier():
         if world > 1:
@@ -423,6 +425,8 @@ def run_c4(args, rank, world, local_rank):
     pose, st = ctx.frame_result()
     # per-stage CUDA-event times of this rank (a few extra frames of the periodic sequence, untimed above)
     stage = np.zeros(4)
+    comp_us = 0.0
+    manual_composite = world > 1 and os.environ.get("HKF_SHARD_MANUAL_COMPOSITE") == "1"
     nst = min(10, W + K - 1)
     for j in range(nst):
         i = 1 + j
@@ -432,9 +436,15 @@ def run_c4(args, rank, world, local_rank):
         ev[1].record(stream)
         ctx.icp_track(); ev[2].record(stream)
         ctx.integrate_tracked(); ev[3].record(stream)
-        ctx.raycast_tracked(); ev[4].record(stream)
+        ctx.raycast_tracked()
+        if manual_composite:
+            evc = torch.cuda.Event(enable_timing=True); evc.record(stream)
+            ctx._ck(ctx.lib.hkf_shard_composite_raycast(ctx._h), "composite")
+        ev[4].record(stream)
         ctx.sync()
         stage += np.array([ev[a].elapsed_time(ev[a + 1]) * 1e3 for a in range(4)])
+        if manual_composite:
+            comp_us += evc.elapsed_time(ev[4]) * 1e3
     stage /= max(nst, 1)
     all_stage = [stage.tolist()]
     if world > 1:
@@ -453,7 +463,7 @@ def run_c4(args, rank, world, local_rank):
            "config": {"workload": f"C4: one 640x480 sequence, {cfg.resolution}^3 volume over 2 m, z-slabs over {world} GPU(s), halo {halo if world > 1 else 0} planes",
                       "owned_planes_per_rank": [s[1] - s[0] for s in slabs], "stored_planes_per_rank": [s[3] - s[2] for s in slabs], "track_status_last": int(st),
                       "rank0_stage_us": {"preprocess": float(stage[0]), "icp": float(stage[1]), "integrate": float(stage[2]), "raycast+composite": float(stage[3])},
-                      "integrate_us_per_rank": [round(x[2], 1) for x in all_stage],
+                      "integrate_us_per_rank": [round(x[2], 1) for x in all_stage], "rank0_composite_us": comp_us / max(nst, 1) if manual_composite else None,
                       "note": "per-stage times include waiting for the slowest rank at the next exchange (ICP sums, raycast compositing)",
                       "pose_err_vs_gt_m": float(np.abs(pose[:3, 3] - gt[W + K - 1][:3, 3]).max())},
            "gpu_launches": int(launches)}

@@ -48,7 +48,8 @@ struct HkfDeviceState {
     int   frame_valid;       // 0 until the first frame has been integrated
     unsigned dmax_bits;      // max valid truncated depth of the current frame (float bits)
     unsigned ticket;         // last-block-done counter for the solver kernels
-    unsigned gen;            // generation word of the persistent tracking kernel's grid barrier
+    unsigned gen;            // (spare)
+    unsigned comp_go;        // raycast compositing: epoch that block 0 has released to the other blocks
     unsigned mc_count;       // marching-cubes triangle counter
     unsigned pad;
     unsigned long long upd_count;

@@ -321,7 +321,10 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
     k_track_begin<<<1, 32, 0, c->stream>>>(c->st);
     HKF_LAUNCH_CHECK(c);
     const int* iters = icp_schedule(c->levels);
-    const bool sharded = c->nranks > 1;
+    // HKF_SHARD_ICP=replicated: every rank evaluates the whole image (no exchange at all; the poses are bit-identical
+    // because inputs and arithmetic are).  Default in sharded mode: banded rows + all-reduce of the 27 sums.
+    static const bool replicated = getenv("HKF_SHARD_ICP") && !strcmp(getenv("HKF_SHARD_ICP"), "replicated");
+    const bool sharded = c->nranks > 1 && !replicated;
     if (!sharded || c->p2p) {
         // One launch per iteration, chained with programmatic dependent launch: the next iteration's blocks become
         // resident and issue their pose-independent loads while this iteration's last block is still reducing and

@@ -39,13 +39,6 @@ __global__ void __launch_bounds__(256)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
 {
-    if (SLAB && A.mailbox != nullptr) {
-        // peers read this rank's keys / payload of the previous epoch straight from its memory: do not overwrite
-        // them before every peer has finished compositing that epoch
-        if (threadIdx.x == 0)
-            for (int r = 0; r < A.nranks; ++r) shard_wait_ge(&A.mailbox->done[r], A.epoch - 1u);
-        __syncthreads();
-    }
     // 16x16 pixel block, warps as 8x4 patches
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -225,6 +218,8 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     else k_raycast<true, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
     HKF_LAUNCH_CHECK(c);
     // sharded volume: nearest-hit compositing of the per-slab partial raycasts -> full model maps on every rank
-    if (c->nranks > 1) return hkf_shard_composite_raycast(c);
+    // (HKF_SHARD_MANUAL_COMPOSITE=1: the caller invokes hkf_shard_composite_raycast itself, e.g. to time it separately)
+    static const bool manual = getenv("HKF_SHARD_MANUAL_COMPOSITE") && getenv("HKF_SHARD_MANUAL_COMPOSITE")[0] == '1';
+    if (c->nranks > 1 && !manual) return hkf_shard_composite_raycast(c);
     return HKF_OK;
 }

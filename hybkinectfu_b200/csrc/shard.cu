@@ -141,45 +141,68 @@ extern "C" int hkf_shard_connect(hkf_ctx* c, const void* all_handles, int nranks
     return HKF_OK;
 }
 
-// One kernel composites the per-slab raycasts: a barrier over mailbox flags (every rank's keys and payload of this
-// epoch are complete), then per pixel the minimum key over ranks read straight from peer memory and, where another
-// rank won with a successful refinement, that rank's vertex/normal.  In place: a rank only overwrites pixels it did
-// not win, and nobody reads a loser's payload.
+// One kernel composites the per-slab raycasts.  Block 0 is the only one that talks to the peers' flags: it announces
+// that this rank's keys / payload of the epoch are complete, waits until every rank has announced the same, and
+// releases the other blocks through a device-local word (one system-scope fence per launch instead of one per block
+// and peer).  Then, per pixel, the minimum key over ranks is read straight from peer memory and, where another rank
+// won with a successful refinement, that rank's vertex/normal.  In place: a rank only overwrites pixels it did not
+// win, and nobody reads a loser's payload.  The last block to finish tells the peers that this rank is done reading
+// and waits for the same from them, so the next raycast may overwrite keys and payload without any further check.
 __global__ void __launch_bounds__(256)
 k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ out_n, unsigned npix, unsigned epoch, HkfDeviceState* st)
 {
     __shared__ int s_ok;
     if (threadIdx.x == 0) {
         bool ok = true;
-        if (blockIdx.x == 0)
-            for (int r = 0; r < P.nranks; ++r) shard_signal(&P.mail[r]->ready[P.rank], epoch);
-        for (int r = 0; r < P.nranks; ++r) ok = shard_wait_ge(&P.mail[P.rank]->ready[r], epoch) && ok;
+        if (blockIdx.x == 0) {
+            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->ready[P.rank] = epoch;    // stream order: the raycast is complete
+            const long long t0 = clock64();
+            for (int r = 0; r < P.nranks && ok; ++r)
+                while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->ready[r] - epoch) < 0)
+                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }                          // ~2 s: a peer died
+            __threadfence_system();
+            *(volatile unsigned*)&st->comp_go = ok ? epoch : (epoch | 0x80000000u);
+        } else {
+            unsigned g;
+            const long long t0 = clock64();
+            while ((int)(((g = *(volatile const unsigned*)&st->comp_go) & 0x7fffffffu) - epoch) < 0)
+                if (clock64() - t0 > 6000000000ll) { g = 0x80000000u; break; }
+            ok = !(g & 0x80000000u);
+            __threadfence();
+        }
         s_ok = ok;
     }
     __syncthreads();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (s_ok && i < npix) {
+        // peer memory is read through L2 only (never a stale L1 line); all loads are issued before the first compare
+        unsigned long long k[HKF_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) k[r] = r < P.nranks ? __ldcg(P.keys[r] + i) : ~0ull;
         unsigned long long best = ~0ull;
-        for (int r = 0; r < P.nranks; ++r) {
-            const unsigned long long k = __ldcv(P.keys[r] + i);       // peer memory: never from a stale cache line
-            best = k < best ? k : best;
-        }
+#pragma unroll
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) best = k[r] < best ? k[r] : best;
         const int w = (int)(best & 0xffu);
         if (best == ~0ull || !((best >> 8) & 1ull)) {
             out_v[i] = make_float4(0.f, 0.f, 0.f, 0.f); out_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else if (w != P.rank) {
-            out_v[i] = __ldcv(P.v[w] + i); out_n[i] = __ldcv(P.n[w] + i);
+            out_v[i] = __ldcg(P.v[w] + i); out_n[i] = __ldcg(P.n[w] + i);
         }
     }
     // everything this rank reads from its peers for this epoch has been read
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         const unsigned t = atomicAdd(&st->ticket, 1u);
         if (t == gridDim.x - 1) {
             st->ticket = 0;
             if (!s_ok) st->track_status = HKF_TRACK_SINGULAR;
-            for (int r = 0; r < P.nranks; ++r) shard_signal(&P.mail[r]->done[P.rank], epoch);
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->done[P.rank] = epoch;
+            const long long t0 = clock64();
+            for (int r = 0; r < P.nranks; ++r)
+                while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->done[r] - epoch) < 0)
+                    if (clock64() - t0 > 4000000000ll) break;
         }
     }
 }
