@@ -6,7 +6,7 @@
 // (src/CameraPoseFinderSDF.cpp:44-106) including the se(3) exponential map
 // (src/utils/eigen_utils.cpp:84-127).
 //
-// Same tile/lane mapping and bit-identical reduction trees as icp.cu.  The 104 voxel reads per pixel hit
+// Same thread-per-pixel tiles and bit-identical reduction trees as icp.cu.  The 104 voxel reads per pixel hit
 // packed 8-byte voxels (two sectors per trilinear corner pair instead of the reference's 12-byte AoS
 // stride) and all eight loads of an evaluation are issued together.  The six rotation-perturbed
 // transforms, which the reference builds on the host every iteration (:118-133), are built once per
@@ -74,21 +74,31 @@ __device__ __forceinline__ void sdf_row(const SdfArgs& A, const float* cur, cons
     r[6] = sdf0;
 }
 
-#define SDF_WARPS 4
+#define SDF_TILES 2
+#define SDF_THREADS (SDF_TILES * 256)
+#define SDF_WARPS (SDF_THREADS / 32)
 
+// One thread per depth pixel, two 16x16 tiles per block (the structure of icp.cu): the 13 trilinear evaluations of
+// a pixel are independent gathers, so thread-per-pixel puts 8x more of them in flight than the earlier
+// warp-per-tile mapping; the 7-float rows go through shared memory and the 27 sums are folded with the reference's
+// trees exactly as in the ICP kernel.  Launches are chained with programmatic dependent launch.
 template <bool FROM_STATE>
-__global__ void __launch_bounds__(SDF_WARPS * 32)
+__global__ void __launch_bounds__(SDF_THREADS, 2)
 k_sdf(SdfArgs A, HkfDeviceState* st)
 {
+    __shared__ float s_r[SDF_TILES][7][256];
     __shared__ float s_T[6][16];
     __shared__ float s_cur[16];
     __shared__ float s_sums[HKF_SUMS];
-    __shared__ int s_last;
+    __shared__ int s_flag[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (FROM_STATE && (st->track_status != HKF_TRACK_OK || st->sdf_done)) return;
-
-    if (threadIdx.x < 16) s_cur[threadIdx.x] = FROM_STATE ? st->cur[threadIdx.x] : A.cur[threadIdx.x];
+    const int tl = threadIdx.x >> 8, t = threadIdx.x & 255;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x < 16) s_cur[threadIdx.x] = FROM_STATE ? __ldcg(&st->cur[threadIdx.x]) : A.cur[threadIdx.x];
+    if (threadIdx.x == 32) s_flag[0] = FROM_STATE ? (__ldcg(&st->track_status) == HKF_TRACK_OK && !__ldcg(&st->sdf_done)) : 1;
     __syncthreads();
+    if (!s_flag[0]) return;
     if (threadIdx.x < 6) {
         // delta = I with one antisymmetric pair set to -/+ w_h, T = delta * cur (host Mat44 product, no FMA)
         const int neg[6] = { 6, 9, 8, 2, 1, 4 }, pos[6] = { 9, 6, 2, 8, 4, 1 };
@@ -103,40 +113,35 @@ k_sdf(SdfArgs A, HkfDeviceState* st)
     }
     __syncthreads();
 
-    const int tile = blockIdx.x * SDF_WARPS + warp;
-    if (tile < A.ntiles) {
+    {
+        const int tile = blockIdx.x * SDF_TILES + tl;
         const int bx = tile % A.gx, by = tile / A.gx;
-        float r[8][7];
+        float rr[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) rr[k] = 0.f;
+        // the reference has no image bounds guard (fine for multiples of 16); out-of-image pixels add 0
+        if (tile < A.ntiles) sdf_row(A, s_cur, s_T, bx * 16 + (t & 15), by * 16 + (t >> 4), rr);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s_r[tl][k][t] = rr[k];
+    }
+    __syncthreads();
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const int tid = lane + 32 * j;
-            float rr[7];
-            sdf_row(A, s_cur, s_T, bx * 16 + (tid & 15), by * 16 + (tid >> 4), rr);
-#pragma unroll
-            for (int k = 0; k < 7; ++k) r[j][k] = rr[k];
-        }
-        int shift = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = i; j < 7; ++j) {
-                float p[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) p[k] = __fmul_rn(r[k][i], r[k][j]);
-                const float c = tile_tree(p);
-                if (lane == 0) A.partials[(size_t)shift * A.ntiles + tile] = c;
-                ++shift;
-            }
+    for (int job = warp; job < SDF_TILES * HKF_SUMS; job += SDF_WARPS) {
+        const int jt = job / HKF_SUMS, k = job - jt * HKF_SUMS;
+        const int tile2 = blockIdx.x * SDF_TILES + jt;
+        if (tile2 >= A.ntiles) break;
+        const float c = tile_sum_from_rows(s_r[jt], k, lane);
+        if (lane == 0) __stcg(A.partials + (size_t)k * A.ntiles + tile2, c);
     }
 
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        unsigned tk = atomicAdd(&st->ticket, 1u);
+        s_flag[1] = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_flag[1]) return;
     __threadfence();
     second_stage_all<SDF_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
     __syncthreads();
@@ -193,7 +198,7 @@ extern "C" int hkf_cal_sdf_solver_params(hkf_ctx* c, const HkfCameraParams* cam,
     if (cam->cols != c->cols[0] || cam->rows != c->rows[0]) { c->err = "camera size mismatch"; return HKF_ERR_ARG; }
     SdfArgs A; int rc = fill_sdf_args(c, cam, &A); if (rc) return rc;
     memcpy(A.cur, cur->m, 64);
-    k_sdf<false><<<div_up(A.ntiles, SDF_WARPS), SDF_WARPS * 32, 0, c->stream>>>(A, c->st);
+    k_sdf<false><<<div_up(A.ntiles, SDF_TILES), SDF_THREADS, 0, c->stream>>>(A, c->st);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -208,7 +213,13 @@ extern "C" int hkf_sdf_track(hkf_ctx* c, const HkfFrameParams* fp)
     if (fp->sdf_max_iter == 0) return HKF_OK;          // while (iter < 0) never runs: pose unchanged
     for (unsigned it = 0; it < fp->sdf_max_iter; ++it) {
         A.is_last = (it == fp->sdf_max_iter - 1) ? 1 : 0;
-        k_sdf<true><<<div_up(A.ntiles, SDF_WARPS), SDF_WARPS * 32, 0, c->stream>>>(A, c->st);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(div_up(A.ntiles, SDF_TILES)); cfg.blockDim = dim3(SDF_THREADS); cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_sdf<true>, A, c->st);
         HKF_LAUNCH_CHECK(c);
     }
     return HKF_OK;
