@@ -3,6 +3,7 @@
 #include <iostream>
 #include "AppParamsProducer.h"
 #include "CudaDeviceDataMan.h"
+#include "DataSourceProducerRGBDDataset.h"
 #include "DataSourceProducerSynthetic.h"
 
 bool MainController::init(const std::string& config_filename, int device)
@@ -11,8 +12,9 @@ bool MainController::init(const std::string& config_filename, int device)
     if (!AppParamsProducer::readParams(config_filename)) { _err = "cannot read " + config_filename; return false; }
     if (!CudaDeviceDataMan::instance()->init(device)) { _err = "device init failed: " + CudaDeviceDataMan::instance()->lastError(); return false; }
     const SwitchParams& sw = AppParams::instance()->_switch_params;
-    if (!sw.useSyntheticData) { _err = "only the synthetic data source is built (OpenNI2 / TUM dataset readers are out of scope, SURVEY.md 2.1)"; return false; }
-    _data_source = new DataSourceProducerSynthetic();
+    if (sw.useSyntheticData) _data_source = new DataSourceProducerSynthetic();
+    else if (sw.useDatasetRGBD) _data_source = new DataSourceProducerRGBDDataset();
+    else { _err = "the OpenNI2 live source needs hardware and a library that are not available: use the synthetic or the TUM dataset source"; return false; }
     if (!_data_source->init()) { _err = "data source init failed"; return false; }
     _kinect_fusioner = new HybKinectfu();
     if (!_kinect_fusioner->init()) { _err = "HybKinectfu::init failed"; return false; }

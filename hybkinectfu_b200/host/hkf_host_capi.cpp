@@ -5,7 +5,9 @@
 #include "AppParamsProducer.h"
 #include "CameraPoseFinderFromFile.h"
 #include "CudaDeviceDataMan.h"
+#include "DataSourceProducerRGBDDataset.h"
 #include "DataSourceProducerSynthetic.h"
+#include "PngReader.h"
 #include "MainController.h"
 #include "TrajectoryRecorder.h"
 
@@ -43,6 +45,37 @@ void hkfhost_synth_render(const double* pose16, unsigned cols, unsigned rows, fl
 int hkfhost_write_tum(const char* path, unsigned n, double phase, double volume_size, double trunc_min)
 {
     return DataSourceProducerSynthetic::writeTumTrajectory(path, n, phase, volume_size, trunc_min) ? 0 : 1;
+}
+
+// ---- TUM dataset reader (pure host): read up to n frames of the dataset at `dir` (with trailing slash) at the
+// configured depth camera size; returns the number of frames read, timestamps in ts
+namespace { struct OpenDataset : DataSourceProducerRGBDDataset { using DataSourceProducer::init; }; }
+int hkfhost_read_dataset(const char* dir, unsigned cols, unsigned rows, unsigned n, uint16_t* out, double* ts)
+{
+    AppParams* P = AppParams::instance();
+    P->_io_params.rgbdReadFilename = dir;
+    P->_switch_params.useRGBData = false; P->_switch_params.recordRGBD = false;
+    P->_depth_camera_params.cols = cols; P->_depth_camera_params.rows = rows;
+    OpenDataset src;
+    if (!src.init()) { g_err = src.lastError(); return -1; }
+    unsigned k = 0;
+    for (; k < n; ++k) {
+        DepthFrameData d; ColorFrameData c;
+        if (!src.readNewFrame(d, c)) break;
+        if ((unsigned)d.cols() != cols || (unsigned)d.rows() != rows) { g_err = "size"; return -2; }
+        std::memcpy(out + (size_t)k * cols * rows, d.mm(), (size_t)cols * rows * 2);
+        ts[k] = d.timeStamp();
+    }
+    if (k < n) g_err = src.lastError();
+    return (int)k;
+}
+int hkfhost_read_png(const char* path, unsigned* w, unsigned* h, unsigned* ch, unsigned* depth, uint16_t* out, size_t cap)
+{
+    PngImage img; std::string e;
+    if (!readPng(path, img, &e)) { g_err = e; return 1; }
+    *w = img.width; *h = img.height; *ch = img.channels; *depth = img.bit_depth;
+    if (out && cap >= img.samples.size()) std::memcpy(out, img.samples.data(), img.samples.size() * 2);
+    return 0;
 }
 
 // ---- trajectory file round trip (pure host): record poses, then replay them through CameraPoseFinderFromFile

@@ -32,17 +32,18 @@ def host():
     return lib
 
 
-def write_ini(path, cols=192, rows=144, res=128, levels=3, sdf=0, fromfile=0, stepwise=0, record=0, traj_in="", traj_out="", mesh="", frames=200):
+def write_ini(path, cols=192, rows=144, res=128, levels=3, sdf=0, fromfile=0, stepwise=0, record=0, traj_in="", traj_out="", mesh="", frames=200,
+              synthetic=1, dataset=0, source=""):
     cam = synth.Camera().scaled(cols, rows)
     open(path, "w").write(f"""[switch]
 use_color=0
 record_rgbd=0
-read_rgbd_from_rgbddataset=0
+read_rgbd_from_rgbddataset={dataset}
 record_trajectory={record}
 read_trajactory_from_file={fromfile}
 color_angle_weight=0
 use_sdf_tracker={sdf}
-use_synthetic_data=1
+use_synthetic_data={synthetic}
 stepwise_tracking={stepwise}
 [camera]
 rgb_cols={cols}
@@ -82,7 +83,7 @@ camera_shake_angle=0.4
 max_triangle_num=400000
 [IO]
 rgbd_record_filename=
-rgbd_source_filename=
+rgbd_source_filename={source}
 trajectory_record_filename={traj_out}
 trajectory_source_filename={traj_in}
 mesh_filename={mesh}
@@ -180,6 +181,53 @@ def test_weld_and_obj(host, tmp_path):
     obj2 = str(tmp_path / "m2.obj")
     assert host.hkfhost_weld(np.ascontiguousarray(tri[::-1]).ctypes.data, 4, obj2.encode(), None, None) == 0
     assert open(obj).read() == open(obj2).read()
+
+
+def test_tum_dataset_reader_matches_opencv(host, tmp_path):
+    """DataSourceProducerRGBDDataset: depth.txt parsing, 16-bit PNG decoding, /5 to millimetres and cv::pyrDown, checked
+    against Python OpenCV (the reference uses the C++ API of the same library, src/DataSourceProducerRGBDDataset.cpp:100-125)"""
+    cv2 = pytest.importorskip("cv2")
+    from hybkinectfu_b200 import synth
+    d = tmp_path / "ds"
+    (d / "depth").mkdir(parents=True)
+    cam = synth.Camera()
+    poses = synth.trajectory(30)[::10]
+    imgs = []
+    lines = ["# depth maps", "# file: synthetic", "# timestamp filename"]
+    for i, p in enumerate(poses):
+        mm = synth.render_depth_mm(p, cam).astype(np.uint32)
+        raw = np.minimum(mm * 5 + (i % 5), 65535).astype(np.uint16)           # TUM convention: 5000 units per metre
+        assert cv2.imwrite(str(d / "depth" / f"{i}.png"), raw)
+        imgs.append(raw)
+        lines.append(f"{1000.5 + i / 30:.6f} depth/{i}.png")
+    (d / "depth.txt").write_text("\n".join(lines) + "\n")
+    host.hkfhost_read_dataset.argtypes = [C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+    # (a) full resolution
+    out = np.zeros((3, 480, 640), np.uint16); ts = np.zeros(3)
+    assert host.hkfhost_read_dataset((str(d) + "/").encode(), 640, 480, 3, out.ctypes.data, ts.ctypes.data) == 3, host.hkfhost_last_error()
+    for i in range(3):
+        want = cv2.divide(imgs[i], 5)                                        # cv::Mat /= 5 on CV_16U
+        assert np.array_equal(out[i], want)
+    assert np.allclose(ts, [1000.5, 1000.5 + 1 / 30, 1000.5 + 2 / 30], atol=1e-6)
+    # (b) half-size depth camera -> pyrDown, as with the reference's root config.ini (depth_cols=320)
+    out2 = np.zeros((3, 240, 320), np.uint16)
+    assert host.hkfhost_read_dataset((str(d) + "/").encode(), 320, 240, 3, out2.ctypes.data, ts.ctypes.data) == 3
+    for i in range(3):
+        assert np.array_equal(out2[i], cv2.pyrDown(cv2.divide(imgs[i], 5)))
+    # (c) the list ends: fewer frames than asked for, no crash; a wrong camera size is an error
+    out4 = np.zeros((5, 480, 640), np.uint16); ts4 = np.zeros(5)
+    assert host.hkfhost_read_dataset((str(d) + "/").encode(), 640, 480, 5, out4.ctypes.data, ts4.ctypes.data) == 3
+    assert host.hkfhost_read_dataset((str(d) + "/").encode(), 100, 100, 1, out4.ctypes.data, ts4.ctypes.data) == 0
+    assert host.hkfhost_read_dataset(b"/nonexistent/", 640, 480, 1, out4.ctypes.data, ts4.ctypes.data) == -1
+    # (d) the PNG reader on its own: 8-bit RGB with every filter type OpenCV may pick
+    rgb = (np.random.default_rng(1).integers(0, 255, (37, 53, 3))).astype(np.uint8)
+    cv2.imwrite(str(tmp_path / "c.png"), rgb)
+    host.hkfhost_read_png.argtypes = [C.c_char_p] + [C.c_void_p] * 5 + [C.c_size_t]
+    w, h, ch, dp = C.c_uint(), C.c_uint(), C.c_uint(), C.c_uint()
+    buf = np.zeros(37 * 53 * 3, np.uint16)
+    assert host.hkfhost_read_png(str(tmp_path / "c.png").encode(), C.byref(w), C.byref(h), C.byref(ch), C.byref(dp), buf.ctypes.data, buf.size) == 0
+    assert (w.value, h.value, ch.value, dp.value) == (53, 37, 3, 8)
+    assert np.array_equal(buf.reshape(37, 53, 3), rgb[..., ::-1])               # OpenCV writes BGR as RGB
 
 
 def test_init_without_gpu_reports_no_fallback(host, tmp_path):
@@ -285,3 +333,37 @@ def test_main_controller_loop_with_synthetic_source(host, tmp_path):
     assert host.hkfhost_run(6, 1) == 6
     host.hkfhost_release()
     assert os.path.getsize(tmp_path / "m.obj") > 1000
+
+
+@pytest.mark.gpu
+def test_main_controller_on_a_tum_format_dataset(host, pipeline, tmp_path):
+    """the caller-side data formats end to end: depth PNGs + depth.txt (TUM RGB-D layout) read by
+    DataSourceProducerRGBDDataset, poses from groundtruth.txt through CameraPoseFinderFromFile, MainController loop"""
+    cv2 = pytest.importorskip("cv2")
+    d = tmp_path / "ds"
+    (d / "depth").mkdir(parents=True)
+    frames = pipeline["frames"]
+    n = len(frames)
+    lines = ["# depth maps", "# file: synthetic", "# timestamp filename"]
+    for i, mm in enumerate(frames):
+        assert cv2.imwrite(str(d / "depth" / f"{i:04d}.png"), (mm.astype(np.uint32) * 5).astype(np.uint16))
+        lines.append(f"{i / 30:.6f} depth/{i:04d}.png")
+    (d / "depth.txt").write_text("\n".join(lines) + "\n")
+    synth.write_tum_trajectory(str(d / "groundtruth.txt"), pipeline["gt_poses"].astype(np.float64))
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), synthetic=0, dataset=1, source=str(d) + "/", fromfile=1, traj_in=str(d / "groundtruth.txt"))
+    assert host.hkfhost_init(str(ini).encode(), 0) == 0, host.hkfhost_last_error()
+    assert host.hkfhost_run(n + 3, 0) == n                       # the loop ends when the dataset does
+    vol = np.zeros((128, 128, 128, 2), np.float32)
+    lib = capi.load()
+    assert lib.hkf_download(C.c_void_p(host.hkfhost_ctx()), capi.BUF_VOLUME, 0, vol.ctypes.data, vol.nbytes) == vol.nbytes
+    host.hkfhost_release()
+    # frames round-trip exactly (mm*5 -> /5), poses are the file's: same volume as the in-memory path with those poses
+    from conftest import small_config
+    from test_gpu_pipeline import run_fused
+    ts = np.round(np.arange(n) / 30.0, 6)
+    out = np.zeros((n, 4, 4), np.float32)
+    assert host.hkfhost_replay_trajectory(str(d / "groundtruth.txt").encode(), synth.pose0().astype(np.float32).ctypes.data, ts.ctypes.data, n, out.ctypes.data) == 0
+    _, _, c = run_fused(small_config(128), frames, 2, out)
+    assert bits_equal(vol, c.download(capi.BUF_VOLUME))
+    c.close()
