@@ -28,8 +28,8 @@ def test_slabs_partition_the_volume_with_halos():
         assert rs[0][0] == 0 and rs[-1][1] == 128 and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
         assert all(z1 - z0 >= 8 for z0, z1, _, _ in rs)
         w = shard.plane_work(cfg)
-        share = [w[z0:z1].sum() / w.sum() for z0, z1, _, _ in rs]
-        assert max(share) < 1.3 / G
+        stored = np.array([w[s0:s1].sum() for _, _, s0, s1 in rs])        # what a rank really processes: owned + halo
+        assert stored.max() <= 1.25 * stored.mean()
     bands = [shard.icp_band(120, r, 8) for r in range(8)]
     assert bands[0][0] == 0 and bands[-1][1] == 120 and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
 
