@@ -144,6 +144,52 @@ def test_against_cpu_oracle_other_frames():
         assert bits_equal(canon_tris(c.download(capi.BUF_TRIANGLES)), canon_tris(t_cpu))
 
 
+def _rot(axis, a):
+    c, s = np.cos(a), np.sin(a)
+    m = np.eye(4)
+    i, j = [(1, 2), (2, 0), (0, 1)][axis]
+    m[i, i], m[i, j], m[j, i], m[j, j] = c, -s, s, c
+    return m
+
+
+@pytest.mark.parametrize("name,resolution,size,pose_fn", [
+    # camera INSIDE the volume, pitched and rolled: voxels behind the camera (Z <= 0), rows grazing the image border,
+    # the ill-conditioned Z ~ 0 region of the row intervals
+    ("inside", 96, 2.0, lambda: np.array([[1, 0, 0, 1.0], [0, 1, 0, 0.9], [0, 0, 1, 0.45], [0, 0, 0, 1.0]]) @ _rot(0, 0.35) @ _rot(2, 0.6) @ _rot(1, -0.4)),
+    # the reference's default volume: 3 m (R/S is not a power of two -> the raycast's exact-division fallback), odd-ish R
+    ("size3", 100, 3.0, lambda: synth.pose0(3.0, 0.3) @ _rot(1, 0.2)),
+    # looking back out of the volume: almost nothing is in view
+    ("away", 64, 2.0, lambda: synth.pose0() @ _rot(1, 2.6)),
+])
+def test_integration_raycast_exact_for_awkward_views(name, resolution, size, pose_fn):
+    """bit-exact TSDF / raycast against the CPU oracle where the culling logic of integrate.cu is stressed"""
+    import dataclasses
+    cfg = dataclasses.replace(small_config(resolution), volume_size=size)
+    cam = synth.Camera().scaled(192, 144)
+    base = pose_fn()
+    poses = [(base @ _rot(1, 0.02 * i)).astype(np.float32) for i in range(3)]
+    # the scene is rendered from a pose inside the 2 m scene cube regardless of the volume size
+    frames = [synth.render_depth_mm(synth.trajectory(60)[5 * i], cam, noise_sigma_mm=0.5) for i in range(3)]
+    with capi.Context(cfg) as c:
+        vol = np.zeros((resolution, resolution, resolution, 2), np.float32)
+        total = 0
+        for i in range(3):
+            c.preprocess(frames[i])
+            tr = O.trunc(O.decode_mm(frames[i]), cfg.trunc_min, cfg.trunc_max)
+            n_gpu = c.count_updates(poses[i])
+            c.integrate(poses[i])
+            n_cpu = O.integrate(vol, cfg, tr, poses[i])
+            assert n_gpu == n_cpu, (name, i, n_gpu, n_cpu)
+            total += n_cpu
+            assert bits_equal(c.download(capi.BUF_VOLUME), vol), (name, i)
+        if name != "away":
+            assert total > 1000
+        c.raycast(poses[2])
+        v, n = O.raycast(vol, cfg, poses[2])
+        assert bits_equal(c.download(capi.BUF_MODEL_VERTICES), v), name
+        assert bits_equal(c.download(capi.BUF_MODEL_NORMALS), n), name
+
+
 # ---------------------------------------------------------------- edge cases
 def test_empty_and_degenerate_frames():
     cfg = small_config(64)
