@@ -24,6 +24,8 @@
 //   normal  = (fx1-fx2, fy1-fy2, fz1-fz2) * rcp.rn(len), len = sqrt.rn(dot3), fails if (double)len < 1e-8
 #include "tsdf_sample.cuh"
 
+#define RAY_NB 8          // independent samples of a ray in flight
+
 struct RaycastArgs {
     VolView V;
     int cols, rows;
@@ -98,7 +100,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         }
         // Nearest-voxel index of a sample, (int)((p*R)/S) clamped: the quotient is first taken with a multiplication by
         // 1/S (within 2 ulp of the IEEE quotient); only when that lands within 1e-3 of an integer does the reference's
-        // div.rn decide.  The samples of a ray do not depend on each other, so they are taken four at a time: four
+        // div.rn decide.  The samples of a ray do not depend on each other, so they are taken RAY_NB at a time:
         // independent loads in flight, then the crossing test in order.
         const float rS = __frcp_rn(S);
         const unsigned Rm1 = (unsigned)(R - 1);
@@ -111,10 +113,10 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         };
         bool done = false;
         while (!done && t < tmax && t < t_leave) {
-            float ts[4], sd[4];
-            int gzs[4];
+            float ts[RAY_NB], sd[RAY_NB];
+            int gzs[RAY_NB];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < RAY_NB; ++b) {
                 ts[b] = t;
                 const int gx = voxel(__fmaf_rn(dx, t, ox)), gy = voxel(__fmaf_rn(dy, t, oy)), gz = voxel(__fmaf_rn(dz, t, oz));
                 gzs[b] = gz;
@@ -123,7 +125,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 t = __fadd_rn(A.inc, t);
             }
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            for (int b = 0; b < RAY_NB; ++b) {
                 if (done) break;
                 if (!(ts[b] < tmax)) { done = true; break; }
                 const int gz = gzs[b];
