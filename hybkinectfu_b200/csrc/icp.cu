@@ -125,28 +125,43 @@ __device__ __forceinline__ void icp_pixel_row(const IcpArgs& A, const float* __r
 }
 
 // FROM_STATE: pose/status from device state; SOLVE: the last block also solves and advances the pose (single GPU).
-// Sharded ranks run <true,false> over their pixel-row band, allreduce st->sums, then k_icp_solve.
+// Sharded ranks without peer memory run <true,false> over their pixel-row band, allreduce st->sums, then k_icp_solve.
+//
+// Work mapping.  The reference's second stage gives its thread t (of 512) the block partials t, t+512, t+1024, ...
+// ("leaf" t), then folds the 512 leaves with a fixed tree whose first level adds leaf t and leaf t+256.  Here block b
+// (of min(256, tiles)) owns exactly the tiles of leaves b and b+256: tiles b + 256 k, two per round (thread group 0
+// takes the even k = leaf b's terms, group 1 the odd k = leaf b+256's terms), accumulates the two leaf sums in the
+// reference's order and adds them, so that only [27][<=256] values reach the second stage: 16 loads per lane in ONE
+// round trip for the last block instead of 2 x 48.
 template <bool FROM_STATE, bool SOLVE, bool P2P>
 __global__ void __launch_bounds__(ICP_THREADS, 2)
 k_icp(IcpArgs A, HkfDeviceState* st)
 {
     __shared__ float s_r[ICP_TILES][7][256];
     __shared__ float s_m[32];                  // cur | last_inv
+    __shared__ float s_acc[2 * HKF_SUMS];      // leaf sums of leaf b | leaf b+256
     __shared__ float s_sums[HKF_SUMS];
     __shared__ int s_flag[4];                  // 0: tracking live, 1: last block, 2: singular, 3: step result
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tl = threadIdx.x >> 8, t = threadIdx.x & 255;
     const long long t0 = clock64();
     pdl_launch_dependents();
+    const int nblocks = (int)gridDim.x;                                   // = min(256, ntiles)
+    const int rounds = (A.ntiles - (int)blockIdx.x + 2 * 256 - 1) / (2 * 256);   // tiles b + 256 k < ntiles, two k per round
 
-    // ---- independent of the previous iteration: this thread's pixel of the new frame
-    const int tile = blockIdx.x * ICP_TILES + tl;
-    const int bx = tile % A.gx, by = tile / A.gx;
-    const int x = bx * 16 + (t & 15), y = by * 16 + (t >> 4);
-    bool ok = tile < A.ntiles && !(x >= A.cols || y >= A.rows || y < A.y0 || y >= A.y1);
-    const size_t idx = ok ? (size_t)y * A.cols + x : 0;
-    const float4 n = ld_f4(A.new_n + idx);
-    const float4 v = ld_f4(A.new_v + idx);
+    // ---- independent of the previous iteration: this thread's pixel of the new frame (first round)
+    int tile = (int)blockIdx.x + 256 * tl;
+    float4 n, v;
+    bool ok;
+    auto load_pixel = [&]() {
+        const int bx = tile % A.gx, by = tile / A.gx;
+        const int x = bx * 16 + (t & 15), y = by * 16 + (t >> 4);
+        ok = tile < A.ntiles && !(x >= A.cols || y >= A.rows || y < A.y0 || y >= A.y1);
+        const size_t idx = ok ? (size_t)y * A.cols + x : 0;
+        n = ld_f4(A.new_n + idx);
+        v = ld_f4(A.new_v + idx);
+    };
+    load_pixel();
 
     // ---- everything below depends on the previous launch (pose, status, ticket, partials)
     pdl_wait();
@@ -161,20 +176,35 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     if (!s_flag[0]) return;                    // a failed iteration ends the frame's tracking
     const float* cur = s_m; const float* li = s_m + 16;
 
-    icp_pixel_row(A, cur, li, n, v, ok, s_r[tl], t);
-    __syncthreads();
-
-    // ---- first stage: 2 x 27 (tile, sum) jobs over 16 warps
+    // job j = group * 27 + sum, owned by warp j % 16 in accumulator slot j / 16 (lane 0 holds the value)
+    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll 1
-    for (int job = warp; job < ICP_TILES * HKF_SUMS; job += ICP_WARPS) {
-        const int jt = job / HKF_SUMS, k = job - jt * HKF_SUMS;
-        const int tile2 = blockIdx.x * ICP_TILES + jt;
-        if (tile2 >= A.ntiles) break;
-        const float c = tile_sum_from_rows(s_r[jt], k, lane);
-        if (lane == 0) __stcg(A.partials + (size_t)k * A.ntiles + tile2, c);
+    for (int r = 0; r < rounds; ++r) {
+        if (r) { tile = (int)blockIdx.x + 256 * (2 * r + tl); load_pixel(); }
+        icp_pixel_row(A, cur, li, n, v, ok, s_r[tl], t);
+        __syncthreads();
+#pragma unroll
+        for (int slot = 0; slot < 4; ++slot) {
+            const int job = warp + ICP_WARPS * slot;
+            if (job < 2 * HKF_SUMS) {                                     // warp-uniform
+                const int g = job / HKF_SUMS, k = job - g * HKF_SUMS;
+                if ((int)blockIdx.x + 256 * (2 * r + g) < A.ntiles)       // the reference adds only existing partials
+                    acc[slot] = __fadd_rn(acc[slot], tile_sum_from_rows(s_r[g], k, lane));
+            }
+        }
+        __syncthreads();
     }
+#pragma unroll
+    for (int slot = 0; slot < 4; ++slot) {
+        const int job = warp + ICP_WARPS * slot;
+        if (job < 2 * HKF_SUMS && lane == 0) s_acc[job] = acc[slot];
+    }
+    __syncthreads();
+    // first level of the reference's second-stage tree: leaf b + leaf b+256
+    if (threadIdx.x < HKF_SUMS)
+        __stcg(A.partials + (size_t)threadIdx.x * 256 + blockIdx.x, __fadd_rn(s_acc[threadIdx.x], s_acc[HKF_SUMS + threadIdx.x]));
 
-    // ---- last block folds the partials and (fused mode) advances the pose
+    // ---- last block folds the leaf pairs and (fused mode) advances the pose
     const long long t1 = clock64();
     __threadfence();
     __syncthreads();
@@ -186,7 +216,26 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     if (!s_flag[1]) return;
     const long long t2 = clock64();
     __threadfence();
-    second_stage_all<ICP_WARPS>(A.partials, A.ntiles, warp, lane, s_sums);
+    {
+        // rows 2 per warp, all 16 loads in flight; lane owns entries lane + 32 m, the remaining levels 128/64/32 and
+        // 16..1 are the tile tree
+        float pv[2][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = warp + ICP_WARPS * q;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const int e = lane + 32 * m;
+                pv[q][m] = (k < HKF_SUMS && e < nblocks) ? __ldcg(A.partials + (size_t)k * 256 + e) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int k = warp + ICP_WARPS * q;
+            const float c = tile_tree(pv[q]);
+            if (k < HKF_SUMS && lane == 0) s_sums[k] = c;
+        }
+    }
     __syncthreads();
     if (P2P) icp_p2p_allreduce(A.peers, A.seq, s_sums, warp, lane);
     const long long t3 = clock64();
@@ -224,7 +273,6 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     }
 }
 
-
 // start of a frame's tracking: cur = pose, last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63)
 __global__ void k_track_begin(HkfDeviceState* st)
 {
@@ -234,6 +282,8 @@ __global__ void k_track_begin(HkfDeviceState* st)
     }
     if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->gen = 0; st->sdf_done = 0; }
 }
+
+static inline unsigned icp_grid(int ntiles) { return (unsigned)(ntiles < 256 ? ntiles : 256); }
 
 static void fill_icp_args(hkf_ctx* c, int level, const HkfCameraParams* cam, float dist_thres, float sin_thres, IcpArgs* A)
 {
@@ -258,7 +308,7 @@ extern "C" int hkf_cal_point_to_plane_err_solver_params(hkf_ctx* c, unsigned lev
     if (cam->cols != c->cols[level] || cam->rows != c->rows[level]) { c->err = "level camera size mismatch"; return HKF_ERR_ARG; }
     IcpArgs A; fill_icp_args(c, (int)level, cam, dist_thres, norm_sin_thres, &A);
     memcpy(A.cur, cur->m, 64); memcpy(A.last_inv, last_inv->m, 64);
-    k_icp<false, false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+    k_icp<false, false, false><<<icp_grid(A.ntiles), ICP_THREADS, 0, c->stream>>>(A, c->st);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -342,7 +392,7 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
             for (int it = 0; it < iters[l]; ++it) {
                 A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(div_up(A.ntiles, ICP_TILES)); cfg.blockDim = dim3(ICP_THREADS); cfg.stream = c->stream;
+                cfg.gridDim = dim3(icp_grid(A.ntiles)); cfg.blockDim = dim3(ICP_THREADS); cfg.stream = c->stream;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -363,7 +413,7 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
         A.y1 = (int)((long long)A.rows * (c->rank + 1) / c->nranks);
         for (int it = 0; it < iters[l]; ++it) {
             A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;
-            k_icp<true, false, false><<<div_up(A.ntiles, ICP_TILES), ICP_THREADS, 0, c->stream>>>(A, c->st);
+            k_icp<true, false, false><<<icp_grid(A.ntiles), ICP_THREADS, 0, c->stream>>>(A, c->st);
             HKF_LAUNCH_CHECK(c);
             rc = hkf_shard_allreduce_sums(c);
             if (rc != HKF_OK) return rc;
