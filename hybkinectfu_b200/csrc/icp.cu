@@ -245,12 +245,54 @@ k_icp(IcpArgs A, HkfDeviceState* st)
         if (threadIdx.x == 0) { st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3; }
         return;
     }
-    float c2[16];
+    // ---- the solve (hkf_icp_step, operation for operation) spread over warp 0 while warp 1 evaluates the determinant
+    // gate: Cholesky on lane 0, the three sin/cos pairs on lanes 0-2, the 3x3 products on lanes 0-8, the shake gate on
+    // lane 0 next to the 4x4 product T * cur on lanes 16-31
+    __shared__ float s_x[6], s_R[3][9], s_Rxy[9], s_Rf[9], s_c2[16];
     long long t4 = 0;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        if (lane == 0) {
+            float Am[36], bv[6], x[6];
+            hkf_unpack27(s_sums, Am, bv);
+            hkf_llt_solve6(Am, bv, x);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) c2[i] = cur[i];
-        s_flag[3] = hkf_icp_step(s_sums, A.angle_shake, A.dist_shake, c2);
+            for (int i = 0; i < 6; ++i) s_x[i] = x[i];
+        }
+        __syncwarp();
+        if (lane < 3) {
+            float R[9];
+            hkf_rot_axis(lane, s_x[lane], R);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s_R[lane][i] = R[i];
+        }
+        __syncwarp();
+        if (lane < 9) {
+            const int i = lane / 3, j = lane - 3 * i;
+            s_Rxy[lane] = __fadd_rn(__fadd_rn(__fmul_rn(s_R[0][i * 3 + 0], s_R[1][0 * 3 + j]), __fmul_rn(s_R[0][i * 3 + 1], s_R[1][1 * 3 + j])),
+                                    __fmul_rn(s_R[0][i * 3 + 2], s_R[1][2 * 3 + j]));
+        }
+        __syncwarp();
+        if (lane < 9) {
+            const int i = lane / 3, j = lane - 3 * i;
+            s_Rf[lane] = __fadd_rn(__fadd_rn(__fmul_rn(s_Rxy[i * 3 + 0], s_R[2][0 * 3 + j]), __fmul_rn(s_Rxy[i * 3 + 1], s_R[2][1 * 3 + j])),
+                                   __fmul_rn(s_Rxy[i * 3 + 2], s_R[2][2 * 3 + j]));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // the shake gate of hkf_vector6_to_transform (a NaN passes, as in the reference)
+            const float angle = hkf_rotation_angle(s_Rf);
+            const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_x[3], s_x[3]), __fmul_rn(s_x[4], s_x[4])), __fmul_rn(s_x[5], s_x[5])));
+            s_flag[3] = (angle > A.angle_shake || d > A.dist_shake) ? HKF_SOLVE_SHAKE : HKF_SOLVE_OK;
+        } else if (lane >= 16) {
+            // cur <- T * cur, T = [R | x[3..5]; 0 0 0 1] (hkf_mat44_mul, entry by entry)
+            const int e = lane - 16, i = e >> 2, j = e & 3;
+            const float t0r = i < 3 ? s_Rf[i * 3 + 0] : 0.f, t1r = i < 3 ? s_Rf[i * 3 + 1] : 0.f, t2r = i < 3 ? s_Rf[i * 3 + 2] : 0.f;
+            const float t3r = i < 3 ? s_x[3 + i] : 1.f;
+            float acc = __fadd_rn(__fmul_rn(t0r, cur[0 * 4 + j]), __fmul_rn(t1r, cur[1 * 4 + j]));
+            acc = __fadd_rn(acc, __fmul_rn(t2r, cur[2 * 4 + j]));
+            acc = __fadd_rn(acc, __fmul_rn(t3r, cur[3 * 4 + j]));
+            s_c2[e] = acc;
+        }
         t4 = clock64();
     } else if (threadIdx.x == 32) {
         s_flag[2] = hkf_icp_singular(s_sums) ? 1 : 0;
@@ -260,8 +302,9 @@ k_icp(IcpArgs A, HkfDeviceState* st)
         if (s_flag[2]) st->track_status = HKF_TRACK_SINGULAR;          // det(AtA) < 1e-10 is tested first (CameraPoseFinderICP.cpp:138)
         else if (s_flag[3] != HKF_SOLVE_OK) st->track_status = HKF_TRACK_SHAKE;
         else {
+            float c2[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) st->cur[i] = c2[i];
+            for (int i = 0; i < 16; ++i) { c2[i] = s_c2[i]; st->cur[i] = c2[i]; }
             if (A.is_last) {                      // _pose = cur_transform (CameraPoseFinderICP.cpp:84)
                 float inv[16];
                 hkf_mat44_inverse(c2, inv);
