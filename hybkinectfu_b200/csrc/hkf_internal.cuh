@@ -165,6 +165,29 @@ struct hkf_ctx {
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+// Launch with programmatic stream serialisation: the grid may become resident while its predecessor in the stream is
+// still draining (every kernel launched this way starts with hkf_pdl_enter(), which releases ITS successor early and
+// then waits for the predecessor's completion and memory flush), which hides the launch latency between the
+// dependent kernels of a frame.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t hkf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+__device__ __forceinline__ void hkf_pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 // internal cross-file helpers (C++ linkage)
 void hkf_shard_release(hkf_ctx* c);
 int hkf_shard_allreduce_sums(hkf_ctx* c);

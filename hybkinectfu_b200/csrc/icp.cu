@@ -319,6 +319,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
 // start of a frame's tracking: cur = pose, last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63)
 __global__ void k_track_begin(HkfDeviceState* st)
 {
+    hkf_pdl_enter();
     if (threadIdx.x < 16) {
         st->cur[threadIdx.x] = st->pose[threadIdx.x];
         st->last_inv[threadIdx.x] = st->pose_inv[threadIdx.x];
@@ -411,7 +412,7 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
     // cudaDownSampleModelVertices/Normals (the new-frame pyramids were built by hkf_preprocess)
     int rc = hkf_pyramids_fused(c, c->model_v, c->model_n);
     if (rc != HKF_OK) return rc;
-    k_track_begin<<<1, 32, 0, c->stream>>>(c->st);
+    hkf_launch_pdl(k_track_begin, dim3(1), dim3(32), 0, c->stream, c->st);
     HKF_LAUNCH_CHECK(c);
     const int* iters = icp_schedule(c->levels);
     // HKF_SHARD_ICP=replicated: every rank evaluates the whole image (no exchange at all; the poses are bit-identical

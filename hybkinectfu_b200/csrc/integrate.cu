@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256)
 k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity)
 {
     __shared__ int s_lo[INT_GB], s_hi[INT_GB];
+    hkf_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int RG = A.R / INT_G;
     const int ngroups = (A.z_hi - A.z_lo) * RG;
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(INT_THREADS, 4)
 k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict__ vol, HkfDeviceState* __restrict__ st,
             const uint2* __restrict__ items, unsigned capacity, int parity)
 {
+    hkf_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int R = A.R;
     const unsigned n_free = st->int_items[parity * 2 + 0], n_gen = st->int_items[parity * 2 + 1];
@@ -411,10 +413,10 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
     const int ngroups = (A.z_hi - A.z_lo) * (A.R / INT_G);
     const int parity = c->int_parity;
     c->int_parity ^= 1;
-    k_integrate_items<FROM_STATE><<<div_up(ngroups, INT_GB), 256, 0, c->stream>>>(A, c->st, c->int_items, c->int_capacity, parity);
+    hkf_launch_pdl(k_integrate_items<FROM_STATE>, dim3(div_up(ngroups, INT_GB)), dim3(256), 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
-    k_integrate<FROM_STATE, COUNT_ONLY><<<c->sm_count * 4, INT_THREADS, 0, c->stream>>>(A, c->trunc_depth, c->vol, c->st, c->int_items,
-                                                                                       c->int_capacity, parity);
+    hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY>, dim3(c->sm_count * 4), dim3(INT_THREADS), 0, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
+                   (const uint2*)c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }

@@ -252,6 +252,7 @@ __global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __
                                  float4* __restrict__ v2, float4* __restrict__ n2,
                                  unsigned c0, unsigned c1, unsigned r1, unsigned c2, unsigned r2)
 {
+    hkf_pdl_enter();
     unsigned X = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned Y = blockIdx.y * blockDim.y + threadIdx.y;
     float4 lv[2][2], ln[2][2];
@@ -366,8 +367,8 @@ int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream
     bool three = c->levels >= 3;
     unsigned gx = div_up(c->cols[1], 2), gy = div_up(c->rows[1], 2);
     dim3 b(32, 4), g(div_up(gx, 32), div_up(gy, 4));
-    k_pyramids_fused<<<g, b, 0, stream>>>(pv[0], pn[0], pv[1], pn[1], three ? pv[2] : nullptr, three ? pn[2] : nullptr,
-                                             c->cols[0], c->cols[1], c->rows[1], three ? c->cols[2] : 0, three ? c->rows[2] : 0);
+    hkf_launch_pdl(k_pyramids_fused, g, b, 0, stream, (const float4*)pv[0], (const float4*)pn[0], pv[1], pn[1], three ? pv[2] : (float4*)nullptr, three ? pn[2] : (float4*)nullptr,
+                   c->cols[0], c->cols[1], c->rows[1], three ? c->cols[2] : 0u, three ? c->rows[2] : 0u);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
 {
+    hkf_pdl_enter();
     // 16x16 pixel block, warps as 8x4 patches
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -216,8 +217,8 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     if (!c || !fp) return HKF_ERR_ARG;
     RaycastArgs A; fill_ray_args(c, nullptr, &fp->raycast, &c->ip.depth_camera, fp->trunc_min, fp->trunc_max, &A);
     dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
-    if (is_slab(c)) k_raycast<true, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
-    else k_raycast<true, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    if (is_slab(c)) hkf_launch_pdl(k_raycast<true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, (const HkfDeviceState*)c->st);
+    else hkf_launch_pdl(k_raycast<true, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, (const HkfDeviceState*)c->st);
     HKF_LAUNCH_CHECK(c);
     // sharded volume: nearest-hit compositing of the per-slab partial raycasts -> full model maps on every rank
     // (HKF_SHARD_MANUAL_COMPOSITE=1: the caller invokes hkf_shard_composite_raycast itself, e.g. to time it separately)
