@@ -410,10 +410,14 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
     // cudaDownSampleModelVertices/Normals (the new-frame pyramids were built by hkf_preprocess)
-    int rc = hkf_pyramids_fused(c, c->model_v, c->model_n);
-    if (rc != HKF_OK) return rc;
-    hkf_launch_pdl(k_track_begin, dim3(1), dim3(32), 0, c->stream, c->st);
-    HKF_LAUNCH_CHECK(c);
+    int rc;
+    if (c->levels >= 2) {
+        rc = hkf_pyramids_fused(c, c->model_v, c->model_n, nullptr, true);      // also starts the frame's tracking state
+        if (rc != HKF_OK) return rc;
+    } else {
+        hkf_launch_pdl(k_track_begin, dim3(1), dim3(32), 0, c->stream, c->st);
+        HKF_LAUNCH_CHECK(c);
+    }
     const int* iters = icp_schedule(c->levels);
     // HKF_SHARD_ICP=replicated: every rank evaluates the whole image (no exchange at all; the poses are bit-identical
     // because inputs and arithmetic are).  Default in sharded mode: banded rows + all-reduce of the 27 sums.

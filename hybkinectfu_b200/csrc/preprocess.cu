@@ -250,9 +250,16 @@ k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out,
 __global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __restrict__ n0,
                                  float4* __restrict__ v1, float4* __restrict__ n1,
                                  float4* __restrict__ v2, float4* __restrict__ n2,
-                                 unsigned c0, unsigned c1, unsigned r1, unsigned c2, unsigned r2)
+                                 unsigned c0, unsigned c1, unsigned r1, unsigned c2, unsigned r2, HkfDeviceState* track_begin)
 {
     hkf_pdl_enter();
+    // start of a frame's tracking, folded into the model-pyramid launch (saves a launch): cur = pose,
+    // last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63), status cleared
+    if (track_begin != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0) {
+        HkfDeviceState* st = track_begin;
+        if (threadIdx.x < 16) { st->cur[threadIdx.x] = st->pose[threadIdx.x]; st->last_inv[threadIdx.x] = st->pose_inv[threadIdx.x]; }
+        if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->sdf_done = 0; }
+    }
     unsigned X = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned Y = blockIdx.y * blockDim.y + threadIdx.y;
     float4 lv[2][2], ln[2][2];
@@ -360,7 +367,7 @@ extern "C" int hkf_downsample_model_vertices(hkf_ctx* c) { return c ? downsample
 extern "C" int hkf_downsample_model_normals(hkf_ctx* c) { return c ? downsample<true>(c, c->model_n) : HKF_ERR_ARG; }
 
 // all coarser levels of one (vertices, normals) pyramid pair in a single launch
-int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream)
+int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream, bool track_begin)
 {
     if (stream == nullptr) stream = c->stream;
     if (c->levels < 2) return HKF_OK;
@@ -368,7 +375,7 @@ int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream
     unsigned gx = div_up(c->cols[1], 2), gy = div_up(c->rows[1], 2);
     dim3 b(32, 4), g(div_up(gx, 32), div_up(gy, 4));
     hkf_launch_pdl(k_pyramids_fused, g, b, 0, stream, (const float4*)pv[0], (const float4*)pn[0], pv[1], pn[1], three ? pv[2] : (float4*)nullptr, three ? pn[2] : (float4*)nullptr,
-                   c->cols[0], c->cols[1], c->rows[1], three ? c->cols[2] : 0u, three ? c->rows[2] : 0u);
+                   c->cols[0], c->cols[1], c->rows[1], three ? c->cols[2] : 0u, three ? c->rows[2] : 0u, track_begin ? c->st : (HkfDeviceState*)nullptr);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
