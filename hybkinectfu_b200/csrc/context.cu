@@ -156,8 +156,8 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * R * R;
     CREATE_CUDA(cudaMalloc(&c->vol, nvox * sizeof(float2)));
     CREATE_CUDA(cudaMemset(c->vol, 0, nvox * sizeof(float2)));
-    // one work item per 4 x 128 voxel brick at most (integrate.cu)
-    c->int_capacity = (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
+    // at most four work items per 4 x 128 voxel brick: one per general chunk, or one for its free chunks (integrate.cu)
+    c->int_capacity = 4u * (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
     CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint2)));
     c->sm_count = prop.multiProcessorCount;
     if (p->max_triangles) CREATE_CUDA(cudaMalloc(&c->tris, (size_t)p->max_triangles * sizeof(HkfTriangle)));

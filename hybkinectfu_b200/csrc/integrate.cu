@@ -238,21 +238,26 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
                 pu0 = qu0; pu1 = qu1; pv0 = qv0; pv1 = qv1; pz0 = qz0; pz1 = qz1;
             }
         }
-        // bricks made of free-space chunks only grow from the front of `items`, the others from the back
-        const bool isg = gm != 0, isf = !isg && fm != 0;
-        const unsigned bg = __ballot_sync(0xffffffffu, isg), bf = __ballot_sync(0xffffffffu, isf);
+        // Work lists: the free-space chunks of a brick form ONE item (pure streaming, 16 loads in flight) that grows
+        // from the front of `items`; every general chunk (4 rows x 32 voxels, all four rows need projecting) is an item
+        // of its own growing from the back, so pass 2 never spends an instruction on a dead or free chunk slot.
+        const unsigned ng = (unsigned)__popc(gm);
+        const bool isf = fm != 0;
+        unsigned incl = ng;                                        // inclusive warp scan of the general-chunk counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const unsigned totg = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned bf = __ballot_sync(0xffffffffu, isf);
         unsigned baseg = 0, basef = 0;
         if (lane == 0) {
-            if (bg) baseg = atomicAdd(&st->int_items[parity * 2 + 1], (unsigned)__popc(bg));
+            if (totg) baseg = atomicAdd(&st->int_items[parity * 2 + 1], totg);
             if (bf) basef = atomicAdd(&st->int_items[parity * 2 + 0], (unsigned)__popc(bf));
         }
-        baseg = __shfl_sync(0xffffffffu, baseg, 0); basef = __shfl_sync(0xffffffffu, basef, 0);
-        if (isg | isf) {
-            const uint2 it = make_item(yg, zrel, seg, xa - seg * INT_SEG, xe - seg * INT_SEG, gm, fm);
-            const unsigned below = (1u << lane) - 1;
-            if (isg) items[capacity - 1 - (baseg + __popc(bg & below))] = it;
-            else items[basef + __popc(bf & below)] = it;
-        }
+        baseg = __shfl_sync(0xffffffffu, baseg, 0) + (incl - ng); basef = __shfl_sync(0xffffffffu, basef, 0);
+        const int lo_rel = xa - seg * INT_SEG, hi_rel = xe - seg * INT_SEG;
+        if (isf) items[basef + __popc(bf & ((1u << lane) - 1))] = make_item(yg, zrel, seg, lo_rel, hi_rel, 0u, fm);
+        for (unsigned m2 = gm; m2; m2 &= m2 - 1)
+            items[capacity - 1 - baseg++] = make_item(yg, zrel, seg, lo_rel, hi_rel, m2 & (0u - m2), 0u);
     }
 }
 
@@ -288,7 +293,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
     const float trunc = A.trunc, thr_one = A.trunc * 1.000002f, wmax = A.wmax;
     unsigned local_count = 0;
 
-    // ---- bricks with chunks that need projecting (the heavier ones first)
+    // ---- general chunks (the heavier items first): 4 rows x 32 voxels, every voxel is projected
     if (wid < n_gen) {
         float m[12];
         load_pose_inv(A, st, FROM_STATE, m);
@@ -297,73 +302,63 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
         const float ntrunc = -A.trunc;
         const float MAGIC = 12582912.0f;              // 1.5 * 2^23: adding it leaves the nearest integer in the mantissa
         const float edge = 0.5f - 0.00048828125f;     // within 2^-11 px of a rounding boundary -> the exact sequence decides
+        uint2 nxt = __ldg(items + (capacity - 1 - wid));
 #pragma unroll 1
         for (unsigned item = wid; item < n_gen; item += nwarps) {
-            const uint2 cur = __ldg(items + (capacity - 1 - item));
+            const uint2 cur = nxt;
+            if (item + nwarps < n_gen) nxt = __ldg(items + (capacity - 1 - (item + nwarps)));      // prefetch the next item
             const int y0 = (int)(cur.x & 0x3ffu) * INT_G, zrel = (int)((cur.x >> 10) & 0xfffu);
-            const int xb = (int)(cur.x >> 22) * INT_SEG;
-            const int rel = lane - (int)(cur.y & 0xffu);                          // voxel offset relative to the first live one
-            const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
-            const unsigned gen = (cur.y >> 16) & 15u, fre = (cur.y >> 20) & 15u;
-            const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
-            const float xh = (float)(xb + lane) + 0.5f;             // x + 0.5, exact
-#pragma unroll 1
+            const int c = __ffs((int)((cur.y >> 16) & 15u)) - 1;                 // the chunk of the segment
+            const int xb = (int)(cur.x >> 22) * INT_SEG + 32 * c;
+            const bool inr = (unsigned)(lane + 32 * c - (int)(cur.y & 0xffu)) <= ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
+            float2* __restrict__ vp = vol + ((size_t)(zrel * R + y0) * R + xb + lane);
+            // The voxels are requested first: the DRAM round trip then overlaps the projection arithmetic and the depth
+            // read instead of following them (a few voxels that turn out not to be updated are read in vain).
+            float2 old[INT_G];
+#pragma unroll
             for (int r = 0; r < INT_G; ++r) {
-                const int y = y0 + r;
-                const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
-                const float ty1 = __fmul_rn(wy, m[1]), ty2 = __fmul_rn(wy, m[5]), ty3 = __fmul_rn(wy, m[9]);
-                float2* __restrict__ vp = vol + ((size_t)(zrel * R + y) * R + xb + lane);
-                // The voxels are requested first, for every in-range lane of a live chunk: the DRAM round trip then
-                // overlaps the projection arithmetic and the depth read instead of following them (a few voxels
-                // that turn out not to be updated are read in vain).
-                float2 old[INT_NC];
-                bool inr[INT_NC];
+                old[r] = make_float2(0.f, 0.f);
+                if (!COUNT_ONLY && inr) old[r] = vp[(size_t)r * R];
+            }
+            const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
+            const float wx = __fmul_rn((float)(xb + lane) + 0.5f, cell);
+            // the x and z parts of the three camera-space sums are shared by the four rows only in exact arithmetic: the
+            // reference's association is fma(wz, m_3, fma(wx, m_1, wy*m_2)) + m_4 per voxel, kept as is
+            float Z[INT_G];
+            int idx[INT_G];
 #pragma unroll
-                for (int c = 0; c < INT_NC; ++c) {
-                    inr[c] = ((gen | fre) & (1u << c)) && ((unsigned)(rel + 32 * c) <= span);
-                    old[c] = make_float2(0.f, 0.f);
-                    if (!COUNT_ONLY && inr[c]) old[c] = vp[32 * c];
+            for (int r = 0; r < INT_G; ++r) {
+                const float wy = __fmul_rn(__fadd_rn((float)(y0 + r), 0.5f), cell);
+                Z[r] = __fadd_rn(__fmaf_rn(wz, m[10], __fmaf_rn(wx, m[8], __fmul_rn(wy, m[9]))), m[11]);
+                const float X = __fadd_rn(__fmaf_rn(wz, m[2], __fmaf_rn(wx, m[0], __fmul_rn(wy, m[1]))), m[3]);
+                const float Y = __fadd_rn(__fmaf_rn(wz, m[6], __fmaf_rn(wx, m[4], __fmul_rn(wy, m[5]))), m[7]);
+                const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
+                bool in = inr && (Z[r] > 0.f);
+                // approximate pixel coordinate (one MUFU.RCP shared by both axes, < 2e-4 px off) and its nearest
+                // integer = floor(p + 0.5), without leaving the FMA/ALU pipes
+                const float rz = hkf_rcp_approx(Z[r]);
+                const float pu = __fmaf_rn(ax, rz, A.cx), pv = __fmaf_rn(ay, rz, A.cy);
+                const float tu = __fadd_rn(pu, MAGIC), tv = __fadd_rn(pv, MAGIC);
+                int iu = __float_as_int(tu) - 0x4B400000;
+                int iv = __float_as_int(tv) - 0x4B400000;
+                const float eu = __fsub_rn(pu, __fsub_rn(tu, MAGIC)), ev = __fsub_rn(pv, __fsub_rn(tv, MAGIC));
+                if (in && !(fmaxf(fabsf(eu), fabsf(ev)) < edge)) {     // NaN-safe; ~0.2 % of voxels
+                    // the reference's exact sequence: mul, div.rn, add, f64 add, cvt.rzi
+                    iu = hkf_round_px(hkf_project1(X, A.fx, Z[r], A.cx));
+                    iv = hkf_round_px(hkf_project1(Y, A.fy, Z[r], A.cy));
                 }
-                float Z[INT_NC];
-                int idx[INT_NC];
+                in = in && ((unsigned)(iu - 1) < ulim) && ((unsigned)(iv - 1) < vlim);
+                idx[r] = in ? iv * cols + iu : -1;
+            }
+            float d[INT_G];
 #pragma unroll
-                for (int c = 0; c < INT_NC; ++c) {
-                    idx[c] = -1; Z[c] = 0.f;
-                    if (gen & (1u << c)) {                               // warp-uniform
-                        const float wx = __fmul_rn(xh + 32.0f * c, cell);
-                        Z[c] = __fadd_rn(__fmaf_rn(wz, m[10], __fmaf_rn(wx, m[8], ty3)), m[11]);
-                        const float X = __fadd_rn(__fmaf_rn(wz, m[2], __fmaf_rn(wx, m[0], ty1)), m[3]);
-                        const float Y = __fadd_rn(__fmaf_rn(wz, m[6], __fmaf_rn(wx, m[4], ty2)), m[7]);
-                        const float ax = __fmul_rn(X, A.fx), ay = __fmul_rn(Y, A.fy);
-                        bool in = inr[c] && (Z[c] > 0.f);
-                        // approximate pixel coordinate (one MUFU.RCP shared by both axes, < 2e-4 px off) and its nearest
-                        // integer = floor(p + 0.5), without leaving the FMA/ALU pipes
-                        const float rz = hkf_rcp_approx(Z[c]);
-                        const float pu = __fmaf_rn(ax, rz, A.cx), pv = __fmaf_rn(ay, rz, A.cy);
-                        const float tu = __fadd_rn(pu, MAGIC), tv = __fadd_rn(pv, MAGIC);
-                        int iu = __float_as_int(tu) - 0x4B400000;
-                        int iv = __float_as_int(tv) - 0x4B400000;
-                        const float eu = __fsub_rn(pu, __fsub_rn(tu, MAGIC)), ev = __fsub_rn(pv, __fsub_rn(tv, MAGIC));
-                        if (in && !(fmaxf(fabsf(eu), fabsf(ev)) < edge)) {     // NaN-safe; ~0.2 % of voxels
-                            // the reference's exact sequence: mul, div.rn, add, f64 add, cvt.rzi
-                            iu = hkf_round_px(hkf_project1(X, A.fx, Z[c], A.cx));
-                            iv = hkf_round_px(hkf_project1(Y, A.fy, Z[c], A.cy));
-                        }
-                        in = in && ((unsigned)(iu - 1) < ulim) && ((unsigned)(iv - 1) < vlim);
-                        if (in) idx[c] = iv * cols + iu;
-                    }
-                }
-                float d[INT_NC];
+            for (int r = 0; r < INT_G; ++r) d[r] = (idx[r] >= 0) ? __ldg(depth + idx[r]) : 0.f;
 #pragma unroll
-                for (int c = 0; c < INT_NC; ++c) d[c] = (idx[c] >= 0) ? __ldg(depth + idx[c]) : 0.f;
-#pragma unroll
-                for (int c = 0; c < INT_NC; ++c) {
-                    float sdf = __fsub_rn(d[c], Z[c]);
-                    bool live = (d[c] != 0.f) && (d[c] < A.maxdist) && (sdf > ntrunc);
-                    if (fre & (1u << c)) { sdf = 1e30f; live = inr[c]; }   // warp-uniform: free space for certain (pass 1), tsdf = 1
-                    if (COUNT_ONLY) local_count += live ? 1u : 0u;
-                    else if (live) update_voxel(vp + 32 * c, old[c], sdf, trunc, thr_one, wmax);
-                }
+            for (int r = 0; r < INT_G; ++r) {
+                const float sdf = __fsub_rn(d[r], Z[r]);
+                const bool live = (d[r] != 0.f) && (d[r] < A.maxdist) && (sdf > ntrunc);
+                if (COUNT_ONLY) local_count += live ? 1u : 0u;
+                else if (live) update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
             }
         }
     }
