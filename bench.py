@@ -360,6 +360,7 @@ def run_config(args, rank, world, local_rank):
         extra.update({"integration_GBps_algorithmic": gbs, "frac_of_hbm_peak": gbs / peak, "n_upd_mean": n_upd / K})
     if wl == "c3":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.marching_cubes()                                  # first call uploads the case table (one-off)
         e0.record(stream); ntri = ctx.marching_cubes(); e1.record(stream); ctx.sync()
         extra.update({"marching_cubes_triangles": int(ntri), "marching_cubes_ms": e0.elapsed_time(e1)})
     if world > 1:
