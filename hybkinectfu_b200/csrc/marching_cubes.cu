@@ -48,15 +48,18 @@ k_marching_cubes(McArgs A, unsigned* __restrict__ counter)
 {
     const VolView& V = A.V;
     const int R = V.R;
-    const size_t ncells = (size_t)(A.z1 - A.z0) * R * R;
     const int lane = threadIdx.x & 31;
-    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < ncells; base += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = base + threadIdx.x;
+    // a block walks rows (y, z) of cells, its threads the x positions of the row in steps of 256: the row
+    // decomposition is block-uniform integer arithmetic instead of three 64-bit divisions per cell
+    const int nrows = (A.z1 - A.z0) * R;
+    const int xsteps = (R + (int)blockDim.x - 1) / (int)blockDim.x;
+    for (int job = blockIdx.x; job < nrows * xsteps; job += gridDim.x) {
+        const int row = job / xsteps, x = (job - row * xsteps) * (int)blockDim.x + (int)threadIdx.x;
+        const int zr = row / R, y = row - zr * R, z = zr + A.z0;
         int ntri = 0;
         unsigned long long packed = ~0ull;
         float pos[8][3], dist[8];          // corner c = i + 2j + 4k (i along x, j along y, k along z)
-        if (i < ncells) {
-            const int x = (int)(i % R), y = (int)((i / R) % R), z = (int)(i / ((size_t)R * R)) + A.z0;
+        if (x < R) {
             const float cell = V.cell;
             const float wx = __fmul_rn(__fadd_rn((float)x, 0.5f), cell);
             const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
@@ -128,6 +131,7 @@ k_marching_cubes(McArgs A, unsigned* __restrict__ counter)
                 for (int k = 0; k < 16; k += 3) if (((packed >> (4 * k)) & 0xF) != 0xF) ++ntri;
             }
         }
+        if (!__any_sync(0xffffffffu, ntri > 0)) continue;       // nothing to emit in this warp (the common case)
         // one atomic per warp: exclusive prefix of ntri over the lanes
         int incl = ntri;
 #pragma unroll
