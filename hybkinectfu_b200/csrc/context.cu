@@ -68,7 +68,7 @@ static void free_all(hkf_ctx* c)
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->back.new_v[l]); cudaFree(c->back.new_n[l]); }
     cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
-    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->st);
+    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->depth_mm_pinned) cudaFreeHost(c->depth_mm_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -51,6 +51,7 @@ struct HkfDeviceState {
     unsigned gen;            // (spare)
     unsigned comp_go;        // raycast compositing: epoch that block 0 has released to the other blocks
     unsigned mc_count;       // marching-cubes triangle counter
+    unsigned mc_ncand;       // marching-cubes candidate-cell counter
     unsigned pad;
     unsigned long long upd_count;
     float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
@@ -130,6 +131,8 @@ struct hkf_ctx {
     unsigned own_z0 = 0, own_z1 = 0;   // owned planes
     // marching cubes
     HkfTriangle* tris = nullptr;
+    unsigned* mc_cand = nullptr;       // candidate cells of the two-pass extraction
+    unsigned mc_cand_cap = 0;
     // device state
     HkfDeviceState* st = nullptr;
     HkfDeviceState* st_host = nullptr; // pinned mirror for result read-back

@@ -42,24 +42,101 @@ __device__ __forceinline__ void mc_vertex(const float* p1, const float* p2, floa
     for (int k = 0; k < 3; ++k) out[k] = __fmaf_rn(__fsub_rn(p2[k], p1[k]), mu, p1[k]);
 }
 
+// Cheap rejection of cell (x, y, z) on its raw 3x3x3 neighbourhood (the union of the eight corners' 2x2x2 voxel sets),
+// before any interpolation.  If one of the 27 voxels is unobserved some corner's interpolation fails and the reference
+// drops the cell; if all 27 tsdf values have the same strict sign every corner value - a combination of eight of them
+// with weights ~1/8 > 0 - has that sign too, the case is 0 or 255 and no triangle comes out.  Returns true when the
+// cell still has to be evaluated.  (Border cells and slab edges are always evaluated.)
+template <bool SLAB>
+__device__ __forceinline__ bool mc_candidate(const VolView& V, int x, int y, int z, float2 ctr)
+{
+    const int R = V.R;
+    if (!(x >= 1 && y >= 1 && z >= 1 && x <= R - 2 && y <= R - 2 && z <= R - 2 && (!SLAB || (z - 1 >= V.z_lo && z + 1 < V.z_hi)))) return true;
+    if (ctr.y == 0.f) return false;
+    const float2* p0 = V.vol + vol_index(V, x, y, z);
+    bool any_pos = false, any_neg = false, unobserved = false;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const float2 q = __ldg(p0 + ((ptrdiff_t)dz * R + dy) * R + dx);
+                unobserved |= (q.y == 0.f);
+                any_pos |= (q.x > 0.f);
+                any_neg |= (q.x < 0.f);
+                if (!(q.x > 0.f) && !(q.x < 0.f)) { any_pos = true; any_neg = true; }   // zero (or NaN): undecided
+            }
+    return !unobserved && any_pos && any_neg;
+}
+
+// Pass A: a lean streaming sweep (4 cells per thread per step, all centre loads in flight) that appends the cells
+// that survive mc_candidate to a compact list with one atomic per warp.  ~75 % of a volume is unobserved and costs
+// one 8-byte read per cell here; free space costs 27 cached reads; only the thin shell around the surface goes on.
 template <bool SLAB>
 __global__ void __launch_bounds__(256)
-k_marching_cubes(McArgs A, unsigned* __restrict__ counter)
+k_mc_candidates(McArgs A, unsigned* __restrict__ cand, unsigned cap, unsigned* __restrict__ ncand)
 {
     const VolView& V = A.V;
     const int R = V.R;
     const int lane = threadIdx.x & 31;
-    // a block walks rows (y, z) of cells, its threads the x positions of the row in steps of 256: the row
-    // decomposition is block-uniform integer arithmetic instead of three 64-bit divisions per cell
+    const int nrows = (A.z1 - A.z0) * R;
+    const int xsteps = (R + 1023) / 1024;
+    for (int job = blockIdx.x; job < nrows * xsteps; job += gridDim.x) {
+        const int row = job / xsteps, xs = (job - row * xsteps) * 1024 + (int)threadIdx.x;
+        const int zr = row / R, y = row - zr * R, z = zr + A.z0;
+        const bool zin = !SLAB || (z >= V.z_lo && z < V.z_hi);
+        float2 ctr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = xs + 256 * k;
+            ctr[k] = (x < R && zin) ? __ldg(V.vol + vol_index(V, x, y, z)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = xs + 256 * k;
+            const bool keep = (x < R) && mc_candidate<SLAB>(V, x, y, z, ctr[k]);
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (!b) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(ncand, (unsigned)__popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0) + (unsigned)__popc(b & ((1u << lane) - 1));
+            if (keep && base < cap) cand[base] = ((unsigned)(z - A.z0) * (unsigned)R + (unsigned)y) * (unsigned)R + (unsigned)x;
+        }
+    }
+}
+
+// Pass B (or the whole extraction when CANDIDATES is false): the reference's cell evaluation.
+template <bool SLAB, bool CANDIDATES>
+__global__ void __launch_bounds__(256)
+k_marching_cubes(McArgs A, unsigned* __restrict__ counter, const unsigned* __restrict__ cand, const unsigned* __restrict__ ncand)
+{
+    const VolView& V = A.V;
+    const int R = V.R;
+    const int lane = threadIdx.x & 31;
+    // without a candidate list a block walks rows (y, z) of cells, its threads the x positions of the row in steps of 256
     const int nrows = (A.z1 - A.z0) * R;
     const int xsteps = (R + (int)blockDim.x - 1) / (int)blockDim.x;
-    for (int job = blockIdx.x; job < nrows * xsteps; job += gridDim.x) {
-        const int row = job / xsteps, x = (job - row * xsteps) * (int)blockDim.x + (int)threadIdx.x;
-        const int zr = row / R, y = row - zr * R, z = zr + A.z0;
+    const int njobs = CANDIDATES ? (int)((*ncand + blockDim.x - 1) / blockDim.x) : nrows * xsteps;
+    for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+        int x, y, z;
+        bool active;
+        if (CANDIDATES) {
+            const unsigned i = (unsigned)job * blockDim.x + threadIdx.x;
+            active = i < *ncand;
+            const unsigned id = active ? cand[i] : 0u;
+            x = (int)(id % (unsigned)R); y = (int)((id / (unsigned)R) % (unsigned)R); z = (int)(id / ((unsigned)R * (unsigned)R)) + A.z0;
+        } else {
+            const int row = job / xsteps;
+            x = (job - row * xsteps) * (int)blockDim.x + (int)threadIdx.x;
+            const int zr = row / R;
+            y = row - zr * R; z = zr + A.z0;
+            active = x < R;
+        }
         int ntri = 0;
         unsigned long long packed = ~0ull;
         float pos[8][3], dist[8];          // corner c = i + 2j + 4k (i along x, j along y, k along z)
-        if (x < R) {
+        if (active) {
             const float cell = V.cell;
             const float wx = __fmul_rn(__fadd_rn((float)x, 0.5f), cell);
             const float wy = __fmul_rn(__fadd_rn((float)y, 0.5f), cell);
@@ -68,32 +145,9 @@ k_marching_cubes(McArgs A, unsigned* __restrict__ counter)
             // reference evaluation order with early exit: 000,100,010,001,110,011,101,111
             const int order[8] = { 0, 1, 2, 4, 3, 6, 5, 7 };
             bool ok = true;
-            // Cheap rejection on the raw 3x3x3 neighbourhood (the union of the eight corners' 2x2x2 voxel sets) before
-            // any interpolation.  If one of the 27 voxels is unobserved some corner's interpolation fails and the
-            // reference drops the cell; if all 27 tsdf values have the same strict sign every corner value - a
-            // combination of eight of them with weights ~1/8 > 0 - has that sign too, the case is 0 or 255 and no
-            // triangle comes out.  Most cells end here after <= 27 cached loads instead of 64 loads and eight
-            // trilinear evaluations.  (Border cells and slab edges take the full path.)
-            if (x >= 1 && y >= 1 && z >= 1 && x <= R - 2 && y <= R - 2 && z <= R - 2 && (!SLAB || (z - 1 >= V.z_lo && z + 1 < V.z_hi))) {
-                const float2* p0 = V.vol + vol_index(V, x, y, z);
-                const float2 ctr = __ldg(p0);
-                if (ctr.y == 0.f) ok = false;
-                else {
-                    bool any_pos = false, any_neg = false, unobserved = false;
-#pragma unroll
-                    for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const float2 q = __ldg(p0 + ((ptrdiff_t)dz * R + dy) * R + dx);
-                                unobserved |= (q.y == 0.f);
-                                any_pos |= (q.x > 0.f);
-                                any_neg |= (q.x < 0.f);
-                                if (!(q.x > 0.f) && !(q.x < 0.f)) { any_pos = true; any_neg = true; }   // zero (or NaN): undecided
-                            }
-                    if (unobserved || !(any_pos && any_neg)) ok = false;
-                }
+            if (!CANDIDATES) {
+                const bool zin = !SLAB || (z >= V.z_lo && z < V.z_hi);
+                ok = mc_candidate<SLAB>(V, x, y, z, zin ? __ldg(V.vol + vol_index(V, x, y, z)) : make_float2(0.f, 0.f));
             }
 #pragma unroll
             for (int o = 0; o < 8; ++o) {
@@ -184,10 +238,35 @@ extern "C" int hkf_marchingcube(hkf_ctx* c, int has_color, float threshold)
     A.z0 = (int)c->own_z0; A.z1 = (int)c->own_z1;
     A.threshold = threshold; A.tris = c->tris; A.max_tris = c->ip.max_triangles;
     const bool slab = !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution);
-    const int grid = 148 * 8;
-    if (slab) k_marching_cubes<true><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count);
-    else k_marching_cubes<false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count);
+    const int grid = c->sm_count * 8;
+    // candidate list: one entry per 16 cells is far more than the shell around a surface needs; if a volume ever
+    // overflows it the single-pass kernel (same results) is used instead
+    const size_t ncells = (size_t)(A.z1 - A.z0) * A.V.R * A.V.R;
+    const unsigned cap = (unsigned)(ncells / 16 < 65536 ? 65536 : ncells / 16);
+    if (!c->mc_cand || c->mc_cand_cap < cap) {
+        if (c->mc_cand) cudaFree(c->mc_cand);
+        c->mc_cand = nullptr;
+        HKF_CUDA(c, cudaMalloc(&c->mc_cand, (size_t)cap * sizeof(unsigned)));
+        c->mc_cand_cap = cap;
+    }
+    HKF_CUDA(c, cudaMemsetAsync(&c->st->mc_ncand, 0, sizeof(unsigned), c->stream));
+    if (slab) k_mc_candidates<true><<<grid, 256, 0, c->stream>>>(A, c->mc_cand, cap, &c->st->mc_ncand);
+    else k_mc_candidates<false><<<grid, 256, 0, c->stream>>>(A, c->mc_cand, cap, &c->st->mc_ncand);
     HKF_LAUNCH_CHECK(c);
+    HKF_CUDA(c, cudaMemcpyAsync(&c->st_host->mc_ncand, &c->st->mc_ncand, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    HKF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->st_host->mc_ncand <= cap) {
+        const int g2 = (int)div_up(c->st_host->mc_ncand, 256);
+        if (g2 > 0) {
+            if (slab) k_marching_cubes<true, true><<<g2, 256, 0, c->stream>>>(A, &c->st->mc_count, c->mc_cand, &c->st->mc_ncand);
+            else k_marching_cubes<false, true><<<g2, 256, 0, c->stream>>>(A, &c->st->mc_count, c->mc_cand, &c->st->mc_ncand);
+            HKF_LAUNCH_CHECK(c);
+        }
+    } else {
+        if (slab) k_marching_cubes<true, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
+        else k_marching_cubes<false, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
+        HKF_LAUNCH_CHECK(c);
+    }
     return HKF_OK;
 }
 
