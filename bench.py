@@ -49,46 +49,87 @@ def measured_hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled every 10 ms from a thread (the timed
+    region of the default run is ~0.1 s, too short for `nvidia-smi -lms`, which is the fallback when NVML is missing)"""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, sm_max_mhz, reasons bitmask)
         self.proc = None
+        self.t = None
+        self.stop_flag = False
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, self.max_mhz, r))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                bits = 0
+                for bit, val in zip((0x8, 0x40, 0x20, 0x4), f[3:7]):     # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+                    if val.lower().startswith("active"):
+                        bits |= bit
+                self.samples.append((float(f[0]), float(f[1]), bits))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        if self.t:
+            self.t.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"], "samples": 0}
+        sm = [s[0] for s in self.samples]
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(s[1] for s in self.samples),
+                "reasons": sorted(v for k, v in names.items() if bits & k), "samples": len(sm),
+                "source": "NVML, 10 ms period" if self.nvml else "nvidia-smi -lms 20"}
 
 
 def make_sequence(n, phase=0.0, cols=640, rows=480):
