@@ -10,6 +10,7 @@
 #include "PngReader.h"
 #include "MainController.h"
 #include "TrajectoryRecorder.h"
+#include "../csrc/hkf_solver.h"
 
 static std::string g_err;
 
@@ -104,6 +105,13 @@ int hkfhost_replay_trajectory(const char* path, const float* pose0_16, const dou
     }
     return 0;
 }
+
+// ---- the host-side solves of the two trackers as the stepwise host classes run them (csrc/hkf_solver.h compiled for
+// the host): exposed so that the CPU tests can pin them against the oracle's independent restatement (oracle/host_math.h)
+int hkfhost_icp_update(const float* sums27, float angle_shake, float dist_shake, float* cur16) { return hkf_icp_update(sums27, angle_shake, dist_shake, cur16); }
+int hkfhost_sdf_update(const float* sums27, float angle_shake, float dist_shake, float* cur16, int* converged) { return hkf_sdf_update(sums27, angle_shake, dist_shake, cur16, converged); }
+void hkfhost_llt_solve6(const float* sums27, float* x6) { float A[36], b[6]; hkf_unpack27(sums27, A, b); hkf_llt_solve6(A, b, x6); }
+float hkfhost_det6(const float* sums27) { float A[36], b[6]; hkf_unpack27(sums27, A, b); return hkf_det6(A); }
 
 // ---- mesh post-processing (pure host)
 int hkfhost_weld(const HkfTriangle* soup, unsigned n, const char* obj_path, unsigned* n_vertices, unsigned* n_faces)

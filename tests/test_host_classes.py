@@ -230,6 +230,75 @@ def test_tum_dataset_reader_matches_opencv(host, tmp_path):
     assert np.array_equal(buf.reshape(37, 53, 3), rgb[..., ::-1])               # OpenCV writes BGR as RGB
 
 
+def _random_sums(rng, n_rows=400):
+    """27 packed sums of a random, well-conditioned point-to-plane system whose solution is a small motion"""
+    J = rng.normal(size=(n_rows, 6)).astype(np.float32)
+    x_true = (rng.normal(size=6) * np.array([0.01, 0.01, 0.01, 0.005, 0.005, 0.005])).astype(np.float32)
+    r = (J @ x_true + rng.normal(size=n_rows).astype(np.float32) * 1e-4).astype(np.float32)
+    rows = np.concatenate([J, r[:, None]], axis=1).astype(np.float64)
+    s = [np.sum(rows[:, i] * rows[:, j]) for i in range(6) for j in range(i, 7)]
+    return np.array(s, np.float32), x_true
+
+
+def test_host_solves_equal_oracle_and_numpy(host):
+    """csrc/hkf_solver.h (what the device and the stepwise host classes run) against the oracle's independent
+    restatement (bit for bit: same algorithms, same libm) and against float64 NumPy (the Eigen boundary is unpinned in
+    the reference, so this is the external sanity check SURVEY.md 8c asks for)"""
+    import _oracle as O
+    rng = np.random.default_rng(7)
+    host.hkfhost_det6.restype = C.c_float
+    host.hkfhost_icp_update.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    host.hkfhost_sdf_update.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    cur0 = synth.trajectory(50)[7].astype(np.float32)
+    for k in range(25):
+        s27, x_true = _random_sums(rng)
+        # LLT solve: oracle bit-exact, NumPy within float32 conditioning
+        x = np.zeros(6, np.float32)
+        host.hkfhost_llt_solve6(s27.ctypes.data, x.ctypes.data)
+        ok, xo = O.solve_icp(s27)
+        assert ok == 0 and bits_equal(x, xo)
+        A = np.zeros((6, 6)); b = np.zeros(6); it = iter(s27.astype(np.float64))
+        for i in range(6):
+            for j in range(i, 7):
+                v = next(it)
+                if j == 6:
+                    b[i] = v
+                else:
+                    A[i, j] = A[j, i] = v
+        xn = np.linalg.solve(A, b)
+        assert np.abs(x - xn).max() <= 2e-5 * max(1.0, np.abs(xn).max())
+        det = host.hkfhost_det6(s27.ctypes.data)
+        assert abs(det - np.linalg.det(A)) <= 1e-3 * abs(np.linalg.det(A))
+        # whole ICP update: T(x) * cur with Rx*Ry*Rz and the shake gate
+        cur = cur0.copy()
+        rc = host.hkfhost_icp_update(s27.ctypes.data, 0.4, 0.4, cur.ctypes.data)
+        T = np.zeros((4, 4), np.float32)
+        assert O.cpu().orc_vector6_to_transform(O._fp(xo), C.c_float(0.4), C.c_float(0.4), O._fp(T)) == 1 and rc == 0
+        assert bits_equal(cur, O.mat44_mul(T, cur0))
+        from scipy.spatial.transform import Rotation
+        Rn = (Rotation.from_euler("x", xn[0]) * Rotation.from_euler("y", xn[1]) * Rotation.from_euler("z", xn[2])).as_matrix()
+        assert np.abs(T[:3, :3] - Rn).max() < 5e-6 and np.abs(T[:3, 3] - xn[3:]).max() < 2e-5
+        # SDF update: se(3) exponential map and the reference's odd composition R <- R_d^T R, t <- t - R_d^T t_d
+        cur = cur0.copy()
+        conv = C.c_int()
+        assert host.hkfhost_sdf_update(s27.ctypes.data, 0.4, 0.4, cur.ctypes.data, C.byref(conv)) == 0
+        nxt = np.zeros((4, 4), np.float32)
+        O.cpu().orc_sdf_compose(O._fp(np.ascontiguousarray(cur0).reshape(16)), O._fp(xo), O._fp(nxt))
+        if not conv.value:
+            assert bits_equal(cur, nxt)
+            from scipy.linalg import expm
+            w, v = xn[:3], xn[3:]
+            xi = np.zeros((4, 4)); xi[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]; xi[:3, 3] = v
+            E = expm(xi)
+            want = np.eye(4); want[:3, :3] = E[:3, :3].T @ cur0[:3, :3]; want[:3, 3] = cur0[:3, 3] - E[:3, :3].T @ E[:3, 3]
+            assert np.abs(cur - want).max() < 5e-6
+    # gates: a singular system and a "shaking" step are reported, the transform is left alone
+    cur = cur0.copy()
+    assert host.hkfhost_icp_update(np.zeros(27, np.float32).ctypes.data, 0.4, 0.4, cur.ctypes.data) == 1 and bits_equal(cur, cur0)
+    s27, _ = _random_sums(rng)
+    assert host.hkfhost_icp_update(s27.ctypes.data, 1e-6, 1e-6, cur.ctypes.data) == 2 and bits_equal(cur, cur0)
+
+
 def test_init_without_gpu_reports_no_fallback(host, tmp_path):
     import torch
     if torch.cuda.is_available():
