@@ -11,7 +11,7 @@
 //
 // This design (latency-bound: the <= 20 MB working set is L2-resident on B200, and a frame is a chain of
 // 19 dependent iterations, so what counts is the length of the dependent chain inside one iteration):
-//  * a block owns two of the reference's 16x16 pixel tiles, one thread per pixel.  The pixel's new-frame
+//  * one thread per pixel, two of the reference's 16x16 pixel tiles at a time per block.  The pixel's new-frame
 //    vertex/normal are loaded BEFORE the grid dependency wait (programmatic dependent launch: the blocks of
 //    iteration k+1 are already resident and have their coalesced loads in flight while the last block of
 //    iteration k is still solving), then the pose is read, the model maps are gathered and the 7-float
@@ -20,11 +20,12 @@
 //    threads tid = lane + 32 m and folds them ((p0+p4)+(p2+p6))+((p1+p5)+(p3+p7)), i.e. the reference's
 //    tid <-> tid+128, +64, +32 levels, followed by a __shfl_down tree for its 16/8/4/2/1 levels.  No atomics
 //    on data, 1 barrier instead of 108, and the float sums are BIT-IDENTICAL to the reference's;
-//  * the last block to finish (one ticket atomic per block) folds the per-tile partials with the
-//    reference's second-stage tree (512-strided sums, then 256/128/64/32 in registers, then shuffles), all
-//    loads of a row in flight at once, two rows per warp;
-//  * warp 0 then runs the Cholesky solve, the Euler/shake gate and the pose update while warp 1 evaluates
-//    the determinant gate concurrently (hkf_solver.h).
+//  * a block owns the tiles b + 256 k, i.e. exactly the partials that the reference's second stage adds into its
+//    threads b and b+256, accumulates them in that order and stores their sum: the last block to finish (one ticket
+//    atomic per block) reads [27][<=256] values in one round trip and folds them with the remaining levels of the
+//    reference's tree;
+//  * warp 0 then runs the Cholesky solve, the Euler/shake gate and the pose update (trig and the small matrix
+//    products spread over its lanes) while warp 1 evaluates the determinant gate concurrently (hkf_solver.h).
 #include "hkf_internal.cuh"
 #include "hkf_solver.h"
 #include "reduce27.cuh"

@@ -7,28 +7,30 @@
 // field by field, every voxel of the cube projected every frame, plus a cudaMalloc/cudaFree/D2H
 // and an atomicAdd per thread per call.
 //
-// This design (HBM-bound streaming, no tensor cores):
-//  * storage is packed {f32 tsdf, f32 weight} (8 B) in [z][y][x] order, x fastest;
-//  * one warp owns one (y,z) row; a lane owns voxel x = chunk + lane, so a warp moves 256 contiguous
-//    bytes per load/store instruction and rows of a block are adjacent in y (overlapping depth footprints);
-//  * before touching memory the warp intersects its row (a straight line in camera space) with the view
-//    frustum and the frame's depth range analytically, so voxels that cannot be updated are neither
-//    projected nor read.  The interval is a conservative superset (1 px / 1 voxel margins); the per-voxel
-//    tests that decide an update are the reference's, so the update mask is bit-identical;
-//  * the first ncu capture (profiles/r1_integrate_a.txt) showed the straightforward kernel to be
-//    ISSUE-bound (74 % issue-active, 21 % DRAM), not HBM-bound: ~170 instructions per voxel, dominated by
-//    three IEEE divisions, f64 rounding and int<->float conversions on the quarter-rate XU pipe.  The
-//    inner loop therefore decides everything it can from cheap approximations and only falls back to the
-//    reference's exact sequence where the approximation cannot prove the result:
-//      - pixel index: one MUFU.RCP shared by both axes gives the pixel coordinate to < 2e-4 px; unless it
-//        lies within 2^-9 px of a rounding boundary the reference's integer is already decided
-//        (float->int through the 1.5*2^23 magic constant: FMA-pipe only, no XU conversions);
+// This design (HBM-bound by construction, no tensor cores; the history of measurements is in DESIGN.md 3.4 and
+// profiles/r1_integrate_*):
+//  * storage is packed {f32 tsdf, f32 weight} (8 B) in [z][y][x] order, x fastest; a lane owns voxel x = chunk + lane,
+//    so every warp load/store moves 256 contiguous bytes;
+//  * pass 1 (k_integrate_items) intersects every group of 4 voxel rows (straight lines in camera space) with the view
+//    frustum and the frame's depth range analytically, then classifies each 32-voxel chunk of the interval against
+//    per-tile depth extrema published by the preprocess: dead (behind every visible surface), free (in front of every
+//    visible surface, all touched pixels integrable: tsdf = 1 exactly) or general, and writes two compact work lists;
+//  * pass 2 (k_integrate): persistent warps stride over the lists.  Free bricks are a pure streaming read-modify-write
+//    (no projection, no depth read, 16 loads in flight per warp).  General chunks (4 rows x 32 voxels) request their
+//    voxels first and then project.  The first ncu capture of a straightforward kernel showed it ISSUE-bound (74 %
+//    issue-active, 21 % DRAM: ~170 instructions per voxel, dominated by three IEEE divisions, f64 rounding and
+//    int<->float conversions on the quarter-rate XU pipe), so the projection decides everything it can from cheap
+//    approximations and only falls back to the reference's exact sequence where they cannot prove the result:
+//      - pixel index: one MUFU.RCP shared by both axes gives the pixel coordinate to < 2e-4 px; unless it lies within
+//        2^-11 px of a rounding boundary the reference's integer is already decided (float->int through the 1.5*2^23
+//        magic constant: FMA-pipe only, no XU conversions);
 //      - tsdf = fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19) (free space): no division;
 //      - t' = fma(t,w,tsdf)/(w+1) is exactly 1 when t == tsdf == 1: no division;
 //      - a voxel whose bits do not change (saturated weight, unchanged tsdf) is not stored.
-//    Every voxel still ends with exactly the reference's bits (tests/test_gpu_stages.py).
+//    The interval and the classification are conservative supersets; the per-voxel tests that decide an update are
+//    the reference's, so every voxel ends with exactly the reference's bits (tests/test_gpu_stages.py);
 //  * the depth map (1.2 MB) is read through the read-only path and stays L1/L2-resident;
-//  * DRAM traffic ~ 16 B x N_upd.
+//  * DRAM traffic ~ 16 B x N_upd (measured: profiles/integrate_traffic.json).
 //
 // Arithmetic contract (SASS of the reference built for sm_100, see oracle/Makefile):
 //   cell = S / (float)R                     (div.rn, per axis)
