@@ -1,5 +1,6 @@
 #include "MeshGeneratorMarchingcube.h"
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -66,10 +67,64 @@ bool MeshGeneratorMarchingcube::writeObj(const std::string& filename, const std:
     return std::fclose(f) == 0;
 }
 
+void MeshGeneratorMarchingcube::vertexNormals(const std::vector<std::array<float, 3>>& v, const std::vector<std::array<unsigned, 3>>& faces,
+                                              std::vector<std::array<float, 3>>& normals)
+{
+    auto unit = [](std::array<float, 3> n) {
+        const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (len < 1e-8f) return std::array<float, 3>{ 0.f, 0.f, 0.f };              // normalize() of src/cuda/cuda_declar.h:89-94
+        return std::array<float, 3>{ n[0] / len, n[1] / len, n[2] / len };
+    };
+    normals.assign(v.size(), { 0.f, 0.f, 0.f });
+    for (const auto& f : faces) {
+        const auto &a = v[f[0]], &b = v[f[1]], &c = v[f[2]];
+        const float e1[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, e2[3] = { c[0] - a[0], c[1] - a[1], c[2] - a[2] };
+        const auto n = unit({ e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] });
+        for (unsigned idx : f) for (int k = 0; k < 3; ++k) normals[idx][k] += n[k];
+    }
+    for (auto& n : normals) n = unit(n);
+}
+
+bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std::vector<std::array<float, 3>>& v,
+                                          const std::vector<std::array<unsigned, 3>>& faces, const std::vector<std::array<float, 3>>& normals)
+{
+    const size_t dot = filename.find_last_of('.');
+    std::string ext = dot == std::string::npos ? "" : filename.substr(dot + 1);
+    for (auto& ch : ext) ch = (char)std::tolower((unsigned char)ch);
+    const bool with_n = normals.size() == v.size();
+    FILE* f = std::fopen(filename.c_str(), "w");
+    if (!f) return false;
+    if (ext == "ply") {
+        std::fprintf(f, "ply\nformat ascii 1.0\ncomment hybKinectfu marching-cubes mesh\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z\n", v.size());
+        if (with_n) std::fprintf(f, "property float nx\nproperty float ny\nproperty float nz\n");
+        std::fprintf(f, "element face %zu\nproperty list uchar int vertex_indices\nend_header\n", faces.size());
+        for (size_t i = 0; i < v.size(); ++i) {
+            std::fprintf(f, "%.9g %.9g %.9g", v[i][0], v[i][1], v[i][2]);
+            if (with_n) std::fprintf(f, " %.6g %.6g %.6g", normals[i][0], normals[i][1], normals[i][2]);
+            std::fprintf(f, "\n");
+        }
+        for (const auto& t : faces) std::fprintf(f, "3 %u %u %u\n", t[0], t[1], t[2]);
+    } else if (ext == "off") {
+        std::fprintf(f, "OFF\n%zu %zu 0\n", v.size(), faces.size());
+        for (const auto& p : v) std::fprintf(f, "%.9g %.9g %.9g\n", p[0], p[1], p[2]);
+        for (const auto& t : faces) std::fprintf(f, "3 %u %u %u\n", t[0], t[1], t[2]);
+    } else {
+        std::fprintf(f, "# hybKinectfu marching-cubes mesh\n# vertices %zu\n# faces %zu\n", v.size(), faces.size());
+        for (const auto& p : v) std::fprintf(f, "v %.9g %.9g %.9g\n", p[0], p[1], p[2]);
+        if (with_n) for (const auto& n : normals) std::fprintf(f, "vn %.6g %.6g %.6g\n", n[0], n[1], n[2]);
+        for (const auto& t : faces) {
+            if (with_n) std::fprintf(f, "f %u//%u %u//%u %u//%u\n", t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1);
+            else std::fprintf(f, "f %u %u %u\n", t[0] + 1, t[1] + 1, t[2] + 1);
+        }
+    }
+    return std::fclose(f) == 0;
+}
+
 bool MeshGeneratorMarchingcube::saveMesh(const std::string& filename)
 {
     if (!copyTrianglesToCPU()) { std::cout << "copy triangles to cpu failed" << std::endl; return false; }
     weld(_soup, _vertices, _faces);
+    vertexNormals(_vertices, _faces, _normals);
     std::cout << "vertices :\t" << _vertices.size() << "\nfaces :\t" << _faces.size() << std::endl;
-    return writeObj(filename, _vertices, _faces);
+    return writeMesh(filename, _vertices, _faces, _normals);
 }

@@ -122,7 +122,11 @@ int hkfhost_weld(const HkfTriangle* soup, unsigned n, const char* obj_path, unsi
     MeshGeneratorMarchingcube::weld(s, v, f);
     if (n_vertices) *n_vertices = (unsigned)v.size();
     if (n_faces) *n_faces = (unsigned)f.size();
-    if (obj_path && *obj_path) return MeshGeneratorMarchingcube::writeObj(obj_path, v, f) ? 0 : 1;
+    if (obj_path && *obj_path) {
+        std::vector<std::array<float, 3>> nrm;
+        MeshGeneratorMarchingcube::vertexNormals(v, f, nrm);
+        return MeshGeneratorMarchingcube::writeMesh(obj_path, v, f, nrm) ? 0 : 1;
+    }
     return 0;
 }
 

@@ -177,6 +177,22 @@ def test_weld_and_obj(host, tmp_path):
     assert (nv.value, nf.value) == (6, 2)                        # 4 mesh vertices + the 2 of the degenerate triangle
     txt = open(obj).read().splitlines()
     assert sum(l.startswith("v ") for l in txt) == 6 and sum(l.startswith("f ") for l in txt) == 2
+    # vertex normals (ml::MeshData::computeVertexNormals): both faces lie in z = 0 and are counter-clockwise -> +z
+    vn = np.array([[float(x) for x in l.split()[1:]] for l in txt if l.startswith("vn ")])
+    assert len(vn) == 6 and np.allclose(vn[np.abs(vn).sum(1) > 0], [0, 0, 1])
+    assert all("//" in l for l in txt if l.startswith("f "))
+    # the same mesh as PLY and OFF
+    for ext, head in (("ply", "ply"), ("off", "OFF")):
+        path = str(tmp_path / f"m.{ext}")
+        assert host.hkfhost_weld(tri.ctypes.data, 4, path.encode(), None, None) == 0
+        lines = open(path).read().splitlines()
+        assert lines[0] == head
+        if ext == "ply":
+            assert "element vertex 6" in lines and "element face 2" in lines and "property float nx" in lines
+            body = lines[lines.index("end_header") + 1:]
+            assert len(body) == 8 and body[-1].split()[0] == "3" and len(body[0].split()) == 6
+        else:
+            assert lines[1] == "6 2 0" and len(lines) == 2 + 8
     # order independence: shuffling the soup gives the same file
     obj2 = str(tmp_path / "m2.obj")
     assert host.hkfhost_weld(np.ascontiguousarray(tri[::-1]).ctypes.data, 4, obj2.encode(), None, None) == 0
