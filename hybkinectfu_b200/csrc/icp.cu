@@ -205,13 +205,16 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     if (threadIdx.x < HKF_SUMS)
         __stcg(A.partials + (size_t)threadIdx.x * 256 + blockIdx.x, __fadd_rn(s_acc[threadIdx.x], s_acc[HKF_SUMS + threadIdx.x]));
 
-    // ---- last block folds the leaf pairs and (fused mode) advances the pose
+    // ---- last block folds the leaf pairs and (fused mode) advances the pose.  The 27 stores above all belong to
+    // warp 0: it alone orders them before the ticket (warp barrier, then one fence + atomic by lane 0)
     const long long t1 = clock64();
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned tk = atomicAdd(&st->ticket, 1u);
-        s_flag[1] = (tk == gridDim.x - 1);
+    if (warp == 0) {
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            const unsigned tk = atomicAdd(&st->ticket, 1u);
+            s_flag[1] = (tk == gridDim.x - 1);
+        }
     }
     __syncthreads();
     if (!s_flag[1]) return;
