@@ -300,6 +300,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
         t4 = clock64();
     } else if (threadIdx.x == 32) {
         s_flag[2] = hkf_icp_singular(s_sums) ? 1 : 0;
+        st->dbg[5] = clock64() - t3;
     }
     __syncthreads();
     if (threadIdx.x == 0) {

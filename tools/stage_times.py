@@ -72,7 +72,7 @@ def main():
     ctx.icp_track(); ctx.sync()
     dbg = np.zeros(8, np.int64)
     ctx.lib.hkf_download(ctx._h, 100, 0, dbg.ctypes.data, 64)
-    print(f"k_icp<fused> level 0 last-block SM cycles: tile {dbg[0]}  fence+ticket {dbg[1]}  second-stage {dbg[2]}  solve+commit {dbg[3]}  (llt/transform step {dbg[4]})")
+    print(f"k_icp<fused> level 0 last-block SM cycles: tile {dbg[0]}  fence+ticket {dbg[1]}  second-stage {dbg[2]}  solve+commit {dbg[3]}  (warp 0: llt/transform step {dbg[4]}, warp 1: determinant gate {dbg[5]})")
     nupd = ctx.count_updates(pose)
     print(f"N_upd {nupd} ({100.0*nupd/R**3:.1f}%)  integrate algorithmic GB/s {(16*nupd+4*640*480)/t['int']/1e3:.0f}")
     print(f"sum of stages {t['pre']+t['icp']+t['int']+t['ray']:.1f} us -> {1e6/(t['pre']+t['icp']+t['int']+t['ray']):.0f} fps")
