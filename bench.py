@@ -81,18 +81,25 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def _poll(self):
+    def sample_now(self):
+        """one NVML sample from the calling thread (used while the GPU is still working through the timed region, so
+        that there is at least one in-region sample even if the polling thread was starved of the GIL)"""
         n = self.nvml
-        while not self.stop_flag:
+        if n is None:
+            return
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
             try:
-                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
-                try:
-                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((mhz, self.max_mhz, r))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.samples.append((mhz, self.max_mhz, r))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self.sample_now()
             time.sleep(0.01)
 
     def _read(self):
@@ -207,7 +214,10 @@ def run_ours(args, rank, world, local_rank):
         ctx.integrate_tracked()
         ie[k][1].record(stream)
         ctx.raycast_tracked()
+        if k % 50 == 25:
+            sampler.sample_now()             # the host runs ahead of the GPU: these fall inside the timed region
     ev1.record(stream)
+    sampler.sample_now()
     ctx.sync(); torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop()
