@@ -36,7 +36,9 @@ struct RaycastArgs {
     const ShardMailbox* mailbox; int nranks; unsigned epoch;   // peer-memory mode: epoch of this raycast
 };
 
-template <bool FROM_STATE, bool SLAB>
+// FAST: R is a power of two and the stored planes hold at most 2^32 voxels (the host checks both) - the cheaper
+// sample-index arithmetic below applies; the results are the same bits either way.
+template <bool FROM_STATE, bool SLAB, bool FAST>
 __global__ void __launch_bounds__(256)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
@@ -112,6 +114,15 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
             if (fabsf(qa - rintf(qa)) < 1.0e-3f) g = __float2int_rz(__fdiv_rn(q, S));
             return (int)min((unsigned)max(g, 0), Rm1);
         };
+        // FAST sample index.  With R = 2^k the product p*R is exact, so (p*R)*(1/S) == p*(R*(1/S)) bit for bit: one
+        // multiplication gives the same approximate quotient qa as `voxel` (within 2 ulp of the IEEE quotient, both
+        // below R).  All three axes share ONE test: the distance of qa to its nearest integer (1.5*2^23 rounding, FMA
+        // pipe) must exceed 4 ulp(R) on every axis and the truncated indices must lie in [0, R) - otherwise (a few
+        // percent of the warp-samples) `voxel` decides as before, clamping included.
+        const float rRS = __fmul_rn(V.Rf, rS);
+        const float guard = V.Rf * 2.384185791015625e-7f;       // R * 2^-22
+        const float MAGIC = 12582912.0f;
+        const bool mono = A.inc > 0.f;                          // t never decreases: ts[b] <= ts[RAY_NB-1]
         bool done = false;
         while (!done && t < tmax && t < t_leave) {
             float ts[RAY_NB], sd[RAY_NB];
@@ -119,11 +130,36 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
 #pragma unroll
             for (int b = 0; b < RAY_NB; ++b) {
                 ts[b] = t;
-                const int gx = voxel(__fmaf_rn(dx, t, ox)), gy = voxel(__fmaf_rn(dy, t, oy)), gz = voxel(__fmaf_rn(dz, t, oz));
+                const float px = __fmaf_rn(dx, t, ox), py = __fmaf_rn(dy, t, oy), pz = __fmaf_rn(dz, t, oz);
+                int gx, gy, gz;
+                if (FAST) {
+                    const float qx = __fmul_rn(px, rRS), qy = __fmul_rn(py, rRS), qz = __fmul_rn(pz, rRS);
+                    const float ex = fabsf(__fsub_rn(qx, __fsub_rn(__fadd_rn(qx, MAGIC), MAGIC)));
+                    const float ey = fabsf(__fsub_rn(qy, __fsub_rn(__fadd_rn(qy, MAGIC), MAGIC)));
+                    const float ez = fabsf(__fsub_rn(qz, __fsub_rn(__fadd_rn(qz, MAGIC), MAGIC)));
+                    gx = __float2int_rz(qx); gy = __float2int_rz(qy); gz = __float2int_rz(qz);
+                    if (!(fminf(fminf(ex, ey), ez) >= guard) || (unsigned)(gx | gy | gz) > Rm1) { gx = voxel(px); gy = voxel(py); gz = voxel(pz); }
+                } else {
+                    gx = voxel(px); gy = voxel(py); gz = voxel(pz);
+                }
                 gzs[b] = gz;
                 const int gzc = SLAB ? min(max(gz, V.z_lo), V.z_hi - 1) : gz;      // keep the speculative read inside the slab
-                sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gzc)].x);
+                if (FAST) sd[b] = __ldg(&V.vol[((unsigned)(gzc - V.z_lo) * (unsigned)R + (unsigned)gy) * (unsigned)R + (unsigned)gx].x);
+                else sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gzc)].x);
                 t = __fadd_rn(A.inc, t);
+            }
+            // Nothing can happen in this batch (the common case) unless a (+ -> -) pair shows up, the ray reaches t_max,
+            // or a sample lies outside the stored planes: one predicate instead of the in-order scan below.
+            {
+                bool event = !(mono && ts[RAY_NB - 1] < tmax) || !last_known;
+                float prev = last_sdf;
+#pragma unroll
+                for (int b = 0; b < RAY_NB; ++b) {
+                    event |= (prev > 0.0f) & (sd[b] < 0.0f);
+                    if (SLAB) event |= (unsigned)(gzs[b] - V.z_lo) >= (unsigned)(V.z_hi - V.z_lo);
+                    prev = sd[b];
+                }
+                if (!event) { last_sdf = sd[RAY_NB - 1]; last_t = ts[RAY_NB - 1]; continue; }
             }
 #pragma unroll
             for (int b = 0; b < RAY_NB; ++b) {
@@ -197,6 +233,11 @@ static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParam
 }
 
 static inline bool is_slab(const hkf_ctx* c) { return !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution); }
+static inline bool is_fast(const hkf_ctx* c)
+{
+    const unsigned long long R = c->ip.volume_resolution;
+    return (R & (R - 1)) == 0 && (unsigned long long)(c->z_hi - c->z_lo) * R * R <= 0x100000000ull;
+}
 
 extern "C" int hkf_raycasting_volume(hkf_ctx* c, int has_color, const HkfMat44* transform, const HkfRayCasterParams* rp,
                                      const HkfCameraParams* cam, float near_plane, float far_plane)
@@ -206,8 +247,14 @@ extern "C" int hkf_raycasting_volume(hkf_ctx* c, int has_color, const HkfMat44* 
     if (cam->cols != c->cols[0] || cam->rows != c->rows[0]) { c->err = "camera size mismatch"; return HKF_ERR_ARG; }
     RaycastArgs A; fill_ray_args(c, transform->m, rp, cam, near_plane, far_plane, &A);
     dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
-    if (is_slab(c)) k_raycast<false, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
-    else k_raycast<false, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    const bool fast = is_fast(c);
+    if (is_slab(c)) {
+        if (fast) k_raycast<false, true, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+        else k_raycast<false, true, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    } else {
+        if (fast) k_raycast<false, false, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+        else k_raycast<false, false, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    }
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -217,8 +264,15 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     if (!c || !fp) return HKF_ERR_ARG;
     RaycastArgs A; fill_ray_args(c, nullptr, &fp->raycast, &c->ip.depth_camera, fp->trunc_min, fp->trunc_max, &A);
     dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
-    if (is_slab(c)) hkf_launch_pdl(k_raycast<true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, (const HkfDeviceState*)c->st);
-    else hkf_launch_pdl(k_raycast<true, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, (const HkfDeviceState*)c->st);
+    const HkfDeviceState* st = c->st;
+    const bool fast = is_fast(c);
+    if (is_slab(c)) {
+        if (fast) hkf_launch_pdl(k_raycast<true, true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
+        else hkf_launch_pdl(k_raycast<true, true, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
+    } else {
+        if (fast) hkf_launch_pdl(k_raycast<true, false, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
+        else hkf_launch_pdl(k_raycast<true, false, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
+    }
     HKF_LAUNCH_CHECK(c);
     // sharded volume: nearest-hit compositing of the per-slab partial raycasts -> full model maps on every rank
     // (HKF_SHARD_MANUAL_COMPOSITE=1: the caller invokes hkf_shard_composite_raycast itself, e.g. to time it separately)
