@@ -189,6 +189,14 @@ __device__ __forceinline__ void hkf_pdl_enter()
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The same with the successor released only AFTER the predecessor has completed: for a kernel whose successor reads,
+// before its own wait, data written two launches back (k_icp loads the new frame's pyramid level ahead of its wait;
+// with the early release above it could become resident while the kernel that builds that pyramid is still running).
+__device__ __forceinline__ void hkf_pdl_enter_ordered()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 #endif
 
 // internal cross-file helpers (C++ linkage)

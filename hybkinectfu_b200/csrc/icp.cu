@@ -324,7 +324,7 @@ k_icp(IcpArgs A, HkfDeviceState* st)
 // start of a frame's tracking: cur = pose, last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63)
 __global__ void k_track_begin(HkfDeviceState* st)
 {
-    hkf_pdl_enter();
+    hkf_pdl_enter_ordered();      // k_icp follows and preloads the new frame's maps before its own wait
     if (threadIdx.x < 16) {
         st->cur[threadIdx.x] = st->pose[threadIdx.x];
         st->last_inv[threadIdx.x] = st->pose_inv[threadIdx.x];

@@ -297,7 +297,9 @@ __global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __
                                  float4* __restrict__ v2, float4* __restrict__ n2,
                                  unsigned c0, unsigned c1, unsigned r1, unsigned c2, unsigned r2, HkfDeviceState* track_begin)
 {
-    hkf_pdl_enter();
+    // the launch that starts a frame's tracking is followed by k_icp, which preloads the NEW frame's pyramid before its
+    // grid-dependency wait: release it only once the launch that built that pyramid (our predecessor) has completed
+    if (track_begin != nullptr) hkf_pdl_enter_ordered(); else hkf_pdl_enter();
     // start of a frame's tracking, folded into the model-pyramid launch (saves a launch): cur = pose,
     // last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63), status cleared
     if (track_begin != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0) {
