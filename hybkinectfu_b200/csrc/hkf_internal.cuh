@@ -89,6 +89,17 @@ struct HkfFrameSet {
     DepthBounds bounds{};
 };
 
+// Brick bitmaps of the ray-march empty-space skipping: bit (bz*n + by)*n + bx of `fine` (16^3-voxel bricks) / `coarse`
+// (64^3) is set once the brick was ever touched by a "general" integration chunk - the only chunks that can write a
+// negative tsdf.  Null pointers = feature off.
+#define HKF_RAY_FINE 16
+#define HKF_RAY_COARSE 64
+struct RayFlags {
+    unsigned* fine = nullptr;
+    unsigned* coarse = nullptr;
+    int nbf = 0, nbc = 0;
+};
+
 struct hkf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -129,6 +140,11 @@ struct hkf_ctx {
     int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes
     unsigned own_z0 = 0, own_z1 = 0;   // owned planes
+    // EXPERIMENTAL (HKF_RAY_SKIP=1, off by default): brick bitmaps "may hold a voxel with tsdf < 0", written by the
+    // integration item pass, read by the ray march (raycast.cu)
+    unsigned* ray_flags = nullptr;     // fine bitmap, then coarse bitmap
+    RayFlags rflags{};
+    bool ray_skip = false;
     // marching cubes
     HkfTriangle* tris = nullptr;
     unsigned* mc_cand = nullptr;       // candidate cells of the two-pass extraction

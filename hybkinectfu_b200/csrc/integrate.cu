@@ -149,9 +149,27 @@ __device__ __forceinline__ uint2 make_item(int yg, int zrel, int seg, int lo_rel
 //          tsdf = fminf(sdf/trunc, 1) = 1 exactly, so pass 2 needs neither a projection nor a depth read for it;
 //   else : general, decided voxel by voxel in pass 2 with the reference's arithmetic.
 #define INT_GB 64                      // row groups per block of pass 1
-template <bool FROM_STATE>
+
+// EXPERIMENTAL (FLAGS, off by default): a general chunk is the only kind of work item that can write a negative tsdf;
+// mark the ray-march bricks it touches (read first: in a static scene the bits are already set, no atomic is issued)
+__device__ __forceinline__ void ray_flag_set(unsigned* bm, unsigned idx)
+{
+    unsigned* w = bm + (idx >> 5);
+    const unsigned bit = 1u << (idx & 31);
+    if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+}
+__device__ __forceinline__ void ray_flags_mark_chunk(const RayFlags& F, int xb, int y0, int z)
+{
+    const unsigned by = (unsigned)y0 / HKF_RAY_FINE, bz = (unsigned)z / HKF_RAY_FINE;
+    const unsigned base = (bz * F.nbf + by) * F.nbf;
+    ray_flag_set(F.fine, base + (unsigned)xb / HKF_RAY_FINE);
+    ray_flag_set(F.fine, base + (unsigned)(xb + 31) / HKF_RAY_FINE);
+    ray_flag_set(F.coarse, (((unsigned)z / HKF_RAY_COARSE) * F.nbc + (unsigned)y0 / HKF_RAY_COARSE) * F.nbc + (unsigned)xb / HKF_RAY_COARSE);
+}
+
+template <bool FROM_STATE, bool FLAGS = false>
 __global__ void __launch_bounds__(256)
-k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity)
+k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity, RayFlags RF = RayFlags())
 {
     __shared__ int s_lo[INT_GB], s_hi[INT_GB];
     hkf_pdl_enter();
@@ -258,8 +276,10 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
         baseg = __shfl_sync(0xffffffffu, baseg, 0) + (incl - ng); basef = __shfl_sync(0xffffffffu, basef, 0);
         const int lo_rel = xa - seg * INT_SEG, hi_rel = xe - seg * INT_SEG;
         if (isf) items[basef + __popc(bf & ((1u << lane) - 1))] = make_item(yg, zrel, seg, lo_rel, hi_rel, 0u, fm);
-        for (unsigned m2 = gm; m2; m2 &= m2 - 1)
+        for (unsigned m2 = gm; m2; m2 &= m2 - 1) {
             items[capacity - 1 - baseg++] = make_item(yg, zrel, seg, lo_rel, hi_rel, m2 & (0u - m2), 0u);
+            if (FLAGS) ray_flags_mark_chunk(RF, seg * INT_SEG + 32 * (__ffs((int)m2) - 1), yg * INT_G, zrel + A.z_lo);
+        }
     }
 }
 
@@ -410,7 +430,10 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
     const int ngroups = (A.z_hi - A.z_lo) * (A.R / INT_G);
     const int parity = c->int_parity;
     c->int_parity ^= 1;
-    hkf_launch_pdl(k_integrate_items<FROM_STATE>, dim3(div_up(ngroups, INT_GB)), dim3(256), 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
+    if (c->ray_flags)
+        hkf_launch_pdl(k_integrate_items<FROM_STATE, true>, dim3(div_up(ngroups, INT_GB)), dim3(256), 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, c->rflags);
+    else
+    hkf_launch_pdl(k_integrate_items<FROM_STATE>, dim3(div_up(ngroups, INT_GB)), dim3(256), 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, RayFlags());
     HKF_LAUNCH_CHECK(c);
     hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY>, dim3(c->sm_count * 4), dim3(INT_THREADS), 0, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
                    (const uint2*)c->int_items, c->int_capacity, parity);

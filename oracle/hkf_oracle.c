@@ -383,12 +383,77 @@ int orc_interpolate_sdf(const float* vol, int R, float S, float px, float py, fl
 /* ------------------------------------------------------------------ raycast */
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+typedef struct { float ox, oy, oz, dx, dy, dz, tmin, tmax; int live; } Ray;
+
+/* ray set-up of raycastKernel (src/cuda/raycastingVolume.cu:137-153) */
+static Ray ray_setup(const OrcCamera* cam, const float pose[16], float S, float near_plane, float far_plane, int x, int y)
+{
+    Ray r;
+    r.ox = pose[3]; r.oy = pose[7]; r.oz = pose[11];
+    /* cam_dir = normalize(depthToSkeleton(x,y,1)) ; z*z == 1 folds into "+ 1" */
+    float vx = ((float)(unsigned)x - cam->cx) / cam->fx;
+    float vy = ((float)(unsigned)y - cam->cy) / cam->fy;
+    float len = sqrtf(fmaf(vx, vx, vy * vy) + 1.0f);
+    float cdx, cdy, cdz;
+    if ((double)len < 1e-8) { cdx = cdy = cdz = 0.f; }
+    else { float q = 1.0f / len; cdx = vx * q; cdy = vy * q; cdz = q; }
+    /* world_dir = transform * (cam_dir, 0): lead-second rows, w = 0 */
+    float dx = fmaf(pose[3], 0.f, fmaf(cdz, pose[2], fmaf(cdx, pose[0], cdy * pose[1])));
+    float dy = fmaf(pose[7], 0.f, fmaf(cdz, pose[6], fmaf(cdx, pose[4], cdy * pose[5])));
+    float dz = fmaf(pose[11], 0.f, fmaf(cdz, pose[10], fmaf(cdx, pose[8], cdy * pose[9])));
+    if (dx == 0.f) dx = 1e-15f;
+    if (dy == 0.f) dy = 1e-15f;
+    if (dz == 0.f) dz = 1e-15f;
+    float txmin = ((dx > 0 ? 0.f : S) - r.ox) / dx, tymin = ((dy > 0 ? 0.f : S) - r.oy) / dy, tzmin = ((dz > 0 ? 0.f : S) - r.oz) / dz;
+    float tmin = fmaxf(fmaxf(txmin, tymin), tzmin);
+    float txmax = ((dx > 0 ? S : 0.f) - r.ox) / dx, tymax = ((dy > 0 ? S : 0.f) - r.oy) / dy, tzmax = ((dz > 0 ? S : 0.f) - r.oz) / dz;
+    float tmax = fminf(fminf(txmax, tymax), tzmax);
+    r.tmin = fmaxf(tmin, near_plane / cdz);
+    r.tmax = fminf(tmax, far_plane / cdz);
+    r.dx = dx; r.dy = dy; r.dz = dz;
+    r.live = r.tmin < r.tmax;
+    return r;
+}
+
+/* the (+ -> -) pair (last sample at l*, this sample at p*, parameter t): refinement, vertex, normal
+   (src/cuda/raycastingVolume.cu:65-119); leaves the pixel zero on any failure */
+static void ray_hit(const VolView* V, const Ray* r, float inc, float t, float px, float py, float pz, float lx, float ly, float lz,
+                    float* ov, float* on)
+{
+    const int R = V->R;
+    float ftdt, ft;
+    if (!interp_sdf(V, px, py, pz, &ftdt)) return;
+    if (!interp_sdf(V, lx, ly, lz, &ft)) return;
+    float alpha = t - (inc * ftdt) / (ftdt - ft);
+    float wx = fmaf(r->dx, alpha, r->ox), wy = fmaf(r->dy, alpha, r->oy), wz = fmaf(r->dz, alpha, r->oz);
+    /* gradientForPoint(volume, last_world_pos, vertex) */
+    int hx = w2v(V, lx), hy = w2v(V, ly), hz = w2v(V, lz);
+    if (hx <= 1 || hx >= R - 2) return;
+    if (hy <= 1 || hy >= R - 2) return;
+    if (hz <= 1 || hz >= R - 2) return;
+    float cell = V->cell;
+    float f1, f2, nx, ny, nz;
+    if (!interp_sdf(V, wx + cell, wy, wz, &f1)) return;
+    if (!interp_sdf(V, wx - cell, wy, wz, &f2)) return;
+    nx = f1 - f2;
+    if (!interp_sdf(V, wx, wy + cell, wz, &f1)) return;
+    if (!interp_sdf(V, wx, wy - cell, wz, &f2)) return;
+    ny = f1 - f2;
+    if (!interp_sdf(V, wx, wy, wz + cell, &f1)) return;
+    if (!interp_sdf(V, wx, wy, wz - cell, &f2)) return;
+    nz = f1 - f2;
+    float l = sqrtf(dot3c(nx, ny, nz, nx, ny, nz));
+    if ((double)l < 1e-8) return;
+    float q = 1.0f / l;
+    ov[0] = wx; ov[1] = wy; ov[2] = wz; ov[3] = 1.0f;
+    on[0] = nx * q; on[1] = ny * q; on[2] = nz * q; on[3] = 0.f;
+}
+
 void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float inc,
                  float near_plane, float far_plane, float* out_v4, float* out_n4)
 {
     VolView V = volview(vol, R, S);
     const int cols = (int)cam->cols, rows = (int)cam->rows;
-    const float ox = pose[3], oy = pose[7], oz = pose[11];
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < rows; ++y)
         for (int x = 0; x < cols; ++x) {
@@ -396,65 +461,127 @@ void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const f
             float* on = out_n4 + 4 * ((size_t)y * cols + x);
             ov[0] = ov[1] = ov[2] = ov[3] = 0.f;
             on[0] = on[1] = on[2] = on[3] = 0.f;
-            /* cam_dir = normalize(depthToSkeleton(x,y,1)) ; z*z == 1 folds into "+ 1" */
-            float vx = ((float)(unsigned)x - cam->cx) / cam->fx;
-            float vy = ((float)(unsigned)y - cam->cy) / cam->fy;
-            float len = sqrtf(fmaf(vx, vx, vy * vy) + 1.0f);
-            float cdx, cdy, cdz;
-            if ((double)len < 1e-8) { cdx = cdy = cdz = 0.f; }
-            else { float r = 1.0f / len; cdx = vx * r; cdy = vy * r; cdz = r; }
-            /* world_dir = transform * (cam_dir, 0): lead-second rows, w = 0 */
-            float dx = fmaf(pose[3], 0.f, fmaf(cdz, pose[2], fmaf(cdx, pose[0], cdy * pose[1])));
-            float dy = fmaf(pose[7], 0.f, fmaf(cdz, pose[6], fmaf(cdx, pose[4], cdy * pose[5])));
-            float dz = fmaf(pose[11], 0.f, fmaf(cdz, pose[10], fmaf(cdx, pose[8], cdy * pose[9])));
-            if (dx == 0.f) dx = 1e-15f;
-            if (dy == 0.f) dy = 1e-15f;
-            if (dz == 0.f) dz = 1e-15f;
-            float txmin = ((dx > 0 ? 0.f : S) - ox) / dx, tymin = ((dy > 0 ? 0.f : S) - oy) / dy, tzmin = ((dz > 0 ? 0.f : S) - oz) / dz;
-            float tmin = fmaxf(fmaxf(txmin, tymin), tzmin);
-            float txmax = ((dx > 0 ? S : 0.f) - ox) / dx, tymax = ((dy > 0 ? S : 0.f) - oy) / dy, tzmax = ((dz > 0 ? S : 0.f) - oz) / dz;
-            float tmax = fminf(fminf(txmax, tymax), tzmax);
-            tmin = fmaxf(tmin, near_plane / cdz);
-            tmax = fminf(tmax, far_plane / cdz);
-            if (!(tmin < tmax)) continue;
-            float t = tmin, last_sdf = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
-            while (t < tmax) {
-                float px = fmaf(dx, t, ox), py = fmaf(dy, t, oy), pz = fmaf(dz, t, oz);
+            const Ray r = ray_setup(cam, pose, S, near_plane, far_plane, x, y);
+            if (!r.live) continue;
+            float t = r.tmin, last_sdf = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
+            while (t < r.tmax) {
+                float px = fmaf(r.dx, t, r.ox), py = fmaf(r.dy, t, r.oy), pz = fmaf(r.dz, t, r.oz);
                 int gx = clampi(w2v(&V, px), 0, R - 1), gy = clampi(w2v(&V, py), 0, R - 1), gz = clampi(w2v(&V, pz), 0, R - 1);
                 float sdf = voxel(&V, gx, gy, gz)[0];
                 if (last_sdf > 0.0f && sdf < 0.0f) {
-                    float ftdt, ft;
-                    if (!interp_sdf(&V, px, py, pz, &ftdt)) break;
-                    if (!interp_sdf(&V, lx, ly, lz, &ft)) break;
-                    float alpha = t - (inc * ftdt) / (ftdt - ft);
-                    float wx = fmaf(dx, alpha, ox), wy = fmaf(dy, alpha, oy), wz = fmaf(dz, alpha, oz);
-                    /* gradientForPoint(volume, last_world_pos, vertex) */
-                    int hx = w2v(&V, lx), hy = w2v(&V, ly), hz = w2v(&V, lz);
-                    if (hx <= 1 || hx >= R - 2) break;
-                    if (hy <= 1 || hy >= R - 2) break;
-                    if (hz <= 1 || hz >= R - 2) break;
-                    float cell = V.cell;
-                    float f1, f2, nx, ny, nz;
-                    if (!interp_sdf(&V, wx + cell, wy, wz, &f1)) break;
-                    if (!interp_sdf(&V, wx - cell, wy, wz, &f2)) break;
-                    nx = f1 - f2;
-                    if (!interp_sdf(&V, wx, wy + cell, wz, &f1)) break;
-                    if (!interp_sdf(&V, wx, wy - cell, wz, &f2)) break;
-                    ny = f1 - f2;
-                    if (!interp_sdf(&V, wx, wy, wz + cell, &f1)) break;
-                    if (!interp_sdf(&V, wx, wy, wz - cell, &f2)) break;
-                    nz = f1 - f2;
-                    float l = sqrtf(dot3c(nx, ny, nz, nx, ny, nz));
-                    if ((double)l < 1e-8) break;
-                    float r = 1.0f / l;
-                    ov[0] = wx; ov[1] = wy; ov[2] = wz; ov[3] = 1.0f;
-                    on[0] = nx * r; on[1] = ny * r; on[2] = nz * r; on[3] = 0.f;
+                    ray_hit(&V, &r, inc, t, px, py, pz, lx, ly, lz, ov, on);
                     break;
                 }
                 last_sdf = sdf; lx = px; ly = py; lz = pz;
                 t = inc + t;
             }
         }
+}
+
+/* ---- model of an empty-space-skipping march (NOT the reference's algorithm: a CPU statement of the optimisation planned
+   for csrc/raycast.cu, here so that its exactness claim can be checked against orc_raycast on this box).
+   flags[(bz*nb + by)*nb + bx] != 0 when brick (bx,by,bz) of `brick` voxels per side may hold a voxel with tsdf < 0.
+   A (+ -> -) pair ends in a voxel with tsdf < 0, i.e. in a flagged brick, so:
+    (1) a sample whose nearest voxel lies in an unflagged brick need not be READ (its tsdf is >= 0: it cannot end a pair);
+        if the next sample turns out negative, the skipped one is read after all (lazily) for the "last > 0" half;
+    (2) a batch of `nb_batch` consecutive samples is skipped without any per-sample work when the bricks (coarse flags)
+        touched by the axis-aligned box of the voxel indices of its FIRST and LAST sample are all unflagged: fma(d,t,o)
+        and the truncating voxel index are monotone in t, so every sample in between lies in that box.
+   stats: [0] samples visited by the reference march, [1] reads skipped by (1), [2] samples skipped by (2),
+          [3] violations of the box claim or of "skipped implies tsdf >= 0" (must stay 0) */
+void orc_build_ray_flags(const float* vol, int R, int brick, unsigned char* flags)
+{
+    VolView V = volview(vol, R, 1.0f);
+    const int nb = (R + brick - 1) / brick;
+    memset(flags, 0, (size_t)nb * nb * nb);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int z = 0; z < R; ++z)
+        for (int y = 0; y < R; ++y)
+            for (int x = 0; x < R; ++x)
+                if (voxel(&V, x, y, z)[0] < 0.f) flags[((size_t)(z / brick) * nb + y / brick) * nb + x / brick] = 1;
+}
+
+void orc_raycast_skip(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float inc,
+                      float near_plane, float far_plane, const unsigned char* fine, int fine_brick,
+                      const unsigned char* coarse, int coarse_brick, int nb_batch, float* out_v4, float* out_n4, long long stats[4])
+{
+    VolView V = volview(vol, R, S);
+    const int cols = (int)cam->cols, rows = (int)cam->rows;
+    const int nbf = (R + fine_brick - 1) / fine_brick, nbc = (R + coarse_brick - 1) / coarse_brick;
+    long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : s0, s1, s2, s3)
+    for (int y = 0; y < rows; ++y)
+        for (int x = 0; x < cols; ++x) {
+            float* ov = out_v4 + 4 * ((size_t)y * cols + x);
+            float* on = out_n4 + 4 * ((size_t)y * cols + x);
+            ov[0] = ov[1] = ov[2] = ov[3] = 0.f;
+            on[0] = on[1] = on[2] = on[3] = 0.f;
+            const Ray r = ray_setup(cam, pose, S, near_plane, far_plane, x, y);
+            if (!r.live) continue;
+            float t = r.tmin, last_sdf = 0.f, last_t = r.tmin;
+            int last_unread = 0;             /* the previous sample was skipped: last_sdf is not known yet */
+            while (t < r.tmax) {
+                /* (2) whole batch */
+                if (inc > 0.f && nb_batch > 1) {
+                    float te = t;
+                    for (int k = 1; k < nb_batch; ++k) te = inc + te;
+                    if (te < r.tmax) {
+                        int a[3], b[3];
+                        a[0] = clampi(w2v(&V, fmaf(r.dx, t, r.ox)), 0, R - 1); b[0] = clampi(w2v(&V, fmaf(r.dx, te, r.ox)), 0, R - 1);
+                        a[1] = clampi(w2v(&V, fmaf(r.dy, t, r.oy)), 0, R - 1); b[1] = clampi(w2v(&V, fmaf(r.dy, te, r.oy)), 0, R - 1);
+                        a[2] = clampi(w2v(&V, fmaf(r.dz, t, r.oz)), 0, R - 1); b[2] = clampi(w2v(&V, fmaf(r.dz, te, r.oz)), 0, R - 1);
+                        int lo[3], hi[3], any = 0;
+                        for (int d = 0; d < 3; ++d) { lo[d] = (a[d] < b[d] ? a[d] : b[d]); hi[d] = (a[d] < b[d] ? b[d] : a[d]); }
+                        for (int bz = lo[2] / coarse_brick; bz <= hi[2] / coarse_brick && !any; ++bz)
+                            for (int by = lo[1] / coarse_brick; by <= hi[1] / coarse_brick && !any; ++by)
+                                for (int bx = lo[0] / coarse_brick; bx <= hi[0] / coarse_brick; ++bx)
+                                    if (coarse[((size_t)bz * nbc + by) * nbc + bx]) { any = 1; break; }
+                        if (!any) {
+                            /* check the claim on every sample of the batch (test instrumentation only) */
+                            float tk = t;
+                            for (int k = 0; k < nb_batch; ++k) {
+                                int g[3] = { clampi(w2v(&V, fmaf(r.dx, tk, r.ox)), 0, R - 1), clampi(w2v(&V, fmaf(r.dy, tk, r.oy)), 0, R - 1),
+                                             clampi(w2v(&V, fmaf(r.dz, tk, r.oz)), 0, R - 1) };
+                                for (int d = 0; d < 3; ++d) if (g[d] < lo[d] || g[d] > hi[d]) ++s3;
+                                if (voxel(&V, g[0], g[1], g[2])[0] < 0.f) ++s3;
+                                last_t = tk;
+                                tk = inc + tk;
+                            }
+                            s0 += nb_batch; s2 += nb_batch;
+                            last_unread = 1;
+                            t = tk;
+                            continue;
+                        }
+                    }
+                }
+                /* per sample */
+                float px = fmaf(r.dx, t, r.ox), py = fmaf(r.dy, t, r.oy), pz = fmaf(r.dz, t, r.oz);
+                int gx = clampi(w2v(&V, px), 0, R - 1), gy = clampi(w2v(&V, py), 0, R - 1), gz = clampi(w2v(&V, pz), 0, R - 1);
+                ++s0;
+                if (!fine[((size_t)(gz / fine_brick) * nbf + gy / fine_brick) * nbf + gx / fine_brick]) {
+                    /* (1) not read */
+                    if (voxel(&V, gx, gy, gz)[0] < 0.f) ++s3;
+                    ++s1;
+                    last_unread = 1; last_t = t;
+                    t = inc + t;
+                    continue;
+                }
+                float sdf = voxel(&V, gx, gy, gz)[0];
+                if (sdf < 0.0f && last_unread) {
+                    /* the skipped predecessor is needed after all */
+                    float qx = fmaf(r.dx, last_t, r.ox), qy = fmaf(r.dy, last_t, r.oy), qz = fmaf(r.dz, last_t, r.oz);
+                    last_sdf = voxel(&V, clampi(w2v(&V, qx), 0, R - 1), clampi(w2v(&V, qy), 0, R - 1), clampi(w2v(&V, qz), 0, R - 1))[0];
+                    last_unread = 0;
+                }
+                if (!last_unread && last_sdf > 0.0f && sdf < 0.0f) {
+                    ray_hit(&V, &r, inc, t, px, py, pz, fmaf(r.dx, last_t, r.ox), fmaf(r.dy, last_t, r.oy), fmaf(r.dz, last_t, r.oz), ov, on);
+                    break;
+                }
+                last_sdf = sdf; last_unread = 0; last_t = t;
+                t = inc + t;
+            }
+        }
+    if (stats) { stats[0] = s0; stats[1] = s1; stats[2] = s2; stats[3] = s3; }
 }
 
 /* ------------------------------------------------------------------ host-math exports */

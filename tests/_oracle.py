@@ -162,6 +162,26 @@ def raycast(vol, cfg, pose):
     return v, n
 
 
+def ray_flags(vol, R, brick):
+    nb = (R + brick - 1) // brick
+    f = np.zeros((nb, nb, nb), np.uint8)
+    cpu().orc_build_ray_flags(_fp(vol), R, brick, f.ctypes.data_as(C.c_void_p))
+    return f
+
+
+def raycast_skip(vol, cfg, pose, fine, fine_brick, coarse, coarse_brick, batch=8):
+    """CPU model of the empty-space-skipping march (oracle/hkf_oracle.c: orc_raycast_skip) -> v, n, stats[4]"""
+    cam = cam_of(cfg)
+    v = np.empty((cfg.rows, cfg.cols, 4), np.float32)
+    n = np.empty_like(v)
+    st = np.zeros(4, np.int64)
+    p = np.ascontiguousarray(pose, np.float32).reshape(16)
+    cpu().orc_raycast_skip(_fp(vol), cfg.resolution, C.c_float(cfg.volume_size), C.byref(cam), _fp(p), C.c_float(cfg.ray_increment),
+                           C.c_float(cfg.trunc_min), C.c_float(cfg.trunc_max), fine.ctypes.data_as(C.c_void_p), fine_brick,
+                           coarse.ctypes.data_as(C.c_void_p), coarse_brick, batch, _fp(v), _fp(n), st.ctypes.data_as(C.c_void_p))
+    return v, n, st
+
+
 def sdf_sums(vol, cfg, depth, cur):
     cam = cam_of(cfg)
     out = np.zeros(27, np.float32)
