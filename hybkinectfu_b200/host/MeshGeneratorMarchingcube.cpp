@@ -1,4 +1,7 @@
 #include "MeshGeneratorMarchingcube.h"
+#include <cstdint>
+#include <cstring>
+#include <unordered_map>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -26,32 +29,57 @@ bool MeshGeneratorMarchingcube::copyTrianglesToCPU()
     return hkf_download(c, HKF_BUF_TRIANGLES, 0, _soup.data(), _soup.size() * sizeof(HkfTriangle)) == (long)(n * sizeof(HkfTriangle));
 }
 
+namespace {
+struct Vec3Hash {
+    size_t operator()(const std::array<uint32_t, 3>& k) const
+    {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (uint32_t w : k) { h ^= w; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
+        return (size_t)h;
+    }
+};
+inline uint32_t float_bits(float f) { if (f == 0.f) f = 0.f; uint32_t u; std::memcpy(&u, &f, 4); return u; }   // -0 welds with +0
+}
+
+// Canonical order first (marching cubes appends triangles in a nondeterministic order): the soup is sorted by its nine
+// position floats, so vertex numbering and face order - hence the file - depend on the volume only.  Keys are gathered
+// once (the comparator touches 36 contiguous bytes), vertices are numbered through a hash of their bit patterns.
 void MeshGeneratorMarchingcube::weld(std::vector<HkfTriangle> soup, std::vector<std::array<float, 3>>& vertices,
                                      std::vector<std::array<unsigned, 3>>& faces)
 {
-    auto key = [](const HkfTriangle& t) { std::array<float, 9> k; const HkfVertex* v = &t.v0; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) k[i * 3 + j] = v[i].pos[j]; return k; };
-    std::sort(soup.begin(), soup.end(), [&](const HkfTriangle& a, const HkfTriangle& b) { return key(a) < key(b); });
-    std::map<std::array<float, 3>, unsigned> index;
+    const size_t n = soup.size();
+    std::vector<std::array<float, 9>> keys(n);
+    for (size_t t = 0; t < n; ++t) {
+        const HkfVertex* v = &soup[t].v0;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) keys[t][i * 3 + j] = v[i].pos[j];
+    }
+    std::sort(keys.begin(), keys.end());
+    std::unordered_map<std::array<uint32_t, 3>, unsigned, Vec3Hash> index;
+    index.reserve(n * 2);
     vertices.clear(); faces.clear();
-    for (const HkfTriangle& t : soup) {
-        const HkfVertex* v = &t.v0;
+    vertices.reserve(n); faces.reserve(n);
+    for (const auto& k : keys) {
         std::array<unsigned, 3> f;
         for (int i = 0; i < 3; ++i) {
-            std::array<float, 3> p = { v[i].pos[0], v[i].pos[1], v[i].pos[2] };
-            auto it = index.find(p);
-            if (it == index.end()) { it = index.emplace(p, (unsigned)vertices.size()).first; vertices.push_back(p); }
+            const std::array<float, 3> p = { k[i * 3], k[i * 3 + 1], k[i * 3 + 2] };
+            const std::array<uint32_t, 3> bits = { float_bits(p[0]), float_bits(p[1]), float_bits(p[2]) };
+            auto it = index.find(bits);
+            if (it == index.end()) { it = index.emplace(bits, (unsigned)vertices.size()).first; vertices.push_back(p); }
             f[i] = it->second;
         }
         if (f[0] == f[1] || f[1] == f[2] || f[0] == f[2]) continue;                 // degenerate after welding
         faces.push_back(f);
     }
-    // duplicate faces (same vertex set) are dropped, as ml::MeshData::removeDuplicateFaces does
+    // duplicate faces (same vertex set) are dropped, as ml::MeshData::removeDuplicateFaces does; the first in canonical
+    // order stays
+    std::unordered_map<std::array<uint32_t, 3>, bool, Vec3Hash> seen;
+    seen.reserve(faces.size() * 2);
     std::vector<std::array<unsigned, 3>> uniq;
-    std::map<std::array<unsigned, 3>, bool> seen;
+    uniq.reserve(faces.size());
     for (const auto& f : faces) {
-        std::array<unsigned, 3> s = f;
-        std::sort(s.begin(), s.end());
-        if (seen.emplace(s, true).second) uniq.push_back(f);
+        std::array<uint32_t, 3> s3 = { f[0], f[1], f[2] };
+        std::sort(s3.begin(), s3.end());
+        if (seen.emplace(s3, true).second) uniq.push_back(f);
     }
     faces.swap(uniq);
 }
