@@ -1,4 +1,5 @@
 #include "MeshGeneratorMarchingcube.h"
+#include <charconv>
 #include <cstdint>
 #include <cstring>
 #include <unordered_map>
@@ -113,6 +114,39 @@ void MeshGeneratorMarchingcube::vertexNormals(const std::vector<std::array<float
     for (auto& n : normals) n = unit(n);
 }
 
+namespace {
+// Text output through std::to_chars (same characters as printf's %.9g / %.6g / %u in the C locale, several times
+// faster than fprintf: a 553 k-triangle OBJ is 42 MB of numbers) into one buffer that is flushed in large pieces.
+class TextOut {
+public:
+    explicit TextOut(FILE* f) : _f(f) { _buf.reserve(1 << 22); }
+    void str(const char* s) { _buf.append(s); }
+    void num(float v, int precision)
+    {
+        char tmp[48];
+        auto r = std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::general, precision);
+        _buf.append(tmp, r.ptr);
+    }
+    void num(unsigned v)
+    {
+        char tmp[16];
+        auto r = std::to_chars(tmp, tmp + sizeof(tmp), v);
+        _buf.append(tmp, r.ptr);
+    }
+    void maybe_flush() { if (_buf.size() > (1u << 22) - 4096) flush(); }
+    bool flush()
+    {
+        if (!_buf.empty() && std::fwrite(_buf.data(), 1, _buf.size(), _f) != _buf.size()) _ok = false;
+        _buf.clear();
+        return _ok;
+    }
+private:
+    FILE* _f;
+    std::string _buf;
+    bool _ok = true;
+};
+}
+
 bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std::vector<std::array<float, 3>>& v,
                                           const std::vector<std::array<unsigned, 3>>& faces, const std::vector<std::array<float, 3>>& normals)
 {
@@ -122,30 +156,40 @@ bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std
     const bool with_n = normals.size() == v.size();
     FILE* f = std::fopen(filename.c_str(), "w");
     if (!f) return false;
+    TextOut o(f);
+    auto vec3 = [&](const char* lead, const std::array<float, 3>& p, int precision, const char* tail) {
+        o.str(lead); o.num(p[0], precision); o.str(" "); o.num(p[1], precision); o.str(" "); o.num(p[2], precision); o.str(tail);
+        o.maybe_flush();
+    };
     if (ext == "ply") {
         std::fprintf(f, "ply\nformat ascii 1.0\ncomment hybKinectfu marching-cubes mesh\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z\n", v.size());
         if (with_n) std::fprintf(f, "property float nx\nproperty float ny\nproperty float nz\n");
         std::fprintf(f, "element face %zu\nproperty list uchar int vertex_indices\nend_header\n", faces.size());
         for (size_t i = 0; i < v.size(); ++i) {
-            std::fprintf(f, "%.9g %.9g %.9g", v[i][0], v[i][1], v[i][2]);
-            if (with_n) std::fprintf(f, " %.6g %.6g %.6g", normals[i][0], normals[i][1], normals[i][2]);
-            std::fprintf(f, "\n");
+            vec3("", v[i], 9, with_n ? "" : "\n");
+            if (with_n) vec3(" ", normals[i], 6, "\n");
         }
-        for (const auto& t : faces) std::fprintf(f, "3 %u %u %u\n", t[0], t[1], t[2]);
+        for (const auto& t : faces) { o.str("3 "); o.num(t[0]); o.str(" "); o.num(t[1]); o.str(" "); o.num(t[2]); o.str("\n"); o.maybe_flush(); }
     } else if (ext == "off") {
         std::fprintf(f, "OFF\n%zu %zu 0\n", v.size(), faces.size());
-        for (const auto& p : v) std::fprintf(f, "%.9g %.9g %.9g\n", p[0], p[1], p[2]);
-        for (const auto& t : faces) std::fprintf(f, "3 %u %u %u\n", t[0], t[1], t[2]);
+        for (const auto& p : v) vec3("", p, 9, "\n");
+        for (const auto& t : faces) { o.str("3 "); o.num(t[0]); o.str(" "); o.num(t[1]); o.str(" "); o.num(t[2]); o.str("\n"); o.maybe_flush(); }
     } else {
         std::fprintf(f, "# hybKinectfu marching-cubes mesh\n# vertices %zu\n# faces %zu\n", v.size(), faces.size());
-        for (const auto& p : v) std::fprintf(f, "v %.9g %.9g %.9g\n", p[0], p[1], p[2]);
-        if (with_n) for (const auto& n : normals) std::fprintf(f, "vn %.6g %.6g %.6g\n", n[0], n[1], n[2]);
+        for (const auto& p : v) vec3("v ", p, 9, "\n");
+        if (with_n) for (const auto& n : normals) vec3("vn ", n, 6, "\n");
         for (const auto& t : faces) {
-            if (with_n) std::fprintf(f, "f %u//%u %u//%u %u//%u\n", t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1);
-            else std::fprintf(f, "f %u %u %u\n", t[0] + 1, t[1] + 1, t[2] + 1);
+            o.str("f ");
+            for (int i = 0; i < 3; ++i) {
+                o.num(t[i] + 1);
+                if (with_n) { o.str("//"); o.num(t[i] + 1); }
+                o.str(i < 2 ? " " : "\n");
+            }
+            o.maybe_flush();
         }
     }
-    return std::fclose(f) == 0;
+    const bool ok = o.flush();
+    return (std::fclose(f) == 0) && ok;
 }
 
 bool MeshGeneratorMarchingcube::saveMesh(const std::string& filename)
