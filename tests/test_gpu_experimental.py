@@ -36,6 +36,7 @@ for i, mm in enumerate(frames):
     maps.append(np.concatenate([ctx.download(capi.BUF_MODEL_VERTICES).ravel(), ctx.download(capi.BUF_MODEL_NORMALS).ravel()]))
 np.save(sys.argv[1], np.stack(poses))
 np.save(sys.argv[1] + ".maps.npy", np.stack(maps))
+np.save(sys.argv[1] + ".vol.npy", ctx.download(capi.BUF_VOLUME))
 """
 
 
@@ -44,20 +45,31 @@ def _poses(tmp_path, name, env):
     r = subprocess.run([sys.executable, "-c", _TRACK.format(root=ROOT), out], env=dict(os.environ, **env),
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
-    return np.load(out), np.load(out + ".maps.npy")
+    return np.load(out), np.load(out + ".maps.npy"), np.load(out + ".vol.npy")
 
 
 @pytest.mark.parametrize("cs", ["8", "16"])
 def test_cluster_icp_equals_per_iteration_launches(tmp_path, cs):
-    ref, _ = _poses(tmp_path, "default", {"HKF_ICP_CLUSTER": "0"})
-    got, _ = _poses(tmp_path, "cluster" + cs, {"HKF_ICP_CLUSTER": cs})
+    ref, _, _ = _poses(tmp_path, "default", {"HKF_ICP_CLUSTER": "0"})
+    got, _, _ = _poses(tmp_path, "cluster" + cs, {"HKF_ICP_CLUSTER": cs})
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
 
 
 def test_raycast_empty_space_skipping_is_exact(tmp_path):
     """HKF_RAY_SKIP=1: brick flags from the integration item pass + skipped samples / batches in the ray march; the model
     maps of every frame (and therefore the poses) must not change by a bit (CPU model: tests/test_raycast_skip_model.py)"""
-    ref, ref_maps = _poses(tmp_path, "default", {"HKF_RAY_SKIP": "0"})
-    got, got_maps = _poses(tmp_path, "skip", {"HKF_RAY_SKIP": "1"})
+    ref, ref_maps, ref_vol = _poses(tmp_path, "default", {"HKF_RAY_SKIP": "0"})
+    got, got_maps, got_vol = _poses(tmp_path, "skip", {"HKF_RAY_SKIP": "1"})
+    assert np.array_equal(ref_maps.view(np.uint32), got_maps.view(np.uint32))
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+    assert np.array_equal(ref_vol.view(np.uint32), got_vol.view(np.uint32))
+
+
+def test_wider_tile_span_classifier_is_exact(tmp_path):
+    """HKF_INT_SPAN=3: the integration item pass tests a chunk against up to four finer depth tiles per tile row; the
+    classification stays conservative, so the volume (and everything downstream) must not change by a bit"""
+    ref, ref_maps, ref_vol = _poses(tmp_path, "default", {"HKF_INT_SPAN": "1"})
+    got, got_maps, got_vol = _poses(tmp_path, "span3", {"HKF_INT_SPAN": "3"})
+    assert np.array_equal(ref_vol.view(np.uint32), got_vol.view(np.uint32))
     assert np.array_equal(ref_maps.view(np.uint32), got_maps.view(np.uint32))
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))

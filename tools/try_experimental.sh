@@ -9,6 +9,8 @@ echo "== default"
 timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
 echo "== HKF_RAY_SKIP=1"
 HKF_RAY_SKIP=1 timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
+echo "== HKF_INT_SPAN=3"
+HKF_INT_SPAN=3 timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
 for cs in 8 16; do
     echo "== HKF_ICP_CLUSTER=$cs"
     HKF_ICP_CLUSTER=$cs timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
