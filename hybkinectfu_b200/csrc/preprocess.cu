@@ -332,6 +332,111 @@ __global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __
     }
 }
 
+// ---------------------------------------------------------------- EXPERIMENTAL split (HKF_PRE_V2=1, off by default)
+// Written at the end of round 1 without GPU time left: unmeasured, exercised only by tests/test_gpu_experimental.py.
+// k_preprocess_fused filters 340 pixels per 256-pixel tile (a 1-pixel halo, only so that the tile can form its normals)
+// and the bilateral filter is all of its time.  Here the tile kernel filters exactly its own 256 pixels and stops at the
+// filtered depth; vertices, normals and BOTH coarser pyramid levels come from one second launch that reads the filtered
+// map (L2-resident) with the raycast's 8x4-pixel warp patches, so that the 2x2 and 4x4 blocks of the pyramid are warp
+// shuffles (lane ^ 1, ^ 8, ^ 9, then ^ 2, ^ 16, ^ 18) - it replaces k_pyramids_fused for the new frame.
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+k_preprocess_tile_v2(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, float* __restrict__ trunc_out,
+                     float* __restrict__ filt_out, int cols, int rows, int radius, float tmin, float tmax, float ss, float sd,
+                     float thresh, DepthBounds B)
+{
+    extern __shared__ float smem[];
+    __shared__ unsigned s_tmax[TILE_W * TILE_H / 32], s_tmin[TILE_W * TILE_H / 32];
+    const int ap = radius;
+    const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
+    float* s_trunc = smem;              // tw*th, 0 outside the image
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * TILE_H;
+    unsigned local_max = 0, local_min = 0xffffffffu;
+    for (int i = tid; i < tw * th; i += TILE_W * TILE_H) {
+        int lx = i % tw, ly = i / tw;
+        int gx = bx0 - ap + lx, gy = by0 - ap + ly;
+        float t = 0.f;
+        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+            float d = decode_mm(__ldg(mm + (size_t)gy * cols + gx));
+            t = trunc_depth(d, tmin, tmax);
+            if (lx >= ap && lx < ap + TILE_W && ly >= ap && ly < ap + TILE_H) {
+                raw_out[(size_t)gy * cols + gx] = d;
+                trunc_out[(size_t)gy * cols + gx] = t;
+                local_max = max(local_max, __float_as_uint(t));
+                local_min = min(local_min, __float_as_uint(t));
+            }
+        }
+        s_trunc[i] = t;
+    }
+    local_max = __reduce_max_sync(0xffffffffu, local_max);
+    local_min = __reduce_min_sync(0xffffffffu, local_min);
+    if ((tid & 31) == 0) { s_tmax[tid >> 5] = local_max; s_tmin[tid >> 5] = local_min; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned mx = 0, mn = 0xffffffffu;
+        for (int i = 0; i < TILE_W * TILE_H / 32; ++i) { mx = max(mx, s_tmax[i]); mn = min(mn, s_tmin[i]); }
+        hkf_bounds_publish(B, blockIdx.x, blockIdx.y, mx, mn);
+    }
+    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    auto at = [&](int gx, int gy) { return s_trunc[(gy - by0 + ap) * tw + (gx - bx0 + ap)]; };
+    float f;
+    if (radius == 4) f = bilateral_px_tile<4>(s_trunc + (threadIdx.y + ap) * tw + (threadIdx.x + ap), tw, ss, sd, thresh);
+    else f = bilateral_px(at, x, y, cols, rows, radius, ss, sd, thresh);
+    filt_out[(size_t)y * cols + x] = f;
+}
+
+__global__ void __launch_bounds__(256)
+k_maps_pyramids_v2(const float* __restrict__ filt, float4* __restrict__ v0o, float4* __restrict__ n0o,
+                   float4* __restrict__ v1, float4* __restrict__ n1, float4* __restrict__ v2, float4* __restrict__ n2,
+                   int cols, int rows, unsigned c1, unsigned r1, unsigned c2, unsigned r2, float cx, float cy, float fx, float fy)
+{
+    hkf_pdl_enter();
+    // 16x16 pixel block, warps as 8x4 patches (patch origins are multiples of 8 and 4: 2x2 and 4x4 blocks never straddle warps)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
+    if (x < cols && y < rows) {
+        const size_t gi = (size_t)y * cols + x;
+        v = back_project(x, y, filt[gi], cx, cy, fx, fy);
+        if (!(x == cols - 1 || y == rows - 1 || x == 0 || y == 0)) {
+            const float4 vr = back_project(x + 1, y, filt[gi + 1], cx, cy, fx, fy);
+            const float4 vu = back_project(x, y + 1, filt[gi + cols], cx, cy, fx, fy);
+            const float4 vl = back_project(x - 1, y, filt[gi - 1], cx, cy, fx, fy);
+            const float4 vd = back_project(x, y - 1, filt[gi - cols], cx, cy, fx, fy);
+            n = normal_from(v, vr, vu, vl, vd);
+        }
+        v0o[gi] = v;
+        n0o[gi] = n;
+    }
+    if (v1 == nullptr) return;                                   // one level only (uniform)
+    auto sh = [&](const float4& a, int m) {
+        return make_float4(__shfl_xor_sync(0xffffffffu, a.x, m), __shfl_xor_sync(0xffffffffu, a.y, m),
+                           __shfl_xor_sync(0xffffffffu, a.z, m), __shfl_xor_sync(0xffffffffu, a.w, m));
+    };
+    // level 1: the lane with even x and even y holds p00; p01 = x+1 (lane^1), p10 = y+1 (lane^8), p11 (lane^9)
+    const float4 v01 = sh(v, 1), v10 = sh(v, 8), v11 = sh(v, 9);
+    const float4 n01 = sh(n, 1), n10 = sh(n, 8), n11 = sh(n, 9);
+    float4 lv = make_float4(0.f, 0.f, 0.f, 0.f), ln = lv;
+    const unsigned x1 = (unsigned)x >> 1, y1 = (unsigned)y >> 1;
+    if (!(lane & 1) && !(lane & 8) && x1 < c1 && y1 < r1) {
+        lv = down_vertex(v, v01, v10, v11);
+        ln = down_normal(n, n01, n10, n11);
+        v1[(size_t)y1 * c1 + x1] = lv;
+        n1[(size_t)y1 * c1 + x1] = ln;
+    }
+    if (v2 == nullptr) return;
+    // level 2: level-1 pixels sit on the lanes with even x, y; p01 = x+2 (lane^2), p10 = y+2 (lane^16), p11 (lane^18)
+    const float4 w01 = sh(lv, 2), w10 = sh(lv, 16), w11 = sh(lv, 18);
+    const float4 m01 = sh(ln, 2), m10 = sh(ln, 16), m11 = sh(ln, 18);
+    const unsigned x2 = (unsigned)x >> 2, y2 = (unsigned)y >> 2;
+    if (!(lane & 3) && !(lane & 24) && x2 < c2 && y2 < r2) {
+        v2[(size_t)y2 * c2 + x2] = down_vertex(lv, w01, w10, w11);
+        n2[(size_t)y2 * c2 + x2] = down_normal(ln, m01, m10, m11);
+    }
+}
+
 // ---------------------------------------------------------------- host entry points
 
 static inline void bilateral_consts(float sigma_pixel, float sigma_depth, int* radius, float* ss, float* sd, float* thresh)
@@ -441,10 +546,24 @@ static int run_preprocess(hkf_ctx* c, cudaStream_t stream, HkfFrameSet& F, const
     if (radius < 0 || radius > 12) { c->err = "hkf_preprocess: bilateral radius out of range for the fused kernel"; return HKF_ERR_ARG; }
     HKF_CUDA(c, cudaMemsetAsync(F.bounds.base, 0, c->bounds_zero_bytes, stream));
     static_assert(TILE_W == HKF_TILE_W && TILE_H == HKF_TILE_H, "preprocess tile = integration culling tile");
-    const int ap = radius + 1;
-    size_t smem = ((TILE_W + 2 * ap) * (TILE_H + 2 * ap) + (TILE_W + 2) * (TILE_H + 2)) * sizeof(float);
     dim3 b(TILE_W, TILE_H), g(div_up(c->cols[0], TILE_W), div_up(c->rows[0], TILE_H));
     const HkfCameraParams& cam = c->ip.depth_camera;
+    static const bool v2 = getenv("HKF_PRE_V2") && getenv("HKF_PRE_V2")[0] == '1';      // experimental split, see above
+    if (v2) {
+        const size_t smem2 = (size_t)(TILE_W + 2 * radius) * (TILE_H + 2 * radius) * sizeof(float);
+        k_preprocess_tile_v2<<<g, b, smem2, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, (int)c->cols[0], (int)c->rows[0], radius,
+                                                      fp->trunc_min, fp->trunc_max, ss, sd, thresh, F.bounds);
+        HKF_LAUNCH_CHECK(c);
+        const bool two = c->levels >= 2, three = c->levels >= 3;
+        hkf_launch_pdl(k_maps_pyramids_v2, dim3(div_up(c->cols[0], 16), div_up(c->rows[0], 16)), dim3(256), 0, stream, (const float*)F.filtered_depth,
+                       F.new_v[0], F.new_n[0], two ? F.new_v[1] : (float4*)nullptr, two ? F.new_n[1] : (float4*)nullptr,
+                       three ? F.new_v[2] : (float4*)nullptr, three ? F.new_n[2] : (float4*)nullptr, (int)c->cols[0], (int)c->rows[0],
+                       two ? c->cols[1] : 0u, two ? c->rows[1] : 0u, three ? c->cols[2] : 0u, three ? c->rows[2] : 0u, cam.cx, cam.cy, cam.fx, cam.fy);
+        HKF_LAUNCH_CHECK(c);
+        return HKF_OK;
+    }
+    const int ap = radius + 1;
+    size_t smem = ((TILE_W + 2 * ap) * (TILE_H + 2 * ap) + (TILE_W + 2) * (TILE_H + 2)) * sizeof(float);
     k_preprocess_fused<<<g, b, smem, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, F.new_v[0], F.new_n[0],
                                                (int)c->cols[0], (int)c->rows[0], radius, fp->trunc_min, fp->trunc_max, ss, sd, thresh,
                                                cam.cx, cam.cy, cam.fx, cam.fy, F.bounds);

@@ -73,3 +73,42 @@ def test_wider_tile_span_classifier_is_exact(tmp_path):
     assert np.array_equal(ref_vol.view(np.uint32), got_vol.view(np.uint32))
     assert np.array_equal(ref_maps.view(np.uint32), got_maps.view(np.uint32))
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+def test_split_preprocess_is_exact(tmp_path):
+    """HKF_PRE_V2=1: tile kernel without the normals halo + one launch for vertices, normals and both pyramid levels
+    (warp-shuffle 2x2 / 4x4 blocks); every downstream bit must stay the same"""
+    ref, ref_maps, ref_vol = _poses(tmp_path, "default", {"HKF_PRE_V2": "0"})
+    got, got_maps, got_vol = _poses(tmp_path, "prev2", {"HKF_PRE_V2": "1"})
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+    assert np.array_equal(ref_vol.view(np.uint32), got_vol.view(np.uint32))
+    assert np.array_equal(ref_maps.view(np.uint32), got_maps.view(np.uint32))
+
+
+def test_split_preprocess_maps_equal_stage_by_stage():
+    """the new-frame maps of every pyramid level, default vs HKF_PRE_V2=1, in two subprocesses (the switch is read once)"""
+    script = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from conftest import small_config
+from hybkinectfu_b200 import capi, synth
+cfg = small_config(64)
+cam = synth.Camera().scaled(192, 144)
+mm = synth.render_depth_mm(synth.trajectory(200)[7], cam, noise_sigma_mm=1.0, rng=np.random.default_rng(3))
+ctx = capi.Context(cfg)
+ctx.preprocess(mm)
+out = [ctx.download(b).ravel() for b in (capi.BUF_RAW_DEPTH, capi.BUF_TRUNC_DEPTH, capi.BUF_FILTERED_DEPTH)]
+for l in range(3):
+    out += [ctx.download(capi.BUF_NEW_VERTICES, l).ravel(), ctx.download(capi.BUF_NEW_NORMALS, l).ravel()]
+np.save(sys.argv[1], np.concatenate(out))
+"""
+    import tempfile
+    res = []
+    for v in ("0", "1"):
+        with tempfile.TemporaryDirectory() as d:
+            out = os.path.join(d, "o.npy")
+            r = subprocess.run([sys.executable, "-c", script.format(root=ROOT), out], env=dict(os.environ, HKF_PRE_V2=v),
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res.append(np.load(out))
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))

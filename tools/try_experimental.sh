@@ -6,9 +6,11 @@ cd "$(dirname "$0")/.." || exit 1
 echo "== gated tests"
 HKF_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q 2>&1 | tail -15
 echo "== default"
-timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
+timeout 60 python tools/stage_times.py 2>&1 | grep -E "preprocess|icp_track|raycast_tracked|integrate_tracked|sum of"
 echo "== HKF_RAY_SKIP=1"
 HKF_RAY_SKIP=1 timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
+echo "== HKF_PRE_V2=1"
+HKF_PRE_V2=1 timeout 60 python tools/stage_times.py 2>&1 | grep -E "preprocess|icp_track|raycast_tracked|integrate_tracked|sum of"
 echo "== HKF_INT_SPAN=3"
 HKF_INT_SPAN=3 timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
 for cs in 8 16; do
