@@ -184,7 +184,7 @@ struct hkf_ctx {
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(HKF_EMULATE_DEVICE)   /* the latter: tests/emu compiles kernels for the host */
 // Launch with programmatic stream serialisation: the grid may become resident while its predecessor in the stream is
 // still draining (every kernel launched this way starts with hkf_pdl_enter(), which releases ITS successor early and
 // then waits for the predecessor's completion and memory flush), which hides the launch latency between the
@@ -202,16 +202,20 @@ static inline cudaError_t hkf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
 }
 __device__ __forceinline__ void hkf_pdl_enter()
 {
+#ifndef HKF_EMULATE_DEVICE
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 }
 // The same with the successor released only AFTER the predecessor has completed: for a kernel whose successor reads,
 // before its own wait, data written two launches back (k_icp loads the new frame's pyramid level ahead of its wait;
 // with the early release above it could become resident while the kernel that builds that pyramid is still running).
 __device__ __forceinline__ void hkf_pdl_enter_ordered()
 {
+#ifndef HKF_EMULATE_DEVICE
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 #endif
 
@@ -222,7 +226,7 @@ int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 
 // ---------------------------------------------------------------- device arithmetic contract
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(HKF_EMULATE_DEVICE)
 
 // a producer block publishes the extrema (float bits, mn with invalid = 0) of level-0 tile (tx0, ty)
 __device__ __forceinline__ void hkf_bounds_publish(const DepthBounds& B, int tx0, int ty, unsigned mx, unsigned mn)

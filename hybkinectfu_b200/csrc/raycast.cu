@@ -272,6 +272,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
     if (SLAB) keys[pix] = key;
 }
 
+#ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
 static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParams* rp, const HkfCameraParams* cam,
                           float near_plane, float far_plane, RaycastArgs* A)
 {
@@ -340,3 +341,4 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     if (c->nranks > 1 && !manual) return hkf_shard_composite_raycast(c);
     return HKF_OK;
 }
+#endif // HKF_EMULATE_DEVICE

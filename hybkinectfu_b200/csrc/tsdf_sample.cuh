@@ -31,7 +31,7 @@ static inline VolView make_volview(const hkf_ctx* c)
     return V;
 }
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(HKF_EMULATE_DEVICE)
 __device__ __forceinline__ int vol_w2v(const VolView& V, float p)
 {
     return __float2int_rz(__fdiv_rn(__fmul_rn(p, V.Rf), V.S));

@@ -1,0 +1,39 @@
+// raycast_emu.cpp — the ray-march kernel of hybkinectfu_b200/csrc/raycast.cu compiled for the host and run thread by
+// thread (tests/test_raycast_emulated.py compares it with the CPU oracle).  Test infrastructure, not a CPU fallback: the
+// product library never links this.
+#include "emu_shim.h"
+#include "../../hybkinectfu_b200/csrc/tsdf_sample.cuh"
+#include "emu_indices.h"
+#include "../../hybkinectfu_b200/csrc/raycast.cu"
+
+extern "C" int emu_raycast(const float* vol, int R, float S, unsigned cols, unsigned rows, float cx, float cy, float fx, float fy,
+                           const float* pose16, float inc, float near_plane, float far_plane,
+                           unsigned* fine_bits, unsigned* coarse_bits, int fast, int skip, float* out_v4, float* out_n4)
+{
+    RaycastArgs A;
+    memset(&A, 0, sizeof(A));
+    A.V.vol = reinterpret_cast<const float2*>(vol);
+    A.V.R = R; A.V.S = S; A.V.Rf = (float)R; A.V.cell = S / (float)R; A.V.z_lo = 0; A.V.z_hi = R;
+    A.cols = (int)cols; A.rows = (int)rows; A.cx = cx; A.cy = cy; A.fx = fx; A.fy = fy;
+    A.inc = inc; A.near_plane = near_plane; A.far_plane = far_plane;
+    memcpy(A.pose, pose16, 64);
+    A.own_z0 = 0; A.own_z1 = R; A.rank = 0; A.mailbox = nullptr; A.nranks = 1; A.epoch = 0;
+    A.RF.fine = fine_bits; A.RF.coarse = coarse_bits;
+    A.RF.nbf = (R + HKF_RAY_FINE - 1) / HKF_RAY_FINE; A.RF.nbc = (R + HKF_RAY_COARSE - 1) / HKF_RAY_COARSE;
+    if (skip && !(fast && fine_bits && coarse_bits)) return 1;
+    float4* ov = reinterpret_cast<float4*>(out_v4);
+    float4* on = reinterpret_cast<float4*>(out_n4);
+    const unsigned gx = (cols + 15) / 16, gy = (rows + 15) / 16;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    for (unsigned by = 0; by < gy; ++by)
+        for (unsigned bx = 0; bx < gx; ++bx) {
+            emu_blockIdx = { bx, by, 0 }; emu_blockDim = { 256, 1, 1 }; emu_gridDim = { gx, gy, 1 };
+            for (unsigned t = 0; t < 256; ++t) {
+                emu_threadIdx = { t, 0, 0 };
+                if (skip) k_raycast<false, false, true, true>(A, ov, on, nullptr, nullptr);
+                else if (fast) k_raycast<false, false, true, false>(A, ov, on, nullptr, nullptr);
+                else k_raycast<false, false, false, false>(A, ov, on, nullptr, nullptr);
+            }
+        }
+    return 0;
+}
