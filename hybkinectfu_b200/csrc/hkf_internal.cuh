@@ -184,6 +184,13 @@ struct hkf_ctx {
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+// dynamic shared memory of a kernel: `HKF_DYN_SMEM(float, smem);` (tests/emu maps it onto a host buffer)
+#ifdef HKF_EMULATE_DEVICE
+#define HKF_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu_dyn_smem())
+#else
+#define HKF_DYN_SMEM(T, name) extern __shared__ T name[]
+#endif
+
 #if defined(__CUDACC__) || defined(HKF_EMULATE_DEVICE)   /* the latter: tests/emu compiles kernels for the host */
 // Launch with programmatic stream serialisation: the grid may become resident while its predecessor in the stream is
 // still draining (every kernel launched this way starts with hkf_pdl_enter(), which releases ITS successor early and
@@ -314,9 +321,25 @@ __device__ __forceinline__ bool shard_wait_ge(const unsigned* p, unsigned v)
 // provably implied or recomputed with div.rn
 __device__ __forceinline__ float hkf_rcp_approx(float x)
 {
+#ifdef HKF_EMULATE_DEVICE
+    return 1.0f / x;                    // any value within the guarded error must lead to the same result
+#else
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
+}
+
+// raw MUFU.EX2 (no scaling path for results below 2^-126, see bilateral_px_tile in preprocess.cu)
+__device__ __forceinline__ float hkf_ex2_ftz(float x)
+{
+#ifdef HKF_EMULATE_DEVICE
+    return exp2f(x);                    // the CPU oracle's stand-in for ex2.approx as well
+#else
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
 }
 
 #endif // __CUDACC__

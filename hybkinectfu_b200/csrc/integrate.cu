@@ -427,6 +427,22 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
     }
 }
 
+static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* ip, const HkfCameraParams* cam, IntegrateArgs* A)
+{
+    if (inv16) for (int i = 0; i < 12; ++i) A->inv[i] = inv16[i];
+    else for (int i = 0; i < 12; ++i) A->inv[i] = 0.f;
+    // voxelPosToWorld: _size.x / _resolution.x  (float / int -> float division)
+    A->cell = c->ip.volume_size / (float)(int)c->ip.volume_resolution;
+    A->fx = cam->fx; A->fy = cam->fy; A->cx = cam->cx; A->cy = cam->cy;
+    A->cols = (int)cam->cols; A->rows = (int)cam->rows;
+    A->trunc = ip->fSdfTruncation; A->maxdist = ip->fMaxIntegrateDist; A->wmax = c->ip.weight_max;
+    A->R = (int)c->ip.volume_resolution;
+    A->z_lo = (int)c->z_lo; A->z_hi = (int)c->z_hi;
+    A->size = c->ip.volume_size;
+    A->B = c->bounds;
+}
+
+#ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
 // both passes, on the context's stream
 template <bool FROM_STATE, bool COUNT_ONLY>
 static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
@@ -451,20 +467,6 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
     return HKF_OK;
 }
 
-static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* ip, const HkfCameraParams* cam, IntegrateArgs* A)
-{
-    if (inv16) for (int i = 0; i < 12; ++i) A->inv[i] = inv16[i];
-    else for (int i = 0; i < 12; ++i) A->inv[i] = 0.f;
-    // voxelPosToWorld: _size.x / _resolution.x  (float / int -> float division)
-    A->cell = c->ip.volume_size / (float)(int)c->ip.volume_resolution;
-    A->fx = cam->fx; A->fy = cam->fy; A->cx = cam->cx; A->cy = cam->cy;
-    A->cols = (int)cam->cols; A->rows = (int)cam->rows;
-    A->trunc = ip->fSdfTruncation; A->maxdist = ip->fMaxIntegrateDist; A->wmax = c->ip.weight_max;
-    A->R = (int)c->ip.volume_resolution;
-    A->z_lo = (int)c->z_lo; A->z_hi = (int)c->z_hi;
-    A->size = c->ip.volume_size;
-    A->B = c->bounds;
-}
 
 extern "C" int hkf_integrate_volume(hkf_ctx* c, int has_color, int use_angle_weight_color, const HkfMat44* transform,
                                     const HkfIntegrateParams* ip, const HkfCameraParams* cam, const HkfCameraParams* rgb_cam)
@@ -502,3 +504,4 @@ extern "C" int hkf_count_integrate_updates(hkf_ctx* c, const HkfMat44* transform
     HKF_CUDA(c, cudaStreamSynchronize(c->stream));
     return HKF_OK;
 }
+#endif // HKF_EMULATE_DEVICE

@@ -93,8 +93,7 @@ __device__ __forceinline__ float bilateral_px_tile(const float* __restrict__ c, 
             outlier |= valid & (fabsf(d) > thresh);
             const float space2 = __fadd_rn(dy2, (float)(dx * dx));
             const float arg = __fmaf_rn(space2, ss, __fmul_rn(__fmul_rn(d, d), sd));
-            float w;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(__fmul_rn(arg, -1.4426950216293334961f)));
+            const float w = hkf_ex2_ftz(__fmul_rn(arg, -1.4426950216293334961f));
             sum1 = __fmaf_rn(tmp, w, sum1);
             sum2 = __fadd_rn(sum2, valid ? w : 0.f);
         }
@@ -218,7 +217,7 @@ k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out,
                    int cols, int rows, int radius, float tmin, float tmax, float ss, float sd, float thresh,
                    float cx, float cy, float fx, float fy, DepthBounds B)
 {
-    extern __shared__ float smem[];
+    HKF_DYN_SMEM(float, smem);
     __shared__ unsigned s_tmax[TILE_W * TILE_H / 32], s_tmin[TILE_W * TILE_H / 32];
     const int ap = radius + 1;
     const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
@@ -344,7 +343,7 @@ k_preprocess_tile_v2(const uint16_t* __restrict__ mm, float* __restrict__ raw_ou
                      float* __restrict__ filt_out, int cols, int rows, int radius, float tmin, float tmax, float ss, float sd,
                      float thresh, DepthBounds B)
 {
-    extern __shared__ float smem[];
+    HKF_DYN_SMEM(float, smem);
     __shared__ unsigned s_tmax[TILE_W * TILE_H / 32], s_tmin[TILE_W * TILE_H / 32];
     const int ap = radius;
     const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
@@ -450,6 +449,8 @@ static inline void bilateral_consts(float sigma_pixel, float sigma_depth, int* r
     *radius = (int)ceil(2.0 * (double)sigma_pixel);
     *thresh = sigma_depth * 5.0f;
 }
+
+#ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
 
 extern "C" int hkf_upload_depth_mm(hkf_ctx* c, const uint16_t* depth_mm, int is_device)
 {
@@ -667,3 +668,4 @@ extern "C" int hkf_swap_frame(hkf_ctx* c)
     HKF_CUDA(c, cudaEventRecord(c->ev_swap, c->stream));
     return HKF_OK;
 }
+#endif // HKF_EMULATE_DEVICE

@@ -27,7 +27,10 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+// __expf(x) = ex2.approx(x * log2(e)): exp2f of the same product stands in for the MUFU unit, as in the CPU oracle
+#define __expf(x) exp2f((x) * 1.4426950216293334961f)
 static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline int __float2int_rz(float a)
 {   // cvt.rzi.s32.f32: saturating, NaN -> 0
     if (a != a) return 0;
@@ -49,8 +52,18 @@ static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
 template <typename T> static inline void __stcg(T* p, T v) { *p = v; }
-static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+// atomics: real ones, the block-level emulator runs the threads of a block concurrently
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicMax(unsigned* p, unsigned v)
+{
+    unsigned o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
 static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 static inline long long clock64() { return 0; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

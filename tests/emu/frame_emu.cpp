@@ -1,0 +1,136 @@
+// frame_emu.cpp — block-level host emulation (emu_block.h) of the preprocess and integration kernels: the default
+// k_preprocess_fused / k_pyramids_fused / k_integrate_items / k_integrate (which the GPU tests pin: they check the
+// emulator) and the variants that have not seen a GPU yet (k_preprocess_tile_v2 + k_maps_pyramids_v2, item pass with
+// ray-march flags and the wider tile span).  Test infrastructure; the product library never links this.
+#include "emu_shim.h"
+#include "emu_block.h"
+#include "../../hybkinectfu_b200/csrc/hkf_internal.cuh"
+#include "emu_indices.h"
+#include "../../hybkinectfu_b200/csrc/preprocess.cu"
+#include "../../hybkinectfu_b200/csrc/integrate.cu"
+
+namespace {
+struct Bounds { DepthBounds B; std::vector<unsigned> store; size_t zero_bytes; };
+// the allocation of hkf_create (context.cu): coarse levels first = the prefix cleared before each frame
+Bounds make_bounds(unsigned cols, unsigned rows)
+{
+    Bounds b;
+    DepthBounds& B = b.B;
+    B.tiles_y = (int)div_up(rows, HKF_TILE_H);
+    int off = 4;
+    b.zero_bytes = 0;
+    for (int l = HKF_BOUND_LEVELS - 1; l >= 0; --l) {
+        B.tx[l] = (int)div_up(cols, HKF_TILE_W << l);
+        B.off_max[l] = off; off += B.tiles_y * B.tx[l];
+        B.off_min[l] = off; off += B.tiles_y * B.tx[l];
+        if (l == 1) b.zero_bytes = (size_t)off * sizeof(unsigned);
+    }
+    b.store.assign((size_t)off, 0u);
+    B.base = b.store.data();
+    return b;
+}
+}
+
+struct EmuFrame {
+    unsigned cols, rows;
+    Bounds bounds;
+    std::vector<float> raw, trunc, filt;
+    std::vector<float4> v[3], n[3];
+    unsigned lc[3], lr[3];
+};
+
+extern "C" void* emu_frame_create(unsigned cols, unsigned rows)
+{
+    EmuFrame* f = new EmuFrame();
+    f->cols = cols; f->rows = rows;
+    f->bounds = make_bounds(cols, rows);
+    f->bounds.B.base = f->bounds.store.data();
+    const size_t n0 = (size_t)cols * rows;
+    f->raw.assign(n0, 0.f); f->trunc.assign(n0, 0.f); f->filt.assign(n0, 0.f);
+    unsigned c = cols, r = rows;
+    for (int l = 0; l < 3; ++l) { f->lc[l] = c; f->lr[l] = r; f->v[l].assign((size_t)c * r, make_float4(0, 0, 0, 0)); f->n[l] = f->v[l]; c >>= 1; r >>= 1; }
+    return f;
+}
+extern "C" void emu_frame_destroy(void* h) { delete static_cast<EmuFrame*>(h); }
+
+// variant 0: k_preprocess_fused + k_pyramids_fused (default); 1: k_preprocess_tile_v2 + k_maps_pyramids_v2
+extern "C" int emu_preprocess(void* h, const uint16_t* mm, float tmin, float tmax, float sigma_pixel, float sigma_depth,
+                              float cx, float cy, float fx, float fy, int variant)
+{
+    EmuFrame* f = static_cast<EmuFrame*>(h);
+    int radius; float ss, sd, thresh;
+    bilateral_consts(sigma_pixel, sigma_depth, &radius, &ss, &sd, &thresh);
+    memset(f->bounds.store.data(), 0, f->bounds.zero_bytes);
+    const int cols = (int)f->cols, rows = (int)f->rows;
+    const dim3 b(TILE_W, TILE_H), g(div_up(f->cols, TILE_W), div_up(f->rows, TILE_H));
+    const DepthBounds B = f->bounds.B;
+    if (variant == 0) {
+        emu_launch(g, b, [&]() {
+            k_preprocess_fused(mm, f->raw.data(), f->trunc.data(), f->filt.data(), f->v[0].data(), f->n[0].data(), cols, rows, radius,
+                               tmin, tmax, ss, sd, thresh, cx, cy, fx, fy, B);
+        });
+        const unsigned gx = div_up(f->lc[1], 2), gy = div_up(f->lr[1], 2);
+        emu_launch(dim3(div_up(gx, 32), div_up(gy, 4)), dim3(32, 4), [&]() {
+            k_pyramids_fused(f->v[0].data(), f->n[0].data(), f->v[1].data(), f->n[1].data(), f->v[2].data(), f->n[2].data(),
+                             f->lc[0], f->lc[1], f->lr[1], f->lc[2], f->lr[2], nullptr);
+        });
+    } else {
+        emu_launch(g, b, [&]() {
+            k_preprocess_tile_v2(mm, f->raw.data(), f->trunc.data(), f->filt.data(), cols, rows, radius, tmin, tmax, ss, sd, thresh, B);
+        });
+        emu_launch(dim3(div_up(f->cols, 16), div_up(f->rows, 16)), dim3(256), [&]() {
+            k_maps_pyramids_v2(f->filt.data(), f->v[0].data(), f->n[0].data(), f->v[1].data(), f->n[1].data(), f->v[2].data(), f->n[2].data(),
+                               cols, rows, f->lc[1], f->lr[1], f->lc[2], f->lr[2], cx, cy, fx, fy);
+        });
+    }
+    return 0;
+}
+
+// buffer: 0 raw, 1 trunc, 2 filt (floats); 3 + 2*level vertices, 4 + 2*level normals (float4)
+extern "C" const void* emu_frame_buffer(void* h, int which)
+{
+    EmuFrame* f = static_cast<EmuFrame*>(h);
+    if (which == 0) return f->raw.data();
+    if (which == 1) return f->trunc.data();
+    if (which == 2) return f->filt.data();
+    const int l = (which - 3) / 2;
+    return ((which - 3) & 1) ? (const void*)f->n[l].data() : (const void*)f->v[l].data();
+}
+
+// One integration of the frame's truncated depth (k_integrate_items + k_integrate) into vol [R][R][R][2].
+// span: 1 (default) or 3; fine/coarse: ray-march bitmaps to maintain (may be null).  Returns the number of work items
+// written as free | general << 32.
+extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S, float wmax, const float* pose_inv16, float trunc, float maxdist,
+                                            float cx, float cy, float fx, float fy, int span, unsigned* fine, unsigned* coarse)
+{
+    EmuFrame* f = static_cast<EmuFrame*>(h);
+    IntegrateArgs A;
+    for (int i = 0; i < 12; ++i) A.inv[i] = pose_inv16[i];
+    A.cell = S / (float)R;
+    A.fx = fx; A.fy = fy; A.cx = cx; A.cy = cy;
+    A.cols = (int)f->cols; A.rows = (int)f->rows;
+    A.trunc = trunc; A.maxdist = maxdist; A.wmax = wmax;
+    A.R = R; A.z_lo = 0; A.z_hi = R; A.size = S;
+    A.B = f->bounds.B;
+    HkfDeviceState st;
+    memset(&st, 0, sizeof(st));
+    const unsigned capacity = 4u * (unsigned)R * (unsigned)(R / 4) * div_up((unsigned)R, 128);
+    std::vector<uint2> items(capacity);
+    RayFlags RF;
+    RF.fine = fine; RF.coarse = coarse;
+    RF.nbf = (R + HKF_RAY_FINE - 1) / HKF_RAY_FINE; RF.nbc = (R + HKF_RAY_COARSE - 1) / HKF_RAY_COARSE;
+    const int ngroups = R * (R / INT_G);
+    const dim3 g1(div_up((unsigned)ngroups, INT_GB)), b1(256);
+    const bool flags = fine != nullptr && coarse != nullptr;
+    emu_launch(g1, b1, [&]() {
+        if (flags && span == 3) k_integrate_items<false, true, 3>(A, &st, items.data(), capacity, 0, RF);
+        else if (flags) k_integrate_items<false, true, 1>(A, &st, items.data(), capacity, 0, RF);
+        else if (span == 3) k_integrate_items<false, false, 3>(A, &st, items.data(), capacity, 0, RF);
+        else k_integrate_items<false, false, 1>(A, &st, items.data(), capacity, 0, RF);
+    });
+    const unsigned long long counts = (unsigned long long)st.int_items[0] | ((unsigned long long)st.int_items[1] << 32);
+    emu_launch(dim3(2), dim3(INT_THREADS), [&]() {          // persistent warps: any grid size walks the whole list
+        k_integrate<false, false>(A, f->trunc.data(), reinterpret_cast<float2*>(vol), &st, items.data(), capacity, 0);
+    });
+    return counts;
+}

@@ -1,0 +1,131 @@
+"""Block-level host emulation (tests/emu/emu_block.h: one std::thread per simulated CUDA thread, barriers for
+__syncthreads and the warp collectives) of the preprocess and integration KERNEL SOURCES against the CPU oracle, bit for
+bit.  The default kernels are pinned on the GPU already - here they check the emulator; the variants behind
+HKF_PRE_V2, HKF_INT_SPAN and HKF_RAY_SKIP have not run on a GPU yet and are checked here."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _oracle as O
+from conftest import ROOT, bits_equal, n_mismatch, small_config
+from test_raycast_emulated import _pack, _run as _raycast_emulated
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+def _build(target):
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["make", "-C", EMU_DIR, target], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return C.CDLL(os.path.join(EMU_DIR, target))
+
+
+@pytest.fixture(scope="module")
+def frame():
+    lib = _build("libframe_emu.so")
+    lib.emu_frame_create.restype = C.c_void_p
+    lib.emu_frame_buffer.restype = C.c_void_p
+    lib.emu_integrate.restype = C.c_uint64
+    return lib
+
+
+@pytest.fixture(scope="module")
+def ray():
+    return _build("libraycast_emu.so")
+
+
+def _f(x):
+    return C.c_float(float(x))
+
+
+def _preprocess(lib, h, cfg, mm, variant):
+    mm = np.ascontiguousarray(mm, np.uint16)
+    assert lib.emu_preprocess(C.c_void_p(h), mm.ctypes.data_as(C.c_void_p), _f(cfg.trunc_min), _f(cfg.trunc_max), _f(cfg.sigma_pixel),
+                              _f(cfg.sigma_depth), _f(cfg.cx), _f(cfg.cy), _f(cfg.fx), _f(cfg.fy), variant) == 0
+
+
+def _buffer(lib, h, which, shape):
+    p = lib.emu_frame_buffer(C.c_void_p(h), which)
+    return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=shape).copy()
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["default", "HKF_PRE_V2"])
+def test_preprocess_kernels_equal_oracle(frame, variant):
+    from hybkinectfu_b200 import synth
+    cfg = small_config(64)
+    cam = synth.Camera().scaled(cfg.cols, cfg.rows)
+    mm = synth.render_depth_mm(synth.trajectory(200)[7], cam, noise_sigma_mm=1.0, rng=np.random.default_rng(3))
+    raw = O.decode_mm(mm)
+    tr = O.trunc(raw, cfg.trunc_min, cfg.trunc_max)
+    fl = O.bilateral(tr, cfg.sigma_pixel, cfg.sigma_depth)
+    v0 = O.vertices(fl, O.cam_of(cfg)); n0 = O.normals(v0)
+    v1, n1 = O.down(v0, False), O.down(n0, True)
+    v2, n2 = O.down(v1, False), O.down(n1, True)
+    h = frame.emu_frame_create(cfg.cols, cfg.rows)
+    try:
+        _preprocess(frame, h, cfg, mm, variant)
+        for i, (name, want) in enumerate(zip(["raw", "trunc", "filtered", "v0", "n0", "v1", "n1", "v2", "n2"], [raw, tr, fl, v0, n0, v1, n1, v2, n2])):
+            assert n_mismatch(want, _buffer(frame, h, i, want.shape)) == 0, name
+    finally:
+        frame.emu_frame_destroy(C.c_void_p(h))
+
+
+def _integrate_sequence(lib, cfg, poses, span, flags):
+    from hybkinectfu_b200 import synth
+    R = cfg.resolution
+    cam = synth.Camera().scaled(cfg.cols, cfg.rows)
+    vol = np.zeros((R, R, R, 2), np.float32)
+    want = np.zeros_like(vol)
+    nbf, nbc = (R + 15) // 16, (R + 63) // 64
+    fine = np.zeros((nbf ** 3 + 31) // 32, np.uint32)
+    coarse = np.zeros((nbc ** 3 + 31) // 32, np.uint32)
+    items = [0, 0]
+    h = lib.emu_frame_create(cfg.cols, cfg.rows)
+    try:
+        for p in poses:
+            mm = synth.render_depth_mm(p, cam)
+            _preprocess(lib, h, cfg, mm, 0)
+            inv = np.ascontiguousarray(O.mat44_inverse(p.astype(np.float32)), np.float32).reshape(16)
+            cnt = lib.emu_integrate(C.c_void_p(h), vol.ctypes.data_as(C.c_void_p), R, _f(cfg.volume_size), _f(cfg.weight_max),
+                                    inv.ctypes.data_as(C.c_void_p), _f(cfg.sdf_trunc), _f(cfg.max_integrate_dist), _f(cfg.cx), _f(cfg.cy),
+                                    _f(cfg.fx), _f(cfg.fy), span, fine.ctypes.data_as(C.c_void_p) if flags else None,
+                                    coarse.ctypes.data_as(C.c_void_p) if flags else None)
+            items[0] += cnt & 0xffffffff; items[1] += cnt >> 32
+            O.integrate(want, cfg, O.trunc(O.decode_mm(mm), cfg.trunc_min, cfg.trunc_max), p.astype(np.float32))
+    finally:
+        lib.emu_frame_destroy(C.c_void_p(h))
+    return vol, want, fine, coarse, items
+
+
+@pytest.mark.parametrize("span,flags", [(1, False), (3, True)], ids=["default", "HKF_INT_SPAN+flags"])
+def test_integration_kernels_equal_oracle(frame, span, flags):
+    from hybkinectfu_b200 import synth
+    cfg = small_config(64)
+    vol, want, fine, coarse, items = _integrate_sequence(frame, cfg, synth.trajectory(200)[::7][:2], span, flags)
+    assert (want[..., 1] > 0).sum() > 10000 and items[1] > 0
+    assert n_mismatch(vol, want) == 0
+
+
+def test_flags_of_the_item_pass_cover_every_negative_voxel_and_the_skipping_march_is_exact(frame, ray):
+    """the HKF_RAY_SKIP chain end to end on the CPU: bitmaps written by k_integrate_items<FLAGS> -> k_raycast<SKIP>"""
+    from hybkinectfu_b200 import synth
+    cfg = small_config(128)
+    R = cfg.resolution
+    poses = synth.trajectory(200)[::9][:2]
+    vol, want, fine, coarse, items = _integrate_sequence(frame, cfg, poses, 1, True)
+    assert n_mismatch(vol, want) == 0
+    need_f, need_c = O.ray_flags(want, R, 16).ravel().astype(bool), O.ray_flags(want, R, 64).ravel().astype(bool)
+    have_f = np.unpackbits(fine.view(np.uint8), bitorder="little")[:need_f.size].astype(bool)
+    have_c = np.unpackbits(coarse.view(np.uint8), bitorder="little")[:need_c.size].astype(bool)
+    assert need_f.sum() > 0 and not (need_f & ~have_f).any() and not (need_c & ~have_c).any()
+    assert have_f.sum() < have_f.size            # something is left to skip
+    for pose in (poses[-1], synth.trajectory(200)[40]):
+        pose = np.asarray(pose, np.float32)
+        v0, n0 = O.raycast(vol, cfg, pose)
+        v1, n1 = _raycast_emulated(ray, vol, cfg, pose, 1, 1, fine, coarse)
+        assert (n0[..., :3] != 0).any(-1).sum() > 500
+        assert bits_equal(v0, v1) and bits_equal(n0, n1)
