@@ -48,8 +48,13 @@ struct IcpArgs {
 #define ICP_THREADS (ICP_TILES * 256)
 #define ICP_WARPS (ICP_THREADS / 32)
 
+#ifdef HKF_EMULATE_DEVICE      /* tests/emu: host build of the kernels, no launch machinery */
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // All-reduce of the 27 partial sums over peer memory (call from all threads of the block): this rank's sums go into
 // slot [seq & 1][rank] of every rank's mailbox as (value, iteration) words (one 64-bit P2P store each over NVLink),
@@ -332,6 +337,7 @@ __global__ void k_track_begin(HkfDeviceState* st)
     if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->gen = 0; st->sdf_done = 0; }
 }
 
+#ifndef HKF_EMULATE_DEVICE
 static inline unsigned icp_grid(int ntiles) { return (unsigned)(ntiles < 256 ? ntiles : 256); }
 
 static void fill_icp_args(hkf_ctx* c, int level, const HkfCameraParams* cam, float dist_thres, float sin_thres, IcpArgs* A)
@@ -377,6 +383,8 @@ static const int* icp_schedule(int levels)
     static const int s1[3] = { 3, 0, 0 }, s2[3] = { 10, 5, 0 }, s3[3] = { 10, 5, 4 };
     return levels == 1 ? s1 : levels == 2 ? s2 : s3;
 }
+
+#endif // HKF_EMULATE_DEVICE
 
 // sharded mode: the solve of one iteration on the allreduced sums (every rank computes the same bits)
 __global__ void k_icp_solve(HkfDeviceState* st, float angle_shake, float dist_shake, int is_last)
@@ -426,8 +434,10 @@ __global__ void k_icp_solve(HkfDeviceState* st, float angle_shake, float dist_sh
 // iteration of the level) stay in registers.  CTA c of CS owns the tiles c + CS*s (s = 0, 1, ...), up to
 // ICPC_SLOTS of them, four at a time.  The sums keep the reference's association: the tile tree per 16x16 tile,
 // leaf t = 0 + partial t, leaf t + leaf t+256 (= + 0: at most 256 tiles here), then the tree over 256 entries.
+#ifndef HKF_EMULATE_DEVICE
 #include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#endif
+namespace cg = cooperative_groups;      // tests/emu supplies a stand-in with block_rank / num_blocks / sync / map_shared_rank
 
 #define ICPC_THREADS 1024
 #define ICPC_TPR 4                        // tiles per round (one per 256 threads)
@@ -438,7 +448,7 @@ namespace cg = cooperative_groups;
 __global__ void __launch_bounds__(ICPC_THREADS, 1)
 k_icp_cluster(IcpArgs A, HkfDeviceState* st, int iters)
 {
-    extern __shared__ float dyn[];
+    HKF_DYN_SMEM(float, dyn);
     float (*s_r)[7][256] = reinterpret_cast<float (*)[7][256]>(dyn);              // [ICPC_SLOTS][7][256] solver rows
     float* s_part = dyn + ICPC_SLOTS * 7 * 256;                                     // leader: [27][256] tile sums
     __shared__ float s_m[32];                  // cur | last_inv (every CTA keeps its own copy)
@@ -566,6 +576,7 @@ k_icp_cluster(IcpArgs A, HkfDeviceState* st, int iters)
     }
 }
 
+#ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
 // HKF_ICP_CLUSTER=8|16 and the level fits: at most 256 tiles, at most ICPC_SLOTS per CTA
 static int icp_cluster_size(const hkf_ctx* c, const IcpArgs& A, int level)
 {
@@ -664,3 +675,4 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
     }
     return HKF_OK;
 }
+#endif // HKF_EMULATE_DEVICE (host launch code)

@@ -6,6 +6,7 @@
 #include <barrier>
 #include <functional>
 #include <memory>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
@@ -75,31 +76,48 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __fdividef(float a, float b) { return a / b; }       // approximate on the device: only feeds conservative bounds
 
-// run `body` for every thread of every block of the grid (blocks sequentially, the threads of a block concurrently)
-static inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body)
+// hook for emu_cluster.h: per-thread set-up / tear-down of the cluster context
+struct EmuThreadHook { void (*enter)(void*); void (*leave)(void*); void* arg; };
+
+// run `body` for every thread of ONE block (its threads concurrently; 1 MB stacks: a cluster is thousands of threads)
+static inline void emu_run_block(unsigned bx, unsigned by, unsigned bz, dim3 grid, dim3 block, const std::function<void()>& body,
+                                 const EmuThreadHook* hook = nullptr)
 {
     const unsigned nthreads = block.x * block.y * block.z;
+    std::barrier<> block_bar((std::ptrdiff_t)nthreads);
+    std::vector<std::unique_ptr<EmuWarp>> warps;
+    for (unsigned w = 0; w * 32 < nthreads; ++w) warps.emplace_back(new EmuWarp((int)((nthreads - w * 32) < 32 ? (nthreads - w * 32) : 32)));
+    struct Start { std::function<void()> run; };
+    std::vector<Start> starts(nthreads);
+    std::vector<pthread_t> th(nthreads);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 1u << 20);
+    for (unsigned t = 0; t < nthreads; ++t) {
+        starts[t].run = [&, t]() {
+            emu_threadIdx = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
+            emu_blockIdx = { bx, by, bz };
+            emu_blockDim = { block.x, block.y, block.z };
+            emu_gridDim = { grid.x, grid.y, grid.z };
+            emu_lane = t & 31;
+            emu_warp = warps[t >> 5].get();
+            emu_block_bar = &block_bar;
+            if (hook) hook->enter(hook->arg);
+            body();
+            emu_warp->bar.arrive_and_drop();        // an exited thread no longer takes part in collectives
+            block_bar.arrive_and_drop();
+            if (hook) hook->leave(hook->arg);
+        };
+        pthread_create(&th[t], &attr, [](void* p) -> void* { static_cast<Start*>(p)->run(); return nullptr; }, &starts[t]);
+    }
+    for (auto& x : th) pthread_join(x, nullptr);
+    pthread_attr_destroy(&attr);
+}
+
+// run `body` for every thread of every block of the grid (blocks sequentially)
+static inline void emu_launch(dim3 grid, dim3 block, const std::function<void()>& body)
+{
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                std::barrier<> block_bar((std::ptrdiff_t)nthreads);
-                std::vector<std::unique_ptr<EmuWarp>> warps;
-                for (unsigned w = 0; w * 32 < nthreads; ++w) warps.emplace_back(new EmuWarp((int)((nthreads - w * 32) < 32 ? (nthreads - w * 32) : 32)));
-                std::vector<std::thread> th;
-                th.reserve(nthreads);
-                for (unsigned t = 0; t < nthreads; ++t)
-                    th.emplace_back([&, t]() {
-                        emu_threadIdx = { t % block.x, (t / block.x) % block.y, t / (block.x * block.y) };
-                        emu_blockIdx = { bx, by, bz };
-                        emu_blockDim = { block.x, block.y, block.z };
-                        emu_gridDim = { grid.x, grid.y, grid.z };
-                        emu_lane = t & 31;
-                        emu_warp = warps[t >> 5].get();
-                        emu_block_bar = &block_bar;
-                        body();
-                        emu_warp->bar.arrive_and_drop();        // an exited thread no longer takes part in collectives
-                        block_bar.arrive_and_drop();
-                    });
-                for (auto& x : th) x.join();
-            }
+            for (unsigned bx = 0; bx < grid.x; ++bx) emu_run_block(bx, by, bz, grid, block, body);
 }
