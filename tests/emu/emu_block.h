@@ -76,6 +76,26 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline float __fdividef(float a, float b) { return a / b; }       // approximate on the device: only feeds conservative bounds
 
+// can this process have `n` more threads at once?  (containers cap pids; the tests skip instead of crashing)
+static inline bool emu_probe_threads(int n)
+{
+    std::atomic<bool> go{false};
+    std::vector<pthread_t> th;
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 1u << 20);
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) {
+        pthread_t t;
+        if (pthread_create(&t, &attr, [](void* p) -> void* { while (!static_cast<std::atomic<bool>*>(p)->load()) sched_yield(); return nullptr; }, &go) != 0) ok = false;
+        else th.push_back(t);
+    }
+    go.store(true);
+    for (auto& t : th) pthread_join(t, nullptr);
+    pthread_attr_destroy(&attr);
+    return ok;
+}
+
 // hook for emu_cluster.h: per-thread set-up / tear-down of the cluster context
 struct EmuThreadHook { void (*enter)(void*); void (*leave)(void*); void* arg; };
 
@@ -108,7 +128,10 @@ static inline void emu_run_block(unsigned bx, unsigned by, unsigned bz, dim3 gri
             block_bar.arrive_and_drop();
             if (hook) hook->leave(hook->arg);
         };
-        pthread_create(&th[t], &attr, [](void* p) -> void* { static_cast<Start*>(p)->run(); return nullptr; }, &starts[t]);
+        if (pthread_create(&th[t], &attr, [](void* p) -> void* { static_cast<Start*>(p)->run(); return nullptr; }, &starts[t]) != 0) {
+            fprintf(stderr, "tests/emu: cannot create thread %u of %u (pid limit?)\n", t, nthreads);
+            abort();
+        }
     }
     for (auto& x : th) pthread_join(x, nullptr);
     pthread_attr_destroy(&attr);

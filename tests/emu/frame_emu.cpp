@@ -134,3 +134,5 @@ extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S,
     });
     return counts;
 }
+
+extern "C" int emu_can_spawn(int n) { return emu_probe_threads(n) ? 1 : 0; }

@@ -69,3 +69,5 @@ extern "C" void emu_state_read(const void* st, float* cur16, float* sums27, int*
     const HkfDeviceState* s = static_cast<const HkfDeviceState*>(st);
     memcpy(cur16, s->cur, 64); memcpy(sums27, s->sums, HKF_SUMS * sizeof(float)); *status = s->track_status;
 }
+
+extern "C" int emu_can_spawn(int n) { return emu_probe_threads(n) ? 1 : 0; }

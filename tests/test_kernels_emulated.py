@@ -27,6 +27,8 @@ def _build(target):
 @pytest.fixture(scope="module")
 def frame():
     lib = _build("libframe_emu.so")
+    if not lib.emu_can_spawn(512):
+        pytest.skip("this container does not allow the threads of an emulated block")
     lib.emu_frame_create.restype = C.c_void_p
     lib.emu_frame_buffer.restype = C.c_void_p
     lib.emu_integrate.restype = C.c_uint64
