@@ -582,7 +582,10 @@ static int icp_cluster_size(const hkf_ctx* c, const IcpArgs& A, int level)
 {
     static const int want = getenv("HKF_ICP_CLUSTER") ? atoi(getenv("HKF_ICP_CLUSTER")) : 0;
     if (want != 8 && want != 16) return 0;
-    if (level == 0 || c->nranks > 1) return 0;      // level 0 carries the commit of the pose (is_last) and needs the whole GPU
+    // level 0 carries the commit of the pose (is_last) and needs the whole GPU.  Sharded mode: the cluster evaluates the
+    // WHOLE level on every rank (replicated: inputs and arithmetic are identical, so are the poses) - no exchange at all
+    // for these iterations.
+    if (level == 0) return 0;
     if (A.ntiles > 256 || (A.ntiles + want - 1) / want > ICPC_SLOTS) return 0;
     return want;
 }
