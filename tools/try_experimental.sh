@@ -17,3 +17,6 @@ for cs in 8 16; do
     echo "== HKF_ICP_CLUSTER=$cs"
     HKF_ICP_CLUSTER=$cs timeout 60 python tools/stage_times.py 2>&1 | grep -E "icp_track|raycast_tracked|integrate_tracked|sum of"
 done
+echo "== all switches (cluster 16)"
+HKF_RAY_SKIP=1 HKF_PRE_V2=1 HKF_INT_SPAN=3 HKF_ICP_CLUSTER=16 timeout 60 python tools/stage_times.py 2>&1 | grep -E "preprocess|icp_track|raycast_tracked|integrate_tracked|sum of"
+HKF_RAY_SKIP=1 HKF_PRE_V2=1 HKF_INT_SPAN=3 HKF_ICP_CLUSTER=16 timeout 120 python bench.py --no-cpu-baseline 2>/dev/null | tail -c 700
