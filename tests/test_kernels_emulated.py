@@ -131,3 +131,35 @@ def test_flags_of_the_item_pass_cover_every_negative_voxel_and_the_skipping_marc
         v1, n1 = _raycast_emulated(ray, vol, cfg, pose, 1, 1, fine, coarse)
         assert (n0[..., :3] != 0).any(-1).sum() > 500
         assert bits_equal(v0, v1) and bits_equal(n0, n1)
+
+
+def test_odd_image_size_and_non_power_of_two_volume(frame, ray):
+    """sizes the GPU tests do not use: 193 x 145 pixels (odd: the pyramid levels floor, tiles are cut at both edges) into a
+    68^3 volume (not a multiple of the 32-voxel chunk nor of the bricks; the ray march takes its generic index path)"""
+    import dataclasses
+    from hybkinectfu_b200 import synth
+    cols, rows, R = 193, 145, 68
+    cam = synth.Camera().scaled(cols, rows)
+    cfg = dataclasses.replace(small_config(64), cols=cols, rows=rows, cx=cam.cx, cy=cam.cy, fx=cam.fx, fy=cam.fy, resolution=R)
+    traj = synth.trajectory(200)
+    mm = synth.render_depth_mm(traj[7], cam, noise_sigma_mm=1.0, rng=np.random.default_rng(3))
+    raw = O.decode_mm(mm)
+    tr = O.trunc(raw, cfg.trunc_min, cfg.trunc_max)
+    fl = O.bilateral(tr, cfg.sigma_pixel, cfg.sigma_depth)
+    v0 = O.vertices(fl, O.cam_of(cfg)); n0 = O.normals(v0)
+    v1, n1 = O.down(v0, False), O.down(n0, True)
+    v2, n2 = O.down(v1, False), O.down(n1, True)
+    for variant in (0, 1):
+        h = frame.emu_frame_create(cols, rows)
+        try:
+            _preprocess(frame, h, cfg, mm, variant)
+            for i, (name, want) in enumerate(zip(["raw", "trunc", "filtered", "v0", "n0", "v1", "n1", "v2", "n2"], [raw, tr, fl, v0, n0, v1, n1, v2, n2])):
+                assert n_mismatch(want, _buffer(frame, h, i, want.shape)) == 0, (variant, name)
+        finally:
+            frame.emu_frame_destroy(C.c_void_p(h))
+    vol, want, fine, coarse, items = _integrate_sequence(frame, cfg, traj[::9][:2], 3, True)
+    assert items[0] > 0 and items[1] > 0 and n_mismatch(vol, want) == 0
+    pose = traj[20].astype(np.float32)
+    a, b = O.raycast(want, cfg, pose)
+    c, d = _raycast_emulated(ray, want, cfg, pose, 0, 0)
+    assert (b[..., :3] != 0).any(-1).sum() > 500 and bits_equal(a, c) and bits_equal(b, d)
