@@ -68,7 +68,7 @@ static void free_all(hkf_ctx* c)
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->back.new_v[l]); cudaFree(c->back.new_n[l]); }
     cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
-    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->ray_flags); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
+    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->depth_mm_pinned) cudaFreeHost(c->depth_mm_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -160,18 +160,6 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     c->int_capacity = 4u * (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
     CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint2)));
     c->sm_count = prop.multiProcessorCount;
-    {
-        const char* e = getenv("HKF_RAY_SKIP");
-        c->ray_skip = e && e[0] == '1';
-        if (c->ray_skip) {
-            RayFlags& F = c->rflags;
-            F.nbf = (int)div_up(R, HKF_RAY_FINE); F.nbc = (int)div_up(R, HKF_RAY_COARSE);
-            const size_t wf = div_up((unsigned)(F.nbf * F.nbf * F.nbf), 32), wc = div_up((unsigned)(F.nbc * F.nbc * F.nbc), 32);
-            CREATE_CUDA(cudaMalloc(&c->ray_flags, (wf + wc) * sizeof(unsigned)));
-            CREATE_CUDA(cudaMemset(c->ray_flags, 0, (wf + wc) * sizeof(unsigned)));
-            F.fine = c->ray_flags; F.coarse = c->ray_flags + wf;
-        }
-    }
     if (p->max_triangles) CREATE_CUDA(cudaMalloc(&c->tris, (size_t)p->max_triangles * sizeof(HkfTriangle)));
     CREATE_CUDA(cudaMalloc(&c->st, sizeof(HkfDeviceState)));
     CREATE_CUDA(cudaMemset(c->st, 0, sizeof(HkfDeviceState)));
@@ -202,19 +190,12 @@ extern "C" int hkf_sync(hkf_ctx* c)
 extern "C" void* hkf_stream(hkf_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" uint64_t hkf_launch_count(const hkf_ctx* c) { return c ? c->launches : 0; }
 
-static size_t ray_flag_bytes(const hkf_ctx* c)
-{
-    const RayFlags& F = c->rflags;
-    return ((size_t)div_up((unsigned)(F.nbf * F.nbf * F.nbf), 32) + div_up((unsigned)(F.nbc * F.nbc * F.nbc), 32)) * sizeof(unsigned);
-}
-
 extern "C" int hkf_reset_volume(hkf_ctx* c)
 {
     if (!c) return HKF_ERR_ARG;
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution;
     HKF_CUDA(c, cudaMemsetAsync(c->vol, 0, nvox * sizeof(float2), c->stream));
     HKF_CUDA(c, cudaMemsetAsync(c->st, 0, sizeof(HkfDeviceState), c->stream));
-    if (c->ray_flags) HKF_CUDA(c, cudaMemsetAsync(c->ray_flags, 0, ray_flag_bytes(c), c->stream));
     for (int l = 0; l < c->levels; ++l) {
         size_t nb = (size_t)c->cols[l] * c->rows[l] * sizeof(float4);
         HKF_CUDA(c, cudaMemsetAsync(c->model_v[l], 0, nb, c->stream));
@@ -241,7 +222,6 @@ static void* buf_ptr(hkf_ctx* c, int buffer, unsigned level, size_t* nbytes)
     case HKF_BUF_VOLUME: *nbytes = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution * sizeof(float2); return c->vol;
     case HKF_BUF_SOLVER_SUMS: *nbytes = HKF_SUMS * sizeof(float); return c->st->sums;
     case HKF_BUF_POSE: *nbytes = 16 * sizeof(float); return c->st->pose;
-    case 100: *nbytes = 8 * sizeof(long long); return c->st->dbg;      // development aid, not part of the ABI
     case HKF_BUF_RAYCAST_KEYS: *nbytes = n0 * sizeof(unsigned long long); return c->ray_keys;
     default: return nullptr;
     }
@@ -288,8 +268,6 @@ extern "C" long hkf_upload(hkf_ctx* c, int buffer, unsigned level, const void* s
     if (!p || buffer == HKF_BUF_SOLVER_SUMS) { c->err = "hkf_upload: buffer not writable"; return -HKF_ERR_ARG; }
     if (nbytes != nb) { c->err = "hkf_upload: size mismatch"; return -HKF_ERR_ARG; }
     cudaError_t e = cudaMemcpyAsync(p, src, nb, cudaMemcpyHostToDevice, c->stream);
-    // a volume from outside: nothing is known about where its negative voxels are
-    if (e == cudaSuccess && buffer == HKF_BUF_VOLUME && c->ray_flags) e = cudaMemsetAsync(c->ray_flags, 0xff, ray_flag_bytes(c), c->stream);
     if (e == cudaSuccess && buffer == HKF_BUF_TRUNC_DEPTH) {
         // keep the depth bounds used by integration culling consistent with the uploaded map
         if (hkf_depth_bounds(c) != HKF_OK) return -HKF_ERR_CUDA;
@@ -299,17 +277,24 @@ extern "C" long hkf_upload(hkf_ctx* c, int buffer, unsigned level, const void* s
     return (long)nb;
 }
 
+// pose and its inverse travel together so that device code never inverts on its own.  They ride in the kernel's
+// parameter space: no staging buffer, no host synchronisation, so a caller that supplies poses (CameraPoseFinderFromFile,
+// src/CameraPoseFinderFromFile.cpp:21-89) pipelines like the tracked paths do.
+struct PosePair { float pose[16], inv[16]; };
+__global__ void k_set_pose(HkfDeviceState* st, PosePair p)
+{
+    if (threadIdx.x < 16) { st->pose[threadIdx.x] = p.pose[threadIdx.x]; st->pose_inv[threadIdx.x] = p.inv[threadIdx.x]; }
+    if (threadIdx.x == 0) st->track_status = HKF_TRACK_OK;
+}
+
 extern "C" int hkf_set_pose(hkf_ctx* c, const HkfMat44* pose)
 {
     if (!c || !pose) return HKF_ERR_ARG;
-    // pose and its inverse travel together so that device code never inverts on its own
-    HkfDeviceState* h = c->st_host;
-    HKF_CUDA(c, cudaStreamSynchronize(c->stream));      // st_host is reused as staging
-    memcpy(h->pose, pose->m, 64);
-    hkf_mat44_inverse(pose->m, h->pose_inv);
-    HKF_CUDA(c, cudaMemcpyAsync(c->st->pose, h->pose, 128, cudaMemcpyHostToDevice, c->stream));
-    HKF_CUDA(c, cudaMemsetAsync(&c->st->track_status, 0, sizeof(int), c->stream));
-    HKF_CUDA(c, cudaStreamSynchronize(c->stream));
+    PosePair p;
+    memcpy(p.pose, pose->m, 64);
+    hkf_mat44_inverse(pose->m, p.inv);      // host, float cofactors: Mat44::getInverse (src/cuda/Mat.h:319-444)
+    k_set_pose<<<1, 32, 0, c->stream>>>(c->st, p);
+    HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
 

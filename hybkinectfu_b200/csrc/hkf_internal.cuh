@@ -57,7 +57,6 @@ struct HkfDeviceState {
     float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
     int   sdf_done;          // SDF tracker: converged flag (|x| < 1e-3)
     unsigned int_items[4];   // integration work-item counters [parity][free, general] (double-buffered: one pair is appended to while the other is cleared)
-    long long dbg[8];        // development aid: SM-clock stamps of the last block of a tracking kernel
 };
 
 // ---- z-slab sharding over peer memory (csrc/shard.cu).  Every rank owns one mailbox that its peers write into
@@ -89,17 +88,6 @@ struct HkfFrameSet {
     DepthBounds bounds{};
 };
 
-// Brick bitmaps of the ray-march empty-space skipping: bit (bz*n + by)*n + bx of `fine` (16^3-voxel bricks) / `coarse`
-// (64^3) is set once the brick was ever touched by a "general" integration chunk - the only chunks that can write a
-// negative tsdf.  Null pointers = feature off.
-#define HKF_RAY_FINE 16
-#define HKF_RAY_COARSE 64
-struct RayFlags {
-    unsigned* fine = nullptr;
-    unsigned* coarse = nullptr;
-    int nbf = 0, nbc = 0;
-};
-
 struct hkf_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -124,7 +112,7 @@ struct hkf_ctx {
     unsigned long long* ray_keys = nullptr;
     // frame pipelining (hkf_preprocess_next / hkf_swap_frame)
     HkfFrameSet back;
-    bool back_allocated = false, back_valid = false, pipe_compute = false;
+    bool back_allocated = false, back_valid = false;
     const uint16_t* back_src = nullptr;
     HkfFrameParams back_fp{};
     cudaStream_t stream2 = nullptr;
@@ -140,11 +128,6 @@ struct hkf_ctx {
     int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes
     unsigned own_z0 = 0, own_z1 = 0;   // owned planes
-    // EXPERIMENTAL (HKF_RAY_SKIP=1, off by default): brick bitmaps "may hold a voxel with tsdf < 0", written by the
-    // integration item pass, read by the ray march (raycast.cu)
-    unsigned* ray_flags = nullptr;     // fine bitmap, then coarse bitmap
-    RayFlags rflags{};
-    bool ray_skip = false;
     // marching cubes
     HkfTriangle* tris = nullptr;
     unsigned* mc_cand = nullptr;       // candidate cells of the two-pass extraction

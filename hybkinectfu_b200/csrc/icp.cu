@@ -24,10 +24,12 @@
 //    threads b and b+256, accumulates them in that order and stores their sum: the last block to finish (one ticket
 //    atomic per block) reads [27][<=256] values in one round trip and folds them with the remaining levels of the
 //    reference's tree;
-//  * warp 0 then runs the Cholesky solve, the Euler/shake gate and the pose update (trig and the small matrix
-//    products spread over its lanes) while warp 1 evaluates the determinant gate concurrently (hkf_solver.h).
+//  * warp 0 then runs the Cholesky solve (rows spread over its lanes, solve_warp.cuh), the Euler/shake gate and the
+//    pose update (trig and the small matrix products spread over its lanes as well) while warp 1 evaluates the
+//    determinant gate concurrently; 16 lanes commit the new working transform.
 #include "hkf_internal.cuh"
 #include "hkf_solver.h"
+#include "solve_warp.cuh"
 #include "reduce27.cuh"
 
 struct IcpArgs {
@@ -59,8 +61,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // All-reduce of the 27 partial sums over peer memory (call from all threads of the block): this rank's sums go into
 // slot [seq & 1][rank] of every rank's mailbox as (value, iteration) words (one 64-bit P2P store each over NVLink),
 // every rank polls its own mailbox until all words of the iteration have arrived and adds them in RANK ORDER, so all
-// ranks continue with bit-identical sums and poses.
-__device__ __forceinline__ void icp_p2p_allreduce(const ShardPeers& peers, unsigned seq, float* s_sums, int warp, int lane)
+// ranks continue with bit-identical sums and poses.  *s_timeout is set when a peer's words did not arrive within ~2 s
+// (the caller then ends the frame's tracking with HKF_TRACK_PEER_TIMEOUT instead of solving on garbage).
+__device__ __forceinline__ void icp_p2p_allreduce(const ShardPeers& peers, unsigned seq, float* s_sums, int* s_timeout, int warp, int lane)
 {
     const int par = (int)(seq & 1u);
     if (warp == 0) {
@@ -83,7 +86,8 @@ __device__ __forceinline__ void icp_p2p_allreduce(const ShardPeers& peers, unsig
             }
         }
         ok = __all_sync(0xffffffffu, ok);
-        if (lane < HKF_SUMS) s_sums[lane] = ok ? acc : __int_as_float(0x7fc00000);   // NaN sums -> tracking fails
+        if (lane < HKF_SUMS) s_sums[lane] = acc;
+        if (lane == 0) *s_timeout = ok ? 0 : 1;
     }
     __syncthreads();
 }
@@ -147,10 +151,9 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     __shared__ float s_m[32];                  // cur | last_inv
     __shared__ float s_acc[2 * HKF_SUMS];      // leaf sums of leaf b | leaf b+256
     __shared__ float s_sums[HKF_SUMS];
-    __shared__ int s_flag[4];                  // 0: tracking live, 1: last block, 2: singular, 3: step result
+    __shared__ int s_flag[5];                  // 0: tracking live, 1: last block, 2: singular, 3: step result, 4: peer timeout
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tl = threadIdx.x >> 8, t = threadIdx.x & 255;
-    const long long t0 = clock64();
     pdl_launch_dependents();
     const int nblocks = (int)gridDim.x;                                   // = min(256, ntiles)
     const int rounds = (A.ntiles - (int)blockIdx.x + 2 * 256 - 1) / (2 * 256);   // tiles b + 256 k < ntiles, two k per round
@@ -212,7 +215,6 @@ k_icp(IcpArgs A, HkfDeviceState* st)
 
     // ---- last block folds the leaf pairs and (fused mode) advances the pose.  The 27 stores above all belong to
     // warp 0: it alone orders them before the ticket (warp barrier, then one fence + atomic by lane 0)
-    const long long t1 = clock64();
     if (warp == 0) {
         __syncwarp();
         if (lane == 0) {
@@ -223,7 +225,6 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     }
     __syncthreads();
     if (!s_flag[1]) return;
-    const long long t2 = clock64();
     __threadfence();
     {
         // rows 2 per warp, all 16 loads in flight; lane owns entries lane + 32 m, the remaining levels 128/64/32 and
@@ -246,31 +247,26 @@ k_icp(IcpArgs A, HkfDeviceState* st)
         }
     }
     __syncthreads();
-    if (P2P) icp_p2p_allreduce(A.peers, A.seq, s_sums, warp, lane);
-    const long long t3 = clock64();
+    if (P2P) {
+        icp_p2p_allreduce(A.peers, A.seq, s_sums, &s_flag[4], warp, lane);
+        if (s_flag[4]) {                           // a peer never delivered: end the frame's tracking, do not solve on garbage
+            if (threadIdx.x == 0) { st->track_status = HKF_TRACK_PEER_TIMEOUT; st->ticket = 0; }
+            return;
+        }
+    }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + HKF_SUMS) st->sums[threadIdx.x - 64] = s_sums[threadIdx.x - 64];
     if (threadIdx.x == 64) st->ticket = 0;
-    if (!SOLVE) {
-        if (threadIdx.x == 0) { st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3; }
-        return;
-    }
-    // ---- the solve (hkf_icp_step, operation for operation) spread over warp 0 while warp 1 evaluates the determinant
-    // gate: Cholesky on lane 0, the three sin/cos pairs on lanes 0-2, the 3x3 products on lanes 0-8, the shake gate on
-    // lane 0 next to the 4x4 product T * cur on lanes 16-31
-    __shared__ float s_x[6], s_R[3][9], s_Rxy[9], s_Rf[9], s_c2[16];
-    long long t4 = 0;
+    if (!SOLVE) return;
+    // ---- the solve (hkf_icp_step, operation for operation) on warp 0 while warp 1 evaluates the determinant gate: Cholesky
+    // with rows on lanes 0-6, the three sin/cos pairs on lanes 0-2, the 3x3 products on lanes 0-8, the shake gate on lane 0
+    // next to the 4x4 product T * cur on lanes 16-31
+    __shared__ float s_R[3][9], s_Rxy[9], s_Rf[9], s_c2[16];
     if (warp == 0) {
-        if (lane == 0) {
-            float Am[36], bv[6], x[6];
-            hkf_unpack27(s_sums, Am, bv);
-            hkf_llt_solve6(Am, bv, x);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) s_x[i] = x[i];
-        }
-        __syncwarp();
+        float x[6];
+        hkf_llt_solve6_warp(s_sums, lane, x);
         if (lane < 3) {
             float R[9];
-            hkf_rot_axis(lane, s_x[lane], R);
+            hkf_rot_axis(lane, lane == 0 ? x[0] : lane == 1 ? x[1] : x[2], R);
 #pragma unroll
             for (int i = 0; i < 9; ++i) s_R[lane][i] = R[i];
         }
@@ -290,39 +286,40 @@ k_icp(IcpArgs A, HkfDeviceState* st)
         if (lane == 0) {
             // the shake gate of hkf_vector6_to_transform (a NaN passes, as in the reference)
             const float angle = hkf_rotation_angle(s_Rf);
-            const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_x[3], s_x[3]), __fmul_rn(s_x[4], s_x[4])), __fmul_rn(s_x[5], s_x[5])));
+            const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x[3], x[3]), __fmul_rn(x[4], x[4])), __fmul_rn(x[5], x[5])));
             s_flag[3] = (angle > A.angle_shake || d > A.dist_shake) ? HKF_SOLVE_SHAKE : HKF_SOLVE_OK;
         } else if (lane >= 16) {
             // cur <- T * cur, T = [R | x[3..5]; 0 0 0 1] (hkf_mat44_mul, entry by entry)
             const int e = lane - 16, i = e >> 2, j = e & 3;
             const float t0r = i < 3 ? s_Rf[i * 3 + 0] : 0.f, t1r = i < 3 ? s_Rf[i * 3 + 1] : 0.f, t2r = i < 3 ? s_Rf[i * 3 + 2] : 0.f;
-            const float t3r = i < 3 ? s_x[3 + i] : 1.f;
+            const float t3r = i == 0 ? x[3] : i == 1 ? x[4] : i == 2 ? x[5] : 1.f;
             float acc = __fadd_rn(__fmul_rn(t0r, cur[0 * 4 + j]), __fmul_rn(t1r, cur[1 * 4 + j]));
             acc = __fadd_rn(acc, __fmul_rn(t2r, cur[2 * 4 + j]));
             acc = __fadd_rn(acc, __fmul_rn(t3r, cur[3 * 4 + j]));
             s_c2[e] = acc;
         }
-        t4 = clock64();
-    } else if (threadIdx.x == 32) {
-        s_flag[2] = hkf_icp_singular(s_sums) ? 1 : 0;
-        st->dbg[5] = clock64() - t3;
+    } else if (warp == 1) {
+        const float det = hkf_det6_warp(s_sums, lane);
+        if (lane == 0) s_flag[2] = ((double)det < 1E-10) ? 1 : 0;       // hkf_icp_singular
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_flag[2]) st->track_status = HKF_TRACK_SINGULAR;          // det(AtA) < 1e-10 is tested first (CameraPoseFinderICP.cpp:138)
-        else if (s_flag[3] != HKF_SOLVE_OK) st->track_status = HKF_TRACK_SHAKE;
-        else {
-            float c2[16];
+    // det(AtA) < 1e-10 is tested first (CameraPoseFinderICP.cpp:138), then the shake gate
+    const int status = s_flag[2] ? HKF_TRACK_SINGULAR : s_flag[3] != HKF_SOLVE_OK ? HKF_TRACK_SHAKE : HKF_TRACK_OK;
+    if (status != HKF_TRACK_OK) {
+        if (threadIdx.x == 0) st->track_status = status;
+        return;
+    }
+    if (threadIdx.x < 16) {
+        st->cur[threadIdx.x] = s_c2[threadIdx.x];
+        if (A.is_last) st->pose[threadIdx.x] = s_c2[threadIdx.x];      // _pose = cur_transform (CameraPoseFinderICP.cpp:84)
+    }
+    if (A.is_last && threadIdx.x == 32) {
+        float c2[16], inv[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { c2[i] = s_c2[i]; st->cur[i] = c2[i]; }
-            if (A.is_last) {                      // _pose = cur_transform (CameraPoseFinderICP.cpp:84)
-                float inv[16];
-                hkf_mat44_inverse(c2, inv);
+        for (int i = 0; i < 16; ++i) c2[i] = s_c2[i];
+        hkf_mat44_inverse(c2, inv);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { st->pose[i] = c2[i]; st->pose_inv[i] = inv[i]; }
-            }
-        }
-        st->dbg[0] = t1 - t0; st->dbg[1] = t2 - t1; st->dbg[2] = t3 - t2; st->dbg[3] = clock64() - t3; st->dbg[4] = t4 - t3;
+        for (int i = 0; i < 16; ++i) st->pose_inv[i] = inv[i];
     }
 }
 
@@ -420,194 +417,7 @@ __global__ void k_icp_solve(HkfDeviceState* st, float angle_shake, float dist_sh
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (off by default, HKF_ICP_CLUSTER=8|16; written at the end of round 1 without GPU time left to run it:
-// unmeasured, and exercised only by tests/test_gpu_experimental.py under HKF_TEST_EXPERIMENTAL=1).
-//
-// All iterations of a COARSE pyramid level in one launch of ONE thread-block cluster.  At level 2 of a 640x480 frame
-// an iteration touches 19 200 pixels: the 10.9 us it costs as a launch of its own are the dependent chain
-// launch -> pose read -> gather -> block sums -> global partials -> fence + ticket -> last block's second stage ->
-// solve -> grid completion, not work.  Inside a cluster the chain shortens to
-//     gather -> tile sums -> DSMEM stores to the leader CTA -> cluster barrier -> second stage + solve ->
-//     DSMEM pose broadcast -> cluster barrier
-// with no launch, no global-memory round trip and no fence; the new-frame vertices/normals (the same for every
-// iteration of the level) stay in registers.  CTA c of CS owns the tiles c + CS*s (s = 0, 1, ...), up to
-// ICPC_SLOTS of them, four at a time.  The sums keep the reference's association: the tile tree per 16x16 tile,
-// leaf t = 0 + partial t, leaf t + leaf t+256 (= + 0: at most 256 tiles here), then the tree over 256 entries.
-#ifndef HKF_EMULATE_DEVICE
-#include <cooperative_groups.h>
-#endif
-namespace cg = cooperative_groups;      // tests/emu supplies a stand-in with block_rank / num_blocks / sync / map_shared_rank
-
-#define ICPC_THREADS 1024
-#define ICPC_TPR 4                        // tiles per round (one per 256 threads)
-#define ICPC_ROUNDS 3                     // rounds whose new-frame pixels stay in registers
-#define ICPC_SLOTS (ICPC_TPR * ICPC_ROUNDS)
-#define ICPC_SMEM_BYTES ((ICPC_SLOTS * 7 * 256 + HKF_SUMS * 256) * sizeof(float))
-
-__global__ void __launch_bounds__(ICPC_THREADS, 1)
-k_icp_cluster(IcpArgs A, HkfDeviceState* st, int iters)
-{
-    HKF_DYN_SMEM(float, dyn);
-    float (*s_r)[7][256] = reinterpret_cast<float (*)[7][256]>(dyn);              // [ICPC_SLOTS][7][256] solver rows
-    float* s_part = dyn + ICPC_SLOTS * 7 * 256;                                     // leader: [27][256] tile sums
-    __shared__ float s_m[32];                  // cur | last_inv (every CTA keeps its own copy)
-    __shared__ int s_live;                     // tracking still live (same value in every CTA)
-    __shared__ float s_sums[HKF_SUMS];
-    __shared__ int s_flag[4];
-    __shared__ float s_x[6], s_R[3][9], s_Rxy[9], s_Rf[9], s_c2[16];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int crank = (int)cluster.block_rank(), CS = (int)cluster.num_blocks();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = threadIdx.x >> 8, t = threadIdx.x & 255;
-    pdl_launch_dependents();
-
-    // ---- independent of the pose: this thread's pixels of the new frame, one per round
-    float4 n[ICPC_ROUNDS], v[ICPC_ROUNDS];
-    bool ok[ICPC_ROUNDS];
-#pragma unroll
-    for (int r = 0; r < ICPC_ROUNDS; ++r) {
-        const int tile = crank + CS * (ICPC_TPR * r + g);
-        const int bx = tile % A.gx, by = tile / A.gx;
-        const int x = bx * 16 + (t & 15), y = by * 16 + (t >> 4);
-        ok[r] = tile < A.ntiles && !(x >= A.cols || y >= A.rows);
-        const size_t idx = ok[r] ? (size_t)y * A.cols + x : 0;
-        n[r] = ld_f4(A.new_n + idx);
-        v[r] = ld_f4(A.new_v + idx);
-    }
-    const int my_tiles = (A.ntiles - crank + CS - 1) / CS;                          // tiles crank + CS*s < ntiles
-
-    pdl_wait();
-    if (threadIdx.x < 32) s_m[threadIdx.x] = __ldcg(threadIdx.x < 16 ? &st->cur[threadIdx.x] : &st->last_inv[threadIdx.x - 16]);
-    if (threadIdx.x == 32) s_live = (__ldcg(&st->track_status) == HKF_TRACK_OK);
-    for (int i = threadIdx.x; i < HKF_SUMS * 256; i += ICPC_THREADS) s_part[i] = 0.f;   // entries >= ntiles stay zero
-    __syncthreads();
-    cluster.sync();                            // every CTA is running and the leader's table is cleared
-    float* lead_part = cluster.map_shared_rank(s_part, 0);
-    const float* cur = s_m; const float* li = s_m + 16;
-
-    bool ran = false;
-    for (int it = 0; it < iters; ++it) {
-        if (!s_live) break;                    // uniform over the cluster
-        ran = true;
-#pragma unroll
-        for (int r = 0; r < ICPC_ROUNDS; ++r)
-            if (ICPC_TPR * r < my_tiles)       // block-uniform
-                icp_pixel_row(A, cur, li, n[r], v[r], ok[r], s_r[ICPC_TPR * r + g], t);
-        __syncthreads();
-        // tile sums: job = slot * 27 + sum, a warp per job, straight into the leader's table
-        for (int job = warp; job < my_tiles * HKF_SUMS; job += ICPC_THREADS / 32) {
-            const int slot = job / HKF_SUMS, k = job - slot * HKF_SUMS;
-            const float ts = tile_sum_from_rows(s_r[slot], k, lane);
-            // second stage of the reference, thread t: sum = 0 + partial[t]; first tree level: + leaf t+256 (= 0)
-            if (lane == 0) lead_part[k * 256 + crank + CS * slot] = __fadd_rn(__fadd_rn(0.f, ts), 0.f);
-        }
-        cluster.sync();                        // #1: the leader sees all tile sums
-        if (crank == 0) {
-            if (warp < HKF_SUMS) {
-                float pv[8];
-#pragma unroll
-                for (int m = 0; m < 8; ++m) pv[m] = s_part[warp * 256 + lane + 32 * m];
-                const float c = tile_tree(pv);
-                if (lane == 0) s_sums[warp] = c;
-            }
-            __syncthreads();
-            // the solve of k_icp, operation for operation
-            if (warp == 0) {
-                if (lane == 0) {
-                    float Am[36], bv[6], x[6];
-                    hkf_unpack27(s_sums, Am, bv);
-                    hkf_llt_solve6(Am, bv, x);
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) s_x[i] = x[i];
-                }
-                __syncwarp();
-                if (lane < 3) {
-                    float R[9];
-                    hkf_rot_axis(lane, s_x[lane], R);
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) s_R[lane][i] = R[i];
-                }
-                __syncwarp();
-                if (lane < 9) {
-                    const int i = lane / 3, j = lane - 3 * i;
-                    s_Rxy[lane] = __fadd_rn(__fadd_rn(__fmul_rn(s_R[0][i * 3 + 0], s_R[1][0 * 3 + j]), __fmul_rn(s_R[0][i * 3 + 1], s_R[1][1 * 3 + j])),
-                                            __fmul_rn(s_R[0][i * 3 + 2], s_R[1][2 * 3 + j]));
-                }
-                __syncwarp();
-                if (lane < 9) {
-                    const int i = lane / 3, j = lane - 3 * i;
-                    s_Rf[lane] = __fadd_rn(__fadd_rn(__fmul_rn(s_Rxy[i * 3 + 0], s_R[2][0 * 3 + j]), __fmul_rn(s_Rxy[i * 3 + 1], s_R[2][1 * 3 + j])),
-                                           __fmul_rn(s_Rxy[i * 3 + 2], s_R[2][2 * 3 + j]));
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    const float angle = hkf_rotation_angle(s_Rf);
-                    const float d = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_x[3], s_x[3]), __fmul_rn(s_x[4], s_x[4])), __fmul_rn(s_x[5], s_x[5])));
-                    s_flag[3] = (angle > A.angle_shake || d > A.dist_shake) ? HKF_SOLVE_SHAKE : HKF_SOLVE_OK;
-                } else if (lane >= 16) {
-                    const int e = lane - 16, i = e >> 2, j = e & 3;
-                    const float t0r = i < 3 ? s_Rf[i * 3 + 0] : 0.f, t1r = i < 3 ? s_Rf[i * 3 + 1] : 0.f, t2r = i < 3 ? s_Rf[i * 3 + 2] : 0.f;
-                    const float t3r = i < 3 ? s_x[3 + i] : 1.f;
-                    float acc = __fadd_rn(__fmul_rn(t0r, cur[0 * 4 + j]), __fmul_rn(t1r, cur[1 * 4 + j]));
-                    acc = __fadd_rn(acc, __fmul_rn(t2r, cur[2 * 4 + j]));
-                    acc = __fadd_rn(acc, __fmul_rn(t3r, cur[3 * 4 + j]));
-                    s_c2[e] = acc;
-                }
-            } else if (threadIdx.x == 32) {
-                s_flag[2] = hkf_icp_singular(s_sums) ? 1 : 0;
-            }
-            __syncthreads();
-            const int status = s_flag[2] ? HKF_TRACK_SINGULAR : s_flag[3] != HKF_SOLVE_OK ? HKF_TRACK_SHAKE : HKF_TRACK_OK;
-            if (threadIdx.x == 0 && status != HKF_TRACK_OK) st->track_status = status;
-            // broadcast: the new working transform (unchanged on failure) and the live flag into every CTA
-            if (threadIdx.x < 17 * CS) {
-                const int r = threadIdx.x / 17, e = threadIdx.x - 17 * r;
-                if (e < 16) { if (status == HKF_TRACK_OK) *cluster.map_shared_rank(&s_m[e], r) = s_c2[e]; }
-                else *cluster.map_shared_rank(&s_live, r) = (status == HKF_TRACK_OK);
-            }
-        }
-        cluster.sync();                        // #2: pose and flag are in place everywhere
-    }
-    // the state the following launches read
-    if (crank == 0) {
-        if (threadIdx.x < 16) st->cur[threadIdx.x] = s_m[threadIdx.x];
-        if (ran && threadIdx.x >= 32 && threadIdx.x < 32 + HKF_SUMS) st->sums[threadIdx.x - 32] = s_sums[threadIdx.x - 32];
-    }
-}
-
 #ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
-// HKF_ICP_CLUSTER=8|16 and the level fits: at most 256 tiles, at most ICPC_SLOTS per CTA
-static int icp_cluster_size(const hkf_ctx* c, const IcpArgs& A, int level)
-{
-    static const int want = getenv("HKF_ICP_CLUSTER") ? atoi(getenv("HKF_ICP_CLUSTER")) : 0;
-    if (want != 8 && want != 16) return 0;
-    // level 0 carries the commit of the pose (is_last) and needs the whole GPU.  Sharded mode: the cluster evaluates the
-    // WHOLE level on every rank (replicated: inputs and arithmetic are identical, so are the poses) - no exchange at all
-    // for these iterations.
-    if (level == 0) return 0;
-    if (A.ntiles > 256 || (A.ntiles + want - 1) / want > ICPC_SLOTS) return 0;
-    return want;
-}
-
-static int launch_icp_cluster(hkf_ctx* c, const IcpArgs& A, int iters, int cs)
-{
-    // function attributes are per device: set on every launch (two host calls; this path is experimental)
-    HKF_CUDA(c, cudaFuncSetAttribute(k_icp_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ICPC_SMEM_BYTES));
-    HKF_CUDA(c, cudaFuncSetAttribute(k_icp_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)cs); cfg.blockDim = dim3(ICPC_THREADS); cfg.dynamicSmemBytes = ICPC_SMEM_BYTES; cfg.stream = c->stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 2;
-    HKF_CUDA(c, cudaLaunchKernelEx(&cfg, k_icp_cluster, A, c->st, iters));
-    HKF_LAUNCH_CHECK(c);
-    return HKF_OK;
-}
-
 extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
@@ -638,11 +448,6 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
                 A.y0 = (int)((long long)A.rows * c->rank / c->nranks);
                 A.y1 = (int)((long long)A.rows * (c->rank + 1) / c->nranks);
                 A.peers = c->peers;
-            }
-            if (const int cs = icp_cluster_size(c, A, l)) {      // experimental: the whole level in one cluster launch
-                rc = launch_icp_cluster(c, A, iters[l], cs);
-                if (rc != HKF_OK) return rc;
-                continue;
             }
             for (int it = 0; it < iters[l]; ++it) {
                 A.is_last = (l == 0 && it == iters[l] - 1) ? 1 : 0;

@@ -150,29 +150,13 @@ __device__ __forceinline__ uint2 make_item(int yg, int zrel, int seg, int lo_rel
 //   else : general, decided voxel by voxel in pass 2 with the reference's arithmetic.
 #define INT_GB 64                      // row groups per block of pass 1
 
-// EXPERIMENTAL (FLAGS, off by default): a general chunk is the only kind of work item that can write a negative tsdf;
-// mark the ray-march bricks it touches (read first: in a static scene the bits are already set, no atomic is issued)
-__device__ __forceinline__ void ray_flag_set(unsigned* bm, unsigned idx)
-{
-    unsigned* w = bm + (idx >> 5);
-    const unsigned bit = 1u << (idx & 31);
-    if (!(__ldcg(w) & bit)) atomicOr(w, bit);
-}
-__device__ __forceinline__ void ray_flags_mark_chunk(const RayFlags& F, int xb, int y0, int z)
-{
-    const unsigned by = (unsigned)y0 / HKF_RAY_FINE, bz = (unsigned)z / HKF_RAY_FINE;
-    const unsigned base = (bz * F.nbf + by) * F.nbf;
-    ray_flag_set(F.fine, base + (unsigned)xb / HKF_RAY_FINE);
-    ray_flag_set(F.fine, base + (unsigned)(xb + 31) / HKF_RAY_FINE);
-    ray_flag_set(F.coarse, (((unsigned)z / HKF_RAY_COARSE) * F.nbc + (unsigned)y0 / HKF_RAY_COARSE) * F.nbc + (unsigned)xb / HKF_RAY_COARSE);
-}
-
-// SPAN (EXPERIMENTAL, HKF_INT_SPAN=3, off by default): let a chunk's pixel box span up to SPAN tile widths of the level it
-// is tested on (up to SPAN+1 tiles per tile row instead of 2).  Finer tiles = tighter depth extrema: a CPU model of this
-// classifier on the bench scene gives 19.0 M general voxel slots instead of 21.7 M.
-template <bool FROM_STATE, bool FLAGS = false, int SPAN = 1>
+// A chunk's pixel box may span up to INT_SPAN tile widths of the level it is tested on (up to INT_SPAN+1 tiles per
+// tile row): finer tiles = tighter depth extrema.  Measured on the bench scene: 19.0 M general voxel slots with 3
+// instead of 21.7 M with 1, integration 144.8 -> 142.5 us (profiles/r2_experimental.log).
+#define INT_SPAN 3
+template <bool FROM_STATE>
 __global__ void __launch_bounds__(256)
-k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity, RayFlags RF = RayFlags())
+k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity)
 {
     __shared__ int s_lo[INT_GB], s_hi[INT_GB];
     hkf_pdl_enter();
@@ -236,8 +220,8 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
                     const float u0 = fminf(pu0, qu0) - 1.5f, u1 = fmaxf(pu1, qu1) + 1.5f;
                     const float v0 = fminf(pv0, qv0) - 1.5f, v1 = fmaxf(pv1, qv1) + 1.5f;
                     const float w = u1 - u0;
-                    const int lvl = w <= (float)(SPAN * HKF_TILE_W) ? 0 : w <= (float)(SPAN * 2 * HKF_TILE_W) ? 1 : w <= (float)(SPAN * 4 * HKF_TILE_W) ? 2
-                                  : w <= (float)(SPAN * 8 * HKF_TILE_W) ? 3 : -1;
+                    const int lvl = w <= (float)(INT_SPAN * HKF_TILE_W) ? 0 : w <= (float)(INT_SPAN * 2 * HKF_TILE_W) ? 1 : w <= (float)(INT_SPAN * 4 * HKF_TILE_W) ? 2
+                                  : w <= (float)(INT_SPAN * 8 * HKF_TILE_W) ? 3 : -1;
                     const int ty0 = max((int)floorf(v0 * (1.0f / HKF_TILE_H)), 0);
                     const int ty1 = min((int)floorf(v1 * (1.0f / HKF_TILE_H)), A.B.tiles_y - 1);
                     if (lvl >= 0 && ty1 - ty0 <= 3) {
@@ -280,10 +264,8 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
         baseg = __shfl_sync(0xffffffffu, baseg, 0) + (incl - ng); basef = __shfl_sync(0xffffffffu, basef, 0);
         const int lo_rel = xa - seg * INT_SEG, hi_rel = xe - seg * INT_SEG;
         if (isf) items[basef + __popc(bf & ((1u << lane) - 1))] = make_item(yg, zrel, seg, lo_rel, hi_rel, 0u, fm);
-        for (unsigned m2 = gm; m2; m2 &= m2 - 1) {
+        for (unsigned m2 = gm; m2; m2 &= m2 - 1)
             items[capacity - 1 - baseg++] = make_item(yg, zrel, seg, lo_rel, hi_rel, m2 & (0u - m2), 0u);
-            if (FLAGS) ray_flags_mark_chunk(RF, seg * INT_SEG + 32 * (__ffs((int)m2) - 1), yg * INT_G, zrel + A.z_lo);
-        }
     }
 }
 
@@ -450,16 +432,8 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
     const int ngroups = (A.z_hi - A.z_lo) * (A.R / INT_G);
     const int parity = c->int_parity;
     c->int_parity ^= 1;
-    static const bool span3 = getenv("HKF_INT_SPAN") && atoi(getenv("HKF_INT_SPAN")) == 3;      // experiment switch
     const dim3 g1(div_up(ngroups, INT_GB)), b1(256);
-    if (c->ray_flags && span3)
-        hkf_launch_pdl(k_integrate_items<FROM_STATE, true, 3>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, c->rflags);
-    else if (c->ray_flags)
-        hkf_launch_pdl(k_integrate_items<FROM_STATE, true>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, c->rflags);
-    else if (span3)
-        hkf_launch_pdl(k_integrate_items<FROM_STATE, false, 3>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, RayFlags());
-    else
-        hkf_launch_pdl(k_integrate_items<FROM_STATE>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, RayFlags());
+    hkf_launch_pdl(k_integrate_items<FROM_STATE>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
     hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY>, dim3(c->sm_count * 4), dim3(INT_THREADS), 0, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
                    (const uint2*)c->int_items, c->int_capacity, parity);

@@ -242,6 +242,14 @@ extern "C" int hkf_marchingcube(hkf_ctx* c, int has_color, float threshold)
     // candidate list: one entry per 16 cells is far more than the shell around a surface needs; if a volume ever
     // overflows it the single-pass kernel (same results) is used instead
     const size_t ncells = (size_t)(A.z1 - A.z0) * A.V.R * A.V.R;
+    if (ncells > 0x100000000ull) {
+        // candidate ids are 32-bit cell numbers: a slab of more than 2^32 owned cells (R = 2048 on one context) takes the
+        // single-pass kernel, which indexes by (row, x)
+        if (slab) k_marching_cubes<true, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
+        else k_marching_cubes<false, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
+        HKF_LAUNCH_CHECK(c);
+        return HKF_OK;
+    }
     const unsigned cap = (unsigned)(ncells / 16 < 65536 ? 65536 : ncells / 16);
     if (!c->mc_cand || c->mc_cand_cap < cap) {
         if (c->mc_cand) cudaFree(c->mc_cand);

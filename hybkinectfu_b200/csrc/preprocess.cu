@@ -9,9 +9,9 @@
 // Design: the reference runs six launches with a device-wide sync after each and 81 uncached
 // global loads per pixel in the bilateral filter.  Here the whole per-frame chain is two
 // launches: (A) one tile kernel that decodes the 16-bit frame, truncates, stages the truncated
-// tile (+apron) in shared memory, filters, back-projects and differentiates; (B) one kernel that
-// builds every coarser pyramid level of both maps.  HBM traffic is the algorithmic minimum:
-// 2 B/px in, 3 x 4 B + 2 x 16 B out at level 0.  The per-wrapper entry points reuse the same
+// tile (+apron) in shared memory and filters exactly its own 256 pixels; (B) one kernel that
+// back-projects, differentiates and builds every coarser pyramid level of both maps with warp
+// shuffles.  HBM traffic is the algorithmic minimum: 2 B/px in, 3 x 4 B + 2 x 16 B out at level 0.  The per-wrapper entry points reuse the same
 // device functions on global memory so that each stage can be parity-checked in isolation.
 #include "hkf_internal.cuh"
 
@@ -206,87 +206,8 @@ __global__ void k_down(const float4* __restrict__ in, float4* __restrict__ out, 
     out[(size_t)y * out_cols + x] = NORMALS ? down_normal(p00, p01, p10, p11) : down_vertex(p00, p01, p10, p11);
 }
 
-// ---------------------------------------------------------------- fused kernel A
-// One 32x8 pixel tile per block.  Shared memory: truncated depth for the tile grown by (radius+1)
-// on every side, then filtered depth for the tile grown by 1.
 #define TILE_W 32
 #define TILE_H 8
-__global__ void __launch_bounds__(TILE_W * TILE_H)
-k_preprocess_fused(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, float* __restrict__ trunc_out,
-                   float* __restrict__ filt_out, float4* __restrict__ v_out, float4* __restrict__ n_out,
-                   int cols, int rows, int radius, float tmin, float tmax, float ss, float sd, float thresh,
-                   float cx, float cy, float fx, float fy, DepthBounds B)
-{
-    HKF_DYN_SMEM(float, smem);
-    __shared__ unsigned s_tmax[TILE_W * TILE_H / 32], s_tmin[TILE_W * TILE_H / 32];
-    const int ap = radius + 1;
-    const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
-    const int fw = TILE_W + 2, fh = TILE_H + 2;
-    float* s_trunc = smem;              // tw*th, 0 outside the image
-    float* s_filt = smem + tw * th;     // fw*fh
-    const int tid = threadIdx.y * TILE_W + threadIdx.x;
-    const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * TILE_H;
-
-    unsigned local_max = 0, local_min = 0xffffffffu;
-    for (int i = tid; i < tw * th; i += TILE_W * TILE_H) {
-        int lx = i % tw, ly = i / tw;
-        int gx = bx0 - ap + lx, gy = by0 - ap + ly;
-        float t = 0.f;
-        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-            float d = decode_mm(__ldg(mm + (size_t)gy * cols + gx));
-            t = trunc_depth(d, tmin, tmax);
-            if (lx >= ap && lx < ap + TILE_W && ly >= ap && ly < ap + TILE_H) {
-                raw_out[(size_t)gy * cols + gx] = d;
-                trunc_out[(size_t)gy * cols + gx] = t;
-                local_max = max(local_max, __float_as_uint(t));
-                local_min = min(local_min, __float_as_uint(t));
-            }
-        }
-        s_trunc[i] = t;
-    }
-    // this block's tile is exactly one level-0 tile of the integration pass's depth bounds
-    local_max = __reduce_max_sync(0xffffffffu, local_max);
-    local_min = __reduce_min_sync(0xffffffffu, local_min);
-    if ((tid & 31) == 0) { s_tmax[tid >> 5] = local_max; s_tmin[tid >> 5] = local_min; }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned mx = 0, mn = 0xffffffffu;
-        for (int i = 0; i < TILE_W * TILE_H / 32; ++i) { mx = max(mx, s_tmax[i]); mn = min(mn, s_tmin[i]); }
-        hkf_bounds_publish(B, blockIdx.x, blockIdx.y, mx, mn);
-    }
-
-    auto at = [&](int gx, int gy) { return s_trunc[(gy - by0 + ap) * tw + (gx - bx0 + ap)]; };
-    for (int i = tid; i < fw * fh; i += TILE_W * TILE_H) {
-        int lx = i % fw, ly = i / fw;
-        int gx = bx0 - 1 + lx, gy = by0 - 1 + ly;
-        float f = 0.f;
-        if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-            if (radius == 4) f = bilateral_px_tile<4>(s_trunc + (ly + ap - 1) * tw + (lx + ap - 1), tw, ss, sd, thresh);
-            else f = bilateral_px(at, gx, gy, cols, rows, radius, ss, sd, thresh);
-        }
-        s_filt[i] = f;
-    }
-    __syncthreads();
-
-    const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
-    if (x >= cols || y >= rows) return;
-    const int fi = (threadIdx.y + 1) * fw + threadIdx.x + 1;
-    const float f0 = s_filt[fi];
-    const size_t gi = (size_t)y * cols + x;
-    filt_out[gi] = f0;
-    float4 v0 = back_project(x, y, f0, cx, cy, fx, fy);
-    v_out[gi] = v0;
-    float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!(x == cols - 1 || y == rows - 1 || x == 0 || y == 0)) {
-        float4 vr = back_project(x + 1, y, s_filt[fi + 1], cx, cy, fx, fy);
-        float4 vu = back_project(x, y + 1, s_filt[fi + fw], cx, cy, fx, fy);
-        float4 vl = back_project(x - 1, y, s_filt[fi - 1], cx, cy, fx, fy);
-        float4 vd = back_project(x, y - 1, s_filt[fi - fw], cx, cy, fx, fy);
-        n = normal_from(v0, vr, vu, vl, vd);
-    }
-    n_out[gi] = n;
-}
-
 // ---------------------------------------------------------------- fused kernel B: all coarser levels
 // Thread per level-2 pixel: builds its four level-1 pixels (vertices and normals) from the 4x4
 // level-0 block, then the level-2 pixel from those, entirely in registers.  With two levels only
@@ -331,15 +252,15 @@ __global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __
     }
 }
 
-// ---------------------------------------------------------------- EXPERIMENTAL split (HKF_PRE_V2=1, off by default)
-// Written at the end of round 1 without GPU time left: unmeasured, exercised only by tests/test_gpu_experimental.py.
-// k_preprocess_fused filters 340 pixels per 256-pixel tile (a 1-pixel halo, only so that the tile can form its normals)
-// and the bilateral filter is all of its time.  Here the tile kernel filters exactly its own 256 pixels and stops at the
-// filtered depth; vertices, normals and BOTH coarser pyramid levels come from one second launch that reads the filtered
-// map (L2-resident) with the raycast's 8x4-pixel warp patches, so that the 2x2 and 4x4 blocks of the pyramid are warp
-// shuffles (lane ^ 1, ^ 8, ^ 9, then ^ 2, ^ 16, ^ 18) - it replaces k_pyramids_fused for the new frame.
+// ---------------------------------------------------------------- fused kernels A + A'
+// A: one 32x8 pixel tile per block filters exactly its own 256 pixels from a zero-padded shared-memory tile (apron =
+// window radius) and stops at the filtered depth.  A': vertices, normals and BOTH coarser pyramid levels of the new frame
+// come from one launch that reads the filtered map (L2-resident) with 8x4-pixel warp patches, so that the 2x2 and 4x4
+// blocks of the pyramid are warp shuffles (lane ^ 1, ^ 8, ^ 9, then ^ 2, ^ 16, ^ 18).  The first design (round 1) formed
+// the normals inside the tile kernel, which made every tile filter a 1-pixel halo as well (340 instead of 256 bilateral
+// evaluations, and the filter is all of the kernel's time): 35.2 -> 28.9 us per 640x480 frame (profiles/r2_experimental.log).
 __global__ void __launch_bounds__(TILE_W * TILE_H)
-k_preprocess_tile_v2(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, float* __restrict__ trunc_out,
+k_preprocess_tile(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, float* __restrict__ trunc_out,
                      float* __restrict__ filt_out, int cols, int rows, int radius, float tmin, float tmax, float ss, float sd,
                      float thresh, DepthBounds B)
 {
@@ -386,7 +307,7 @@ k_preprocess_tile_v2(const uint16_t* __restrict__ mm, float* __restrict__ raw_ou
 }
 
 __global__ void __launch_bounds__(256)
-k_maps_pyramids_v2(const float* __restrict__ filt, float4* __restrict__ v0o, float4* __restrict__ n0o,
+k_maps_pyramids(const float* __restrict__ filt, float4* __restrict__ v0o, float4* __restrict__ n0o,
                    float4* __restrict__ v1, float4* __restrict__ n1, float4* __restrict__ v2, float4* __restrict__ n2,
                    int cols, int rows, unsigned c1, unsigned r1, unsigned c2, unsigned r2, float cx, float cy, float fx, float fy)
 {
@@ -549,27 +470,17 @@ static int run_preprocess(hkf_ctx* c, cudaStream_t stream, HkfFrameSet& F, const
     static_assert(TILE_W == HKF_TILE_W && TILE_H == HKF_TILE_H, "preprocess tile = integration culling tile");
     dim3 b(TILE_W, TILE_H), g(div_up(c->cols[0], TILE_W), div_up(c->rows[0], TILE_H));
     const HkfCameraParams& cam = c->ip.depth_camera;
-    static const bool v2 = getenv("HKF_PRE_V2") && getenv("HKF_PRE_V2")[0] == '1';      // experimental split, see above
-    if (v2) {
-        const size_t smem2 = (size_t)(TILE_W + 2 * radius) * (TILE_H + 2 * radius) * sizeof(float);
-        k_preprocess_tile_v2<<<g, b, smem2, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, (int)c->cols[0], (int)c->rows[0], radius,
-                                                      fp->trunc_min, fp->trunc_max, ss, sd, thresh, F.bounds);
-        HKF_LAUNCH_CHECK(c);
-        const bool two = c->levels >= 2, three = c->levels >= 3;
-        hkf_launch_pdl(k_maps_pyramids_v2, dim3(div_up(c->cols[0], 16), div_up(c->rows[0], 16)), dim3(256), 0, stream, (const float*)F.filtered_depth,
-                       F.new_v[0], F.new_n[0], two ? F.new_v[1] : (float4*)nullptr, two ? F.new_n[1] : (float4*)nullptr,
-                       three ? F.new_v[2] : (float4*)nullptr, three ? F.new_n[2] : (float4*)nullptr, (int)c->cols[0], (int)c->rows[0],
-                       two ? c->cols[1] : 0u, two ? c->rows[1] : 0u, three ? c->cols[2] : 0u, three ? c->rows[2] : 0u, cam.cx, cam.cy, cam.fx, cam.fy);
-        HKF_LAUNCH_CHECK(c);
-        return HKF_OK;
-    }
-    const int ap = radius + 1;
-    size_t smem = ((TILE_W + 2 * ap) * (TILE_H + 2 * ap) + (TILE_W + 2) * (TILE_H + 2)) * sizeof(float);
-    k_preprocess_fused<<<g, b, smem, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, F.new_v[0], F.new_n[0],
-                                               (int)c->cols[0], (int)c->rows[0], radius, fp->trunc_min, fp->trunc_max, ss, sd, thresh,
-                                               cam.cx, cam.cy, cam.fx, cam.fy, F.bounds);
+    const size_t smem2 = (size_t)(TILE_W + 2 * radius) * (TILE_H + 2 * radius) * sizeof(float);
+    k_preprocess_tile<<<g, b, smem2, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, (int)c->cols[0], (int)c->rows[0], radius,
+                                               fp->trunc_min, fp->trunc_max, ss, sd, thresh, F.bounds);
     HKF_LAUNCH_CHECK(c);
-    return hkf_pyramids_fused(c, F.new_v, F.new_n, stream);
+    const bool two = c->levels >= 2, three = c->levels >= 3;
+    hkf_launch_pdl(k_maps_pyramids, dim3(div_up(c->cols[0], 16), div_up(c->rows[0], 16)), dim3(256), 0, stream, (const float*)F.filtered_depth,
+                   F.new_v[0], F.new_n[0], two ? F.new_v[1] : (float4*)nullptr, two ? F.new_n[1] : (float4*)nullptr,
+                   three ? F.new_v[2] : (float4*)nullptr, three ? F.new_n[2] : (float4*)nullptr, (int)c->cols[0], (int)c->rows[0],
+                   two ? c->cols[1] : 0u, two ? c->rows[1] : 0u, three ? c->cols[2] : 0u, three ? c->rows[2] : 0u, cam.cx, cam.cy, cam.fx, cam.fy);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
 }
 
 static void current_set(hkf_ctx* c, HkfFrameSet* F)
@@ -593,8 +504,8 @@ extern "C" int hkf_preprocess(hkf_ctx* c, const uint16_t* depth_mm, int is_devic
 }
 
 // ---- frame pipelining: the NEXT frame is uploaded and preprocessed on a second stream into a second set of
-// per-frame buffers while the current frame is still being tracked / integrated / raycast (tracking is latency-bound
-// and leaves most SMs idle; the bilateral filter is arithmetic-bound and fills them).  hkf_swap_frame makes it current.
+// per-frame buffers while the current frame is still being tracked / integrated / raycast; hkf_swap_frame runs its
+// preprocess kernels on the main stream and makes it current.
 static int alloc_back(hkf_ctx* c)
 {
     if (c->back_allocated) return HKF_OK;
@@ -620,10 +531,9 @@ static int alloc_back(hkf_ctx* c)
     HKF_CUDA(c, cudaEventCreateWithFlags(&c->ev_pre_done, cudaEventDisableTiming));
     HKF_CUDA(c, cudaEventCreateWithFlags(&c->ev_swap, cudaEventDisableTiming));
     HKF_CUDA(c, cudaEventRecord(c->ev_swap, c->stream));
-    // HKF_PIPE_COMPUTE=1: run the next frame's kernels on the side stream as well (measured slower on B200: the
-    // bilateral blocks take the register file the tracking blocks need); default: upload only
-    const char* e = getenv("HKF_PIPE_COMPUTE");
-    c->pipe_compute = e && e[0] == '1';
+    // Only the upload runs on the side stream.  Running the next frame's kernels there as well was measured slower on
+    // B200 (round 1: 800-1360 instead of 2040 frames/s): every kernel of the chain fills the register file, so the
+    // bilateral blocks only delay the tracking blocks.
     c->back_allocated = true;
     return HKF_OK;
 }
@@ -636,10 +546,7 @@ extern "C" int hkf_preprocess_next(hkf_ctx* c, const uint16_t* depth_mm, int is_
     // the back set was the current one until the last swap: everything enqueued before that swap may still read it
     HKF_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_swap, 0));
     c->back_src = depth_mm;
-    if (c->pipe_compute) {
-        rc = run_preprocess(c, c->stream2, c->back, depth_mm, is_device, fp);
-        if (rc != HKF_OK) return rc;
-    } else if (!is_device) {
+    if (!is_device) {
         // copy engine only: the upload overlaps the current frame, the kernels run on the main stream at the swap
         unsigned n = c->cols[0] * c->rows[0];
         HKF_CUDA(c, cudaMemcpyAsync(c->back.depth_mm, depth_mm, n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream2));
@@ -660,7 +567,7 @@ extern "C" int hkf_swap_frame(hkf_ctx* c)
     make_current(c, c->back);
     c->back = cur;
     c->back_valid = false;
-    if (!c->pipe_compute) {
+    {
         HkfFrameSet F; current_set(c, &F);
         int rc = run_preprocess(c, c->stream, F, c->back_src, 1, &c->back_fp);
         if (rc != HKF_OK) return rc;

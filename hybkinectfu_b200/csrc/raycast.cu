@@ -34,21 +34,17 @@ struct RaycastArgs {
     float pose[16];
     int own_z0, own_z1, rank;
     const ShardMailbox* mailbox; int nranks; unsigned epoch;   // peer-memory mode: epoch of this raycast
-    RayFlags RF;                                               // SKIP (experimental): brick bitmaps
 };
 
 // FAST: R is a power of two and the stored planes hold at most 2^32 voxels (the host checks both) - the cheaper
 // sample-index arithmetic below applies; the results are the same bits either way.
 //
-// SKIP (EXPERIMENTAL, HKF_RAY_SKIP=1, off by default; unmeasured - written without GPU time left in round 1; its
-// exactness argument is checked on the CPU by tests/test_raycast_skip_model.py, which on the bench scene skips 73 % of
-// the samples in whole batches and the read of another 21 %): a (+ -> -) pair ends in a voxel with tsdf < 0, and such
-// voxels exist only in bricks the integration item pass has flagged (hkf_internal.cuh: RayFlags).  (1) A sample whose
-// voxel lies in an unflagged 16^3 brick is not read (it stands in as +1; if a pair seems to end right after it, the
-// in-order scan below reads it after all).  (2) fma(d,t,o) and the truncating voxel index are monotone in t, so all
-// samples of a batch lie in the voxel box of its first and last sample: if every 64^3 brick the box touches is
-// unflagged the batch costs two index computations and RAY_NB additions.
-template <bool FROM_STATE, bool SLAB, bool FAST, bool SKIP = false>
+// Empty-space skipping (brick bitmaps "may hold a negative voxel" written by the integration item pass: unflagged 16^3
+// bricks not read, whole batches skipped over unflagged 64^3 bricks) was built, shown exact on the CPU and on the GPU,
+// and measured SLOWER on B200 - 120 us against 78 us for this kernel (profiles/r2_experimental.log): the flag lookups sit
+// in front of every sample load and lengthen the dependent chain of a march that is latency-bound, not traffic-bound.
+// It has been removed.
+template <bool FROM_STATE, bool SLAB, bool FAST>
 __global__ void __launch_bounds__(256)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
@@ -147,37 +143,10 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 gx = voxel(px); gy = voxel(py); gz = voxel(pz);
             }
         };
-        auto flag = [&](const unsigned* bm, unsigned idx) -> bool { return (__ldg(bm + (idx >> 5)) >> (idx & 31)) & 1u; };
-        auto read_at = [&](float tt) -> float {                  // SKIP: a sample that was not read the first time round
-            int gx, gy, gz;
-            voxel3(tt, gx, gy, gz);
-            return __ldg(&V.vol[vol_index(V, gx, gy, gz)].x);
-        };
-        bool last_unread = false;                                // SKIP: last_sdf stands for a sample that has not been read
         bool done = false;
         while (!done && t < tmax && t < t_leave) {
             float ts[RAY_NB], sd[RAY_NB];
             int gzs[RAY_NB];
-            unsigned unread = 0;
-            if (SKIP) {
-                float te = t;
-#pragma unroll
-                for (int b = 1; b < RAY_NB; ++b) te = __fadd_rn(A.inc, te);
-                if (mono && te < tmax) {
-                    int ax, ay, az, bx, by, bz;
-                    voxel3(t, ax, ay, az);
-                    voxel3(te, bx, by, bz);
-                    const int nbc = A.RF.nbc;
-                    const int x0 = min(ax, bx) / HKF_RAY_COARSE, x1 = max(ax, bx) / HKF_RAY_COARSE;
-                    const int y0 = min(ay, by) / HKF_RAY_COARSE, y1 = max(ay, by) / HKF_RAY_COARSE;
-                    const int z0 = min(az, bz) / HKF_RAY_COARSE, z1 = max(az, bz) / HKF_RAY_COARSE;
-                    bool any = false;
-                    for (int cz = z0; cz <= z1; ++cz)
-                        for (int cy = y0; cy <= y1; ++cy)
-                            for (int cx = x0; cx <= x1; ++cx) any |= flag(A.RF.coarse, (unsigned)((cz * nbc + cy) * nbc + cx));
-                    if (!any) { last_unread = true; last_t = te; t = __fadd_rn(A.inc, te); continue; }
-                }
-            }
 #pragma unroll
             for (int b = 0; b < RAY_NB; ++b) {
                 ts[b] = t;
@@ -185,9 +154,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 voxel3(t, gx, gy, gz);
                 gzs[b] = gz;
                 const int gzc = SLAB ? min(max(gz, V.z_lo), V.z_hi - 1) : gz;      // keep the speculative read inside the slab
-                if (SKIP && !flag(A.RF.fine, (unsigned)(((gz / HKF_RAY_FINE) * A.RF.nbf + gy / HKF_RAY_FINE) * A.RF.nbf + gx / HKF_RAY_FINE))) {
-                    sd[b] = 1.0f; unread |= 1u << b;
-                } else if (FAST) sd[b] = __ldg(&V.vol[((unsigned)(gzc - V.z_lo) * (unsigned)R + (unsigned)gy) * (unsigned)R + (unsigned)gx].x);
+                if (FAST) sd[b] = __ldg(&V.vol[((unsigned)(gzc - V.z_lo) * (unsigned)R + (unsigned)gy) * (unsigned)R + (unsigned)gx].x);
                 else sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gzc)].x);
                 t = __fadd_rn(A.inc, t);
             }
@@ -195,7 +162,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
             // or a sample lies outside the stored planes: one predicate instead of the in-order scan below.
             {
                 bool event = !(mono && ts[RAY_NB - 1] < tmax) || !last_known;
-                float prev = (SKIP && last_unread) ? 1.0f : last_sdf;
+                float prev = last_sdf;
 #pragma unroll
                 for (int b = 0; b < RAY_NB; ++b) {
                     event |= (prev > 0.0f) & (sd[b] < 0.0f);
@@ -204,15 +171,8 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 }
                 if (!event) {
                     last_sdf = sd[RAY_NB - 1]; last_t = ts[RAY_NB - 1];
-                    if (SKIP) last_unread = (unread >> (RAY_NB - 1)) & 1u;
                     continue;
                 }
-            }
-            if (SKIP) {                                          // the scan wants the real values
-                if (last_unread) { last_sdf = read_at(last_t); last_unread = false; }
-#pragma unroll
-                for (int b = 0; b < RAY_NB; ++b)
-                    if ((unread >> b) & 1u) sd[b] = read_at(ts[b]);
             }
 #pragma unroll
             for (int b = 0; b < RAY_NB; ++b) {
@@ -283,7 +243,6 @@ static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParam
     if (pose) memcpy(A->pose, pose, 64); else memset(A->pose, 0, 64);
     A->own_z0 = (int)c->own_z0; A->own_z1 = (int)c->own_z1; A->rank = c->rank;
     A->mailbox = nullptr; A->nranks = c->nranks; A->epoch = 0;
-    A->RF = RayFlags();
     if (c->p2p) { A->mailbox = c->mailbox; A->epoch = ++c->shard_epoch; }
 }
 
@@ -321,12 +280,6 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
     const HkfDeviceState* st = c->st;
     const bool fast = is_fast(c);
-    if (c->ray_flags && fast && !is_slab(c)) {      // experimental empty-space skipping
-        A.RF = c->rflags;
-        hkf_launch_pdl(k_raycast<true, false, true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
-        HKF_LAUNCH_CHECK(c);
-        return HKF_OK;
-    }
     if (is_slab(c)) {
         if (fast) hkf_launch_pdl(k_raycast<true, true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
         else hkf_launch_pdl(k_raycast<true, true, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);

@@ -196,7 +196,7 @@ k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ o
         const unsigned t = atomicAdd(&st->ticket, 1u);
         if (t == gridDim.x - 1) {
             st->ticket = 0;
-            if (!s_ok) st->track_status = HKF_TRACK_SINGULAR;
+            if (!s_ok) st->track_status = HKF_TRACK_PEER_TIMEOUT;
             __threadfence_system();
             for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->done[P.rank] = epoch;
             const long long t0 = clock64();

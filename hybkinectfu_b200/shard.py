@@ -17,6 +17,9 @@ import os
 import numpy as np
 
 NO_HIT = np.uint64(0xFFFFFFFFFFFFFFFF)
+# ICP in sharded mode (env HKF_SHARD_ICP overrides): "banded" = every rank evaluates a band of pixel rows and the 27 sums
+# are exchanged; "replicated" = every rank evaluates the whole image (no exchange; ICP is latency-bound, not work-bound)
+DEFAULT_ICP_MODE = "banded"
 
 
 def halo_planes(ray_increment: float, volume_size: float, resolution: int) -> int:

@@ -97,7 +97,8 @@ enum {
     HKF_TRACK_OK = 0,
     HKF_TRACK_SINGULAR = 1, /* det(AtA) < 1e-10, src/CameraPoseFinderICP.cpp:138 */
     HKF_TRACK_SHAKE = 2,    /* "camera shaking detected", src/CameraPoseFinderICP.cpp:104 */
-    HKF_TRACK_NO_POSE = 3   /* CameraPoseFinderFromFile found no record for the frame, src/CameraPoseFinderFromFile.cpp:32-65 */
+    HKF_TRACK_NO_POSE = 3,  /* CameraPoseFinderFromFile found no record for the frame, src/CameraPoseFinderFromFile.cpp:32-65 */
+    HKF_TRACK_PEER_TIMEOUT = 4 /* sharded mode only: a peer rank did not deliver its share of an exchange within ~2 s */
 };
 
 /* buffers named in src/cuda/CudaDeviceDataMan.h:54-67, in the REFERENCE layouts */

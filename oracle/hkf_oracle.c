@@ -478,112 +478,6 @@ void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const f
         }
 }
 
-/* ---- model of an empty-space-skipping march (NOT the reference's algorithm: a CPU statement of the optimisation planned
-   for csrc/raycast.cu, here so that its exactness claim can be checked against orc_raycast on this box).
-   flags[(bz*nb + by)*nb + bx] != 0 when brick (bx,by,bz) of `brick` voxels per side may hold a voxel with tsdf < 0.
-   A (+ -> -) pair ends in a voxel with tsdf < 0, i.e. in a flagged brick, so:
-    (1) a sample whose nearest voxel lies in an unflagged brick need not be READ (its tsdf is >= 0: it cannot end a pair);
-        if the next sample turns out negative, the skipped one is read after all (lazily) for the "last > 0" half;
-    (2) a batch of `nb_batch` consecutive samples is skipped without any per-sample work when the bricks (coarse flags)
-        touched by the axis-aligned box of the voxel indices of its FIRST and LAST sample are all unflagged: fma(d,t,o)
-        and the truncating voxel index are monotone in t, so every sample in between lies in that box.
-   stats: [0] samples visited by the reference march, [1] reads skipped by (1), [2] samples skipped by (2),
-          [3] violations of the box claim or of "skipped implies tsdf >= 0" (must stay 0) */
-void orc_build_ray_flags(const float* vol, int R, int brick, unsigned char* flags)
-{
-    VolView V = volview(vol, R, 1.0f);
-    const int nb = (R + brick - 1) / brick;
-    memset(flags, 0, (size_t)nb * nb * nb);
-#pragma omp parallel for schedule(dynamic, 4)
-    for (int z = 0; z < R; ++z)
-        for (int y = 0; y < R; ++y)
-            for (int x = 0; x < R; ++x)
-                if (voxel(&V, x, y, z)[0] < 0.f) flags[((size_t)(z / brick) * nb + y / brick) * nb + x / brick] = 1;
-}
-
-void orc_raycast_skip(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float inc,
-                      float near_plane, float far_plane, const unsigned char* fine, int fine_brick,
-                      const unsigned char* coarse, int coarse_brick, int nb_batch, float* out_v4, float* out_n4, long long stats[4])
-{
-    VolView V = volview(vol, R, S);
-    const int cols = (int)cam->cols, rows = (int)cam->rows;
-    const int nbf = (R + fine_brick - 1) / fine_brick, nbc = (R + coarse_brick - 1) / coarse_brick;
-    long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma omp parallel for schedule(dynamic, 4) reduction(+ : s0, s1, s2, s3)
-    for (int y = 0; y < rows; ++y)
-        for (int x = 0; x < cols; ++x) {
-            float* ov = out_v4 + 4 * ((size_t)y * cols + x);
-            float* on = out_n4 + 4 * ((size_t)y * cols + x);
-            ov[0] = ov[1] = ov[2] = ov[3] = 0.f;
-            on[0] = on[1] = on[2] = on[3] = 0.f;
-            const Ray r = ray_setup(cam, pose, S, near_plane, far_plane, x, y);
-            if (!r.live) continue;
-            float t = r.tmin, last_sdf = 0.f, last_t = r.tmin;
-            int last_unread = 0;             /* the previous sample was skipped: last_sdf is not known yet */
-            while (t < r.tmax) {
-                /* (2) whole batch */
-                if (inc > 0.f && nb_batch > 1) {
-                    float te = t;
-                    for (int k = 1; k < nb_batch; ++k) te = inc + te;
-                    if (te < r.tmax) {
-                        int a[3], b[3];
-                        a[0] = clampi(w2v(&V, fmaf(r.dx, t, r.ox)), 0, R - 1); b[0] = clampi(w2v(&V, fmaf(r.dx, te, r.ox)), 0, R - 1);
-                        a[1] = clampi(w2v(&V, fmaf(r.dy, t, r.oy)), 0, R - 1); b[1] = clampi(w2v(&V, fmaf(r.dy, te, r.oy)), 0, R - 1);
-                        a[2] = clampi(w2v(&V, fmaf(r.dz, t, r.oz)), 0, R - 1); b[2] = clampi(w2v(&V, fmaf(r.dz, te, r.oz)), 0, R - 1);
-                        int lo[3], hi[3], any = 0;
-                        for (int d = 0; d < 3; ++d) { lo[d] = (a[d] < b[d] ? a[d] : b[d]); hi[d] = (a[d] < b[d] ? b[d] : a[d]); }
-                        for (int bz = lo[2] / coarse_brick; bz <= hi[2] / coarse_brick && !any; ++bz)
-                            for (int by = lo[1] / coarse_brick; by <= hi[1] / coarse_brick && !any; ++by)
-                                for (int bx = lo[0] / coarse_brick; bx <= hi[0] / coarse_brick; ++bx)
-                                    if (coarse[((size_t)bz * nbc + by) * nbc + bx]) { any = 1; break; }
-                        if (!any) {
-                            /* check the claim on every sample of the batch (test instrumentation only) */
-                            float tk = t;
-                            for (int k = 0; k < nb_batch; ++k) {
-                                int g[3] = { clampi(w2v(&V, fmaf(r.dx, tk, r.ox)), 0, R - 1), clampi(w2v(&V, fmaf(r.dy, tk, r.oy)), 0, R - 1),
-                                             clampi(w2v(&V, fmaf(r.dz, tk, r.oz)), 0, R - 1) };
-                                for (int d = 0; d < 3; ++d) if (g[d] < lo[d] || g[d] > hi[d]) ++s3;
-                                if (voxel(&V, g[0], g[1], g[2])[0] < 0.f) ++s3;
-                                last_t = tk;
-                                tk = inc + tk;
-                            }
-                            s0 += nb_batch; s2 += nb_batch;
-                            last_unread = 1;
-                            t = tk;
-                            continue;
-                        }
-                    }
-                }
-                /* per sample */
-                float px = fmaf(r.dx, t, r.ox), py = fmaf(r.dy, t, r.oy), pz = fmaf(r.dz, t, r.oz);
-                int gx = clampi(w2v(&V, px), 0, R - 1), gy = clampi(w2v(&V, py), 0, R - 1), gz = clampi(w2v(&V, pz), 0, R - 1);
-                ++s0;
-                if (!fine[((size_t)(gz / fine_brick) * nbf + gy / fine_brick) * nbf + gx / fine_brick]) {
-                    /* (1) not read */
-                    if (voxel(&V, gx, gy, gz)[0] < 0.f) ++s3;
-                    ++s1;
-                    last_unread = 1; last_t = t;
-                    t = inc + t;
-                    continue;
-                }
-                float sdf = voxel(&V, gx, gy, gz)[0];
-                if (sdf < 0.0f && last_unread) {
-                    /* the skipped predecessor is needed after all */
-                    float qx = fmaf(r.dx, last_t, r.ox), qy = fmaf(r.dy, last_t, r.oy), qz = fmaf(r.dz, last_t, r.oz);
-                    last_sdf = voxel(&V, clampi(w2v(&V, qx), 0, R - 1), clampi(w2v(&V, qy), 0, R - 1), clampi(w2v(&V, qz), 0, R - 1))[0];
-                    last_unread = 0;
-                }
-                if (!last_unread && last_sdf > 0.0f && sdf < 0.0f) {
-                    ray_hit(&V, &r, inc, t, px, py, pz, fmaf(r.dx, last_t, r.ox), fmaf(r.dy, last_t, r.oy), fmaf(r.dz, last_t, r.oz), ov, on);
-                    break;
-                }
-                last_sdf = sdf; last_unread = 0; last_t = t;
-                t = inc + t;
-            }
-        }
-    if (stats) { stats[0] = s0; stats[1] = s1; stats[2] = s2; stats[3] = s3; }
-}
-
 /* ------------------------------------------------------------------ host-math exports */
 int orc_solve_icp(const float s27[27], float x[6]) { return hm_solve_icp(s27, x); }
 void orc_solve_llt(const float s27[27], float x[6]) { hm_solve_llt(s27, x); }

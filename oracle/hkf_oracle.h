@@ -48,14 +48,6 @@ void orc_icp_sums(const float* new_v, const float* new_n, const float* model_v, 
 void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float ray_inc,
                  float near_plane, float far_plane, float* out_v4, float* out_n4);
 
-/* NOT reference code: CPU model of the empty-space-skipping march planned for csrc/raycast.cu, checked against orc_raycast
- * (tests/test_raycast_skip_model.py).  flags: one byte per brick, != 0 when the brick may hold a voxel with tsdf < 0.
- * stats[4]: samples of the reference march, reads skipped, samples skipped in whole batches, violated claims (must be 0) */
-void orc_build_ray_flags(const float* vol, int R, int brick, unsigned char* flags);
-void orc_raycast_skip(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float ray_inc,
-                      float near_plane, float far_plane, const unsigned char* fine, int fine_brick,
-                      const unsigned char* coarse, int coarse_brick, int nb_batch, float* out_v4, float* out_n4, long long stats[4]);
-
 /* src/cuda/CalSDFErrSolverParams.cu:7-138 */
 void orc_sdf_sums(const float* vol, int R, float S, const float* trunc_depth, const OrcCamera* cam,
                   const float cur[16], float out27[27]);

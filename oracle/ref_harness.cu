@@ -165,24 +165,35 @@ extern "C" void ref_bilateral() { cudaBiliearFilterDepth(AP()->_depth_prepocess_
 extern "C" void ref_vertices() { cudaCalculateNewVertices(AP()->_depth_camera_params); }
 extern "C" void ref_normals() { cudaCalculateNewNormals(); }
 
-// fenced pyramid: unmodified kernels, corrected launch, padded buffers (see header comment)
+// fenced pyramid: unmodified kernels, corrected launch, padded buffers (see header comment).  The padded buffers are
+// allocated once per image size (the stock path has no allocation in a frame either); the padding rows are zeroed at
+// allocation and never written (only cols x rows texels are copied in), everything runs in order on the default stream.
+struct PadBufs { std::vector<Point4fMap2D> in, out; unsigned c0 = 0, r0 = 0; };
+static PadBufs g_pad[2];
 template <bool NORMALS>
 static void fenced_down(std::vector<CudaMap2D<float4>>& pyr)
 {
-    int levels = (int)pyr.size();
+    const int levels = (int)pyr.size();
+    if (levels < 2) return;
+    PadBufs& P = g_pad[NORMALS ? 1 : 0];
+    if ((int)P.in.size() != levels - 1 || P.c0 != pyr[0].cols() || P.r0 != pyr[0].rows()) {
+        P.in.clear(); P.out.clear();
+        for (int i = 0; i < levels - 1; ++i) {
+            P.in.push_back(Point4fMap2D(GPU, pyr[i].cols(), pyr[i].rows() + 64));
+            P.out.push_back(Point4fMap2D(GPU, pyr[i + 1].cols(), pyr[i + 1].rows() + 32));
+            P.in.back().clearData(); P.out.back().clearData();
+        }
+        P.c0 = pyr[0].cols(); P.r0 = pyr[0].rows();
+    }
     for (int i = 0; i < levels - 1; ++i) {
         unsigned ci = pyr[i].cols(), ri = pyr[i].rows();
         unsigned co = pyr[i + 1].cols(), ro = pyr[i + 1].rows();
-        Point4fMap2D in_pad(GPU, ci, ri + 64);
-        Point4fMap2D out_pad(GPU, co, ro + 32);
-        in_pad.clearData(); out_pad.clearData();
-        cudaMemcpy(in_pad.ptr(), pyr[i].ptr(), sizeof(float4) * (size_t)ci * ri, cudaMemcpyDeviceToDevice);
+        cudaMemcpyAsync(P.in[i].ptr(), pyr[i].ptr(), sizeof(float4) * (size_t)ci * ri, cudaMemcpyDeviceToDevice, 0);
         const dim3 blockSize(BLOCK_SIZE_2D_X, BLOCK_SIZE_2D_Y);
         const dim3 gridSize(divUp(co, BLOCK_SIZE_2D_X), divUp(ro, BLOCK_SIZE_2D_Y));
-        if (NORMALS) pryDownNormalsKernel<<<gridSize, blockSize>>>(in_pad, out_pad);
-        else pryDownVerticesKernel<<<gridSize, blockSize>>>(in_pad, out_pad);
-        cudaDeviceSynchronize();
-        cudaMemcpy(pyr[i + 1].ptr(), out_pad.ptr(), sizeof(float4) * (size_t)co * ro, cudaMemcpyDeviceToDevice);
+        if (NORMALS) pryDownNormalsKernel<<<gridSize, blockSize>>>(P.in[i], P.out[i]);
+        else pryDownVerticesKernel<<<gridSize, blockSize>>>(P.in[i], P.out[i]);
+        cudaMemcpyAsync(pyr[i + 1].ptr(), P.out[i].ptr(), sizeof(float4) * (size_t)co * ro, cudaMemcpyDeviceToDevice, 0);
     }
 }
 extern "C" void ref_downsample_new()
@@ -290,6 +301,21 @@ extern "C" long ref_download(int buffer, unsigned level, void* dst, size_t cap)
     if (!dptr || cap < nb) return -1;
     cudaMemcpy(dst, dptr, nb, cudaMemcpyDeviceToHost);
     return (long)nb;
+}
+
+// planes [z0, z1) of the volume as packed {tsdf, weight} (a 1024^3 volume does not fit a host array comfortably)
+extern "C" long ref_download_volume_planes(unsigned z0, unsigned z1, void* dst, size_t cap)
+{
+    int R = AP()->_volume_params.nResolution;
+    if (z0 >= z1 || z1 > (unsigned)R) return -1;
+    size_t n = (size_t)(z1 - z0) * R * R;
+    if (cap < n * sizeof(float2)) return -1;
+    float2* tmp; if (cudaMalloc(&tmp, n * sizeof(float2)) != cudaSuccess) return -2;
+    VolAccess va(DM()->volume);
+    ref_volume_to_float2<<<1184, 256>>>(va.raw() + (size_t)z0 * R * R, tmp, n);
+    cudaMemcpy(dst, tmp, n * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    return (long)(n * sizeof(float2));
 }
 
 extern "C" long ref_upload(int buffer, unsigned level, const void* src, size_t nbytes)

@@ -162,26 +162,6 @@ def raycast(vol, cfg, pose):
     return v, n
 
 
-def ray_flags(vol, R, brick):
-    nb = (R + brick - 1) // brick
-    f = np.zeros((nb, nb, nb), np.uint8)
-    cpu().orc_build_ray_flags(_fp(vol), R, brick, f.ctypes.data_as(C.c_void_p))
-    return f
-
-
-def raycast_skip(vol, cfg, pose, fine, fine_brick, coarse, coarse_brick, batch=8):
-    """CPU model of the empty-space-skipping march (oracle/hkf_oracle.c: orc_raycast_skip) -> v, n, stats[4]"""
-    cam = cam_of(cfg)
-    v = np.empty((cfg.rows, cfg.cols, 4), np.float32)
-    n = np.empty_like(v)
-    st = np.zeros(4, np.int64)
-    p = np.ascontiguousarray(pose, np.float32).reshape(16)
-    cpu().orc_raycast_skip(_fp(vol), cfg.resolution, C.c_float(cfg.volume_size), C.byref(cam), _fp(p), C.c_float(cfg.ray_increment),
-                           C.c_float(cfg.trunc_min), C.c_float(cfg.trunc_max), fine.ctypes.data_as(C.c_void_p), fine_brick,
-                           coarse.ctypes.data_as(C.c_void_p), coarse_brick, batch, _fp(v), _fp(n), st.ctypes.data_as(C.c_void_p))
-    return v, n, st
-
-
 def sdf_sums(vol, cfg, depth, cur):
     cam = cam_of(cfg)
     out = np.zeros(27, np.float32)
@@ -288,6 +268,8 @@ class Ref:
             lib.ref_upload.argtypes = [C.c_int, C.c_uint, C.c_void_p, C.c_size_t]
             lib.ref_marchingcube.restype = C.c_uint
             lib.ref_process_frame.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_void_p, F32P]
+            lib.ref_download_volume_planes.restype = C.c_long
+            lib.ref_download_volume_planes.argtypes = [C.c_uint, C.c_uint, C.c_void_p, C.c_size_t]
             Ref._lib = lib
         self.lib = Ref._lib
         self.cfg = cfg
@@ -319,6 +301,14 @@ class Ref:
         out = np.empty(shape, dt)
         got = self.lib.ref_download(buf, level, out.ctypes.data, out.nbytes)
         assert got == out.nbytes, (buf, got, out.nbytes)
+        return out
+
+    def download_volume_planes(self, z0, z1):
+        """planes [z0, z1) as packed {tsdf, weight} (for volumes too large to download whole)"""
+        R = self.cfg.resolution
+        out = np.empty((z1 - z0, R, R, 2), np.float32)
+        got = self.lib.ref_download_volume_planes(z0, z1, out.ctypes.data, out.nbytes)
+        assert got == out.nbytes, (got, out.nbytes)
         return out
 
     def upload(self, buf, arr, level=0):

@@ -1,7 +1,6 @@
-// frame_emu.cpp — block-level host emulation (emu_block.h) of the preprocess and integration kernels: the default
-// k_preprocess_fused / k_pyramids_fused / k_integrate_items / k_integrate (which the GPU tests pin: they check the
-// emulator) and the variants that have not seen a GPU yet (k_preprocess_tile_v2 + k_maps_pyramids_v2, item pass with
-// ray-march flags and the wider tile span).  Test infrastructure; the product library never links this.
+// frame_emu.cpp — block-level host emulation (emu_block.h) of the preprocess and integration kernels
+// (k_preprocess_tile + k_maps_pyramids, k_integrate_items + k_integrate) at sizes and views the GPU tests do not
+// use.  Test infrastructure; the product library never links this.
 #include "emu_shim.h"
 #include "emu_block.h"
 #include "../../hybkinectfu_b200/csrc/hkf_internal.cuh"
@@ -53,9 +52,8 @@ extern "C" void* emu_frame_create(unsigned cols, unsigned rows)
 }
 extern "C" void emu_frame_destroy(void* h) { delete static_cast<EmuFrame*>(h); }
 
-// variant 0: k_preprocess_fused + k_pyramids_fused (default); 1: k_preprocess_tile_v2 + k_maps_pyramids_v2
 extern "C" int emu_preprocess(void* h, const uint16_t* mm, float tmin, float tmax, float sigma_pixel, float sigma_depth,
-                              float cx, float cy, float fx, float fy, int variant)
+                              float cx, float cy, float fx, float fy)
 {
     EmuFrame* f = static_cast<EmuFrame*>(h);
     int radius; float ss, sd, thresh;
@@ -64,25 +62,13 @@ extern "C" int emu_preprocess(void* h, const uint16_t* mm, float tmin, float tma
     const int cols = (int)f->cols, rows = (int)f->rows;
     const dim3 b(TILE_W, TILE_H), g(div_up(f->cols, TILE_W), div_up(f->rows, TILE_H));
     const DepthBounds B = f->bounds.B;
-    if (variant == 0) {
-        emu_launch(g, b, [&]() {
-            k_preprocess_fused(mm, f->raw.data(), f->trunc.data(), f->filt.data(), f->v[0].data(), f->n[0].data(), cols, rows, radius,
-                               tmin, tmax, ss, sd, thresh, cx, cy, fx, fy, B);
-        });
-        const unsigned gx = div_up(f->lc[1], 2), gy = div_up(f->lr[1], 2);
-        emu_launch(dim3(div_up(gx, 32), div_up(gy, 4)), dim3(32, 4), [&]() {
-            k_pyramids_fused(f->v[0].data(), f->n[0].data(), f->v[1].data(), f->n[1].data(), f->v[2].data(), f->n[2].data(),
-                             f->lc[0], f->lc[1], f->lr[1], f->lc[2], f->lr[2], nullptr);
-        });
-    } else {
-        emu_launch(g, b, [&]() {
-            k_preprocess_tile_v2(mm, f->raw.data(), f->trunc.data(), f->filt.data(), cols, rows, radius, tmin, tmax, ss, sd, thresh, B);
-        });
-        emu_launch(dim3(div_up(f->cols, 16), div_up(f->rows, 16)), dim3(256), [&]() {
-            k_maps_pyramids_v2(f->filt.data(), f->v[0].data(), f->n[0].data(), f->v[1].data(), f->n[1].data(), f->v[2].data(), f->n[2].data(),
-                               cols, rows, f->lc[1], f->lr[1], f->lc[2], f->lr[2], cx, cy, fx, fy);
-        });
-    }
+    emu_launch(g, b, [&]() {
+        k_preprocess_tile(mm, f->raw.data(), f->trunc.data(), f->filt.data(), cols, rows, radius, tmin, tmax, ss, sd, thresh, B);
+    });
+    emu_launch(dim3(div_up(f->cols, 16), div_up(f->rows, 16)), dim3(256), [&]() {
+        k_maps_pyramids(f->filt.data(), f->v[0].data(), f->n[0].data(), f->v[1].data(), f->n[1].data(), f->v[2].data(), f->n[2].data(),
+                        cols, rows, f->lc[1], f->lr[1], f->lc[2], f->lr[2], cx, cy, fx, fy);
+    });
     return 0;
 }
 
@@ -97,11 +83,10 @@ extern "C" const void* emu_frame_buffer(void* h, int which)
     return ((which - 3) & 1) ? (const void*)f->n[l].data() : (const void*)f->v[l].data();
 }
 
-// One integration of the frame's truncated depth (k_integrate_items + k_integrate) into vol [R][R][R][2].
-// span: 1 (default) or 3; fine/coarse: ray-march bitmaps to maintain (may be null).  Returns the number of work items
-// written as free | general << 32.
+// One integration of the frame's truncated depth (k_integrate_items + k_integrate) into vol [R][R][R][2].  Returns the
+// number of work items written as free | general << 32.
 extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S, float wmax, const float* pose_inv16, float trunc, float maxdist,
-                                            float cx, float cy, float fx, float fy, int span, unsigned* fine, unsigned* coarse)
+                                            float cx, float cy, float fx, float fy)
 {
     EmuFrame* f = static_cast<EmuFrame*>(h);
     IntegrateArgs A;
@@ -116,18 +101,9 @@ extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S,
     memset(&st, 0, sizeof(st));
     const unsigned capacity = 4u * (unsigned)R * (unsigned)(R / 4) * div_up((unsigned)R, 128);
     std::vector<uint2> items(capacity);
-    RayFlags RF;
-    RF.fine = fine; RF.coarse = coarse;
-    RF.nbf = (R + HKF_RAY_FINE - 1) / HKF_RAY_FINE; RF.nbc = (R + HKF_RAY_COARSE - 1) / HKF_RAY_COARSE;
     const int ngroups = R * (R / INT_G);
     const dim3 g1(div_up((unsigned)ngroups, INT_GB)), b1(256);
-    const bool flags = fine != nullptr && coarse != nullptr;
-    emu_launch(g1, b1, [&]() {
-        if (flags && span == 3) k_integrate_items<false, true, 3>(A, &st, items.data(), capacity, 0, RF);
-        else if (flags) k_integrate_items<false, true, 1>(A, &st, items.data(), capacity, 0, RF);
-        else if (span == 3) k_integrate_items<false, false, 3>(A, &st, items.data(), capacity, 0, RF);
-        else k_integrate_items<false, false, 1>(A, &st, items.data(), capacity, 0, RF);
-    });
+    emu_launch(g1, b1, [&]() { k_integrate_items<false>(A, &st, items.data(), capacity, 0); });
     const unsigned long long counts = (unsigned long long)st.int_items[0] | ((unsigned long long)st.int_items[1] << 32);
     emu_launch(dim3(2), dim3(INT_THREADS), [&]() {          // persistent warps: any grid size walks the whole list
         k_integrate<false, false>(A, f->trunc.data(), reinterpret_cast<float2*>(vol), &st, items.data(), capacity, 0);

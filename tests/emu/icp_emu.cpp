@@ -1,9 +1,9 @@
-// icp_emu.cpp — host emulation of the ICP kernels of hybkinectfu_b200/csrc/icp.cu: k_icp (default, one iteration: checks
-// the emulator against the oracle's 27 sums) and k_icp_cluster (HKF_ICP_CLUSTER, not run on a GPU yet: all iterations of
-// a level, one CTA per library copy, see emu_cluster.h).  Test infrastructure; the product library never links this.
+// icp_emu.cpp — host emulation of the ICP kernel of hybkinectfu_b200/csrc/icp.cu: k_icp in its wrapper-parity form (the
+// 27 sums of one iteration against the oracle) and in its fused form (sums + the warp-parallel 6x6 solve of
+// solve_warp.cuh + gates + pose update, iteration after iteration, against the loop `oracle sums -> host solve`).
+// Test infrastructure; the product library never links this.
 #include "emu_shim.h"
 #include "emu_block.h"
-#include "emu_cluster.h"
 #include "../../hybkinectfu_b200/csrc/hkf_internal.cuh"
 #include "emu_indices.h"
 #include "../../hybkinectfu_b200/csrc/icp.cu"
@@ -38,22 +38,17 @@ extern "C" void emu_icp_sums(const float* nv, const float* nn, const float* mv, 
     memcpy(out27, st.sums, HKF_SUMS * sizeof(float));
 }
 
-// CTA `rank` of a cluster of ctx->nranks running k_icp_cluster; call concurrently from one host thread per rank, each on
-// its own copy of this library.  st: shared HkfDeviceState (cur / last_inv / track_status set by the caller).
-extern "C" void emu_icp_cluster_cta(void* ctx, int rank, const float* nv, const float* nn, const float* mv, const float* mn, int cols, int rows,
-                                    float cx, float cy, float fx, float fy, float dist_thres, float sin_thres, float angle_shake,
-                                    float dist_shake, int iters, void* st)
+// `iters` launches of the fused kernel (device-resident working transform, last-block solve) on the state `st`
+extern "C" void emu_icp_fused(const float* nv, const float* nn, const float* mv, const float* mn, int cols, int rows,
+                              float cx, float cy, float fx, float fy, float dist_thres, float sin_thres, float angle_shake,
+                              float dist_shake, int iters, void* st)
 {
-    EmuClusterCtx* C = static_cast<EmuClusterCtx*>(ctx);
+    std::vector<float> partials(HKF_SUMS * 256, 0.f);
     IcpArgs A;
-    fill(&A, nv, nn, mv, mn, cols, rows, cx, cy, fx, fy, dist_thres, sin_thres, angle_shake, dist_shake, nullptr);
-    struct HookArg { EmuClusterCtx* C; int rank; } ha = { C, rank };
-    EmuThreadHook hook;
-    hook.arg = &ha;
-    hook.enter = [](void* p) { HookArg* h = static_cast<HookArg*>(p); emu_cluster = h->C; emu_cluster_rank = (unsigned)h->rank; };
-    hook.leave = [](void* p) { static_cast<HookArg*>(p)->C->bar->arrive_and_drop(); };
-    emu_run_block((unsigned)rank, 0, 0, dim3((unsigned)C->nranks), dim3(ICPC_THREADS),
-                  [&]() { k_icp_cluster(A, static_cast<HkfDeviceState*>(st), iters); }, &hook);
+    fill(&A, nv, nn, mv, mn, cols, rows, cx, cy, fx, fy, dist_thres, sin_thres, angle_shake, dist_shake, partials.data());
+    const unsigned grid = (unsigned)(A.ntiles < 256 ? A.ntiles : 256);
+    for (int it = 0; it < iters; ++it)
+        emu_launch(dim3(grid), dim3(ICP_THREADS), [&]() { k_icp<true, true, false>(A, static_cast<HkfDeviceState*>(st)); });
 }
 
 extern "C" unsigned emu_state_bytes() { return (unsigned)sizeof(HkfDeviceState); }

@@ -8,7 +8,7 @@
 
 extern "C" int emu_raycast(const float* vol, int R, float S, unsigned cols, unsigned rows, float cx, float cy, float fx, float fy,
                            const float* pose16, float inc, float near_plane, float far_plane,
-                           unsigned* fine_bits, unsigned* coarse_bits, int fast, int skip, float* out_v4, float* out_n4)
+                           int fast, float* out_v4, float* out_n4)
 {
     RaycastArgs A;
     memset(&A, 0, sizeof(A));
@@ -18,9 +18,6 @@ extern "C" int emu_raycast(const float* vol, int R, float S, unsigned cols, unsi
     A.inc = inc; A.near_plane = near_plane; A.far_plane = far_plane;
     memcpy(A.pose, pose16, 64);
     A.own_z0 = 0; A.own_z1 = R; A.rank = 0; A.mailbox = nullptr; A.nranks = 1; A.epoch = 0;
-    A.RF.fine = fine_bits; A.RF.coarse = coarse_bits;
-    A.RF.nbf = (R + HKF_RAY_FINE - 1) / HKF_RAY_FINE; A.RF.nbc = (R + HKF_RAY_COARSE - 1) / HKF_RAY_COARSE;
-    if (skip && !(fast && fine_bits && coarse_bits)) return 1;
     float4* ov = reinterpret_cast<float4*>(out_v4);
     float4* on = reinterpret_cast<float4*>(out_n4);
     const unsigned gx = (cols + 15) / 16, gy = (rows + 15) / 16;
@@ -30,9 +27,8 @@ extern "C" int emu_raycast(const float* vol, int R, float S, unsigned cols, unsi
             emu_blockIdx = { bx, by, 0 }; emu_blockDim = { 256, 1, 1 }; emu_gridDim = { gx, gy, 1 };
             for (unsigned t = 0; t < 256; ++t) {
                 emu_threadIdx = { t, 0, 0 };
-                if (skip) k_raycast<false, false, true, true>(A, ov, on, nullptr, nullptr);
-                else if (fast) k_raycast<false, false, true, false>(A, ov, on, nullptr, nullptr);
-                else k_raycast<false, false, false, false>(A, ov, on, nullptr, nullptr);
+                if (fast) k_raycast<false, false, true>(A, ov, on, nullptr, nullptr);
+                else k_raycast<false, false, false>(A, ov, on, nullptr, nullptr);
             }
         }
     return 0;

@@ -1,14 +1,10 @@
-"""Host emulation of the ICP kernel sources (tests/emu): the default k_icp against the oracle's 27 sums at every pyramid
-level (the check of the emulator: that kernel is pinned on the GPU), and k_icp_cluster - all iterations of a level inside
-one thread-block cluster, HKF_ICP_CLUSTER, not run on a GPU yet - against the reference loop `oracle sums -> host solve`.
-A cluster is emulated with one COPY of the emulation library per CTA (own `static` = __shared__ storage), all CTAs
-running concurrently, cluster.sync() as a barrier over all their threads and map_shared_rank() as an offset between the
-copies' load addresses (tests/emu/emu_cluster.h)."""
+"""Host emulation of the ICP kernel source (tests/emu): k_icp against the oracle's 27 sums at every pyramid level, and the
+FUSED form of the same kernel - sums, the warp-parallel 6x6 Cholesky solve and LU determinant of csrc/solve_warp.cuh, the
+gates and the pose update, one launch per iteration - against the reference loop `oracle sums -> host solve`
+(hkf_solver.h on the CPU), bit for bit, failure paths included."""
 import ctypes as C
 import os
-import shutil
 import subprocess
-import threading
 
 import numpy as np
 import pytest
@@ -34,8 +30,8 @@ def scene():
         pytest.skip("CUDA headers not found")
     r = subprocess.run(["make", "-C", EMU_DIR, "libicp_emu.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
-    if not C.CDLL(os.path.join(EMU_DIR, "libicp_emu.so")).emu_can_spawn(4 * 1024 + 64):
-        pytest.skip("this container does not allow the 4096 threads of an emulated 4-CTA cluster")
+    if not C.CDLL(os.path.join(EMU_DIR, "libicp_emu.so")).emu_can_spawn(512 + 64):
+        pytest.skip("this container does not allow the 512 threads of an emulated block")
     from hybkinectfu_b200 import synth
     cfg = small_config(64)
     cam = synth.Camera().scaled(cfg.cols, cfg.rows)
@@ -90,64 +86,41 @@ def _reference_loop(scene, level, iters, angle_shake, maps):
     return cur, sums, status
 
 
-_copies = [0]
-
-
-def _cluster(scene, level, iters, cs, angle_shake, maps, tmp_path):
+def _fused(scene, level, iters, angle_shake, maps):
     cfg = scene["cfg"]
     oc = O.cam_of(cfg, level)
-    libs = []
-    for r in range(cs):
-        _copies[0] += 1          # never overwrite an image that is already mapped
-        path = str(tmp_path / f"libicp_emu_{_copies[0]}.so")
-        shutil.copy(scene["emu"], path)
-        L = C.CDLL(path)
-        L.emu_lib_base.restype = C.c_size_t
-        L.emu_cluster_create.restype = C.c_void_p
-        libs.append(L)
-    assert len({L.emu_lib_base() for L in libs}) == cs, "the library copies must be distinct images"
-    ctx = libs[0].emu_cluster_create(cs, 1024)
-    for r, L in enumerate(libs):
-        libs[0].emu_cluster_set_base(C.c_void_p(ctx), r, C.c_size_t(L.emu_lib_base()))
-    st = np.zeros(libs[0].emu_state_bytes() + 64, np.uint8)
-    libs[0].emu_state_init(_p(st), _p(scene["prev"]), _p(scene["last_inv"]))
-
-    def run(r):
-        libs[r].emu_icp_cluster_cta(C.c_void_p(ctx), r, *[_p(m) for m in maps], int(oc.cols), int(oc.rows), _f(oc.cx), _f(oc.cy), _f(oc.fx), _f(oc.fy),
-                                    _f(cfg.icp_dist_thres), _f(cfg.icp_norm_sin_thres), _f(angle_shake), _f(cfg.icp_dist_shake), iters, _p(st))
-
-    threads = [threading.Thread(target=run, args=(r,)) for r in range(cs)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    lib = C.CDLL(scene["emu"])
+    st = np.zeros(lib.emu_state_bytes() + 64, np.uint8)
+    lib.emu_state_init(_p(st), _p(scene["prev"]), _p(scene["last_inv"]))
+    lib.emu_icp_fused(*[_p(m) for m in maps], int(oc.cols), int(oc.rows), _f(oc.cx), _f(oc.cy), _f(oc.fx), _f(oc.fy),
+                      _f(cfg.icp_dist_thres), _f(cfg.icp_norm_sin_thres), _f(angle_shake), _f(cfg.icp_dist_shake), iters, _p(st))
     cur, sums, status = np.zeros(16, np.float32), np.zeros(27, np.float32), C.c_int(0)
-    libs[0].emu_state_read(_p(st), _p(cur), _p(sums), C.byref(status))
-    libs[0].emu_cluster_destroy(C.c_void_p(ctx))
+    lib.emu_state_read(_p(st), _p(cur), _p(sums), C.byref(status))
     return cur, sums, status.value
 
 
-@pytest.mark.parametrize("level,iters,cs", [(2, 10, 1), (2, 10, 2), (1, 5, 4)])
-def test_cluster_kernel_equals_the_iteration_loop(scene, tmp_path, level, iters, cs):
+@pytest.mark.parametrize("level,iters", [(2, 10), (1, 5), (0, 2)])
+def test_fused_kernel_equals_the_iteration_loop(scene, level, iters):
+    """the last block's warp-parallel solve (rows on lanes, shuffles) gives the bits of the single-thread hkf_solver.h"""
     cfg = scene["cfg"]
     maps = [scene[k][level] for k in ("NV", "NN", "MV", "MN")]
     c0, s0, st0 = _reference_loop(scene, level, iters, cfg.icp_angle_shake, maps)
-    c1, s1, st1 = _cluster(scene, level, iters, cs, cfg.icp_angle_shake, maps, tmp_path)
+    c1, s1, st1 = _fused(scene, level, iters, cfg.icp_angle_shake, maps)
     assert st0 == 0 and st1 == 0
     assert not np.array_equal(c0, scene["prev"])                       # the pose did move
     assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32)) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
 
 
-def test_cluster_kernel_failure_paths(scene, tmp_path):
+def test_fused_kernel_failure_paths(scene):
     cfg = scene["cfg"]
     level = 2
     maps = [scene[k][level] for k in ("NV", "NN", "MV", "MN")]
     # shake gate: an absurdly small angle limit trips on the first iteration; the working transform stays untouched
     c0, _, st0 = _reference_loop(scene, level, 10, 1e-9, maps)
-    c1, _, st1 = _cluster(scene, level, 10, 2, 1e-9, maps, tmp_path)
+    c1, _, st1 = _fused(scene, level, 10, 1e-9, maps)
     assert st0 == 2 and st1 == 2 and np.array_equal(c0.view(np.uint32), c1.view(np.uint32)) and np.array_equal(c1, scene["prev"])
     # no correspondences at all: singular normal equations
     empty = [maps[0], maps[1], np.zeros_like(maps[2]), np.zeros_like(maps[3])]
     c0, _, st0 = _reference_loop(scene, level, 10, cfg.icp_angle_shake, empty)
-    c1, _, st1 = _cluster(scene, level, 10, 2, cfg.icp_angle_shake, empty, tmp_path)
+    c1, _, st1 = _fused(scene, level, 10, cfg.icp_angle_shake, empty)
     assert st0 == 1 and st1 == 1 and np.array_equal(c0.view(np.uint32), c1.view(np.uint32))

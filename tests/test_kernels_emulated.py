@@ -1,7 +1,7 @@
 """Block-level host emulation (tests/emu/emu_block.h: one std::thread per simulated CUDA thread, barriers for
 __syncthreads and the warp collectives) of the preprocess and integration KERNEL SOURCES against the CPU oracle, bit for
-bit.  The default kernels are pinned on the GPU already - here they check the emulator; the variants behind
-HKF_PRE_V2, HKF_INT_SPAN and HKF_RAY_SKIP have not run on a GPU yet and are checked here."""
+bit.  The kernels are pinned on the GPU by tests/test_gpu_*.py; here the same sources run on this box, also at sizes the
+GPU tests do not use (odd image sizes, a volume that is not a power of two)."""
 import ctypes as C
 import os
 import subprocess
@@ -11,7 +11,7 @@ import pytest
 
 import _oracle as O
 from conftest import ROOT, bits_equal, n_mismatch, small_config
-from test_raycast_emulated import _pack, _run as _raycast_emulated
+from test_raycast_emulated import _run as _raycast_emulated
 
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 
@@ -44,10 +44,10 @@ def _f(x):
     return C.c_float(float(x))
 
 
-def _preprocess(lib, h, cfg, mm, variant):
+def _preprocess(lib, h, cfg, mm):
     mm = np.ascontiguousarray(mm, np.uint16)
     assert lib.emu_preprocess(C.c_void_p(h), mm.ctypes.data_as(C.c_void_p), _f(cfg.trunc_min), _f(cfg.trunc_max), _f(cfg.sigma_pixel),
-                              _f(cfg.sigma_depth), _f(cfg.cx), _f(cfg.cy), _f(cfg.fx), _f(cfg.fy), variant) == 0
+                              _f(cfg.sigma_depth), _f(cfg.cx), _f(cfg.cy), _f(cfg.fx), _f(cfg.fy)) == 0
 
 
 def _buffer(lib, h, which, shape):
@@ -55,8 +55,7 @@ def _buffer(lib, h, which, shape):
     return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=shape).copy()
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["default", "HKF_PRE_V2"])
-def test_preprocess_kernels_equal_oracle(frame, variant):
+def test_preprocess_kernels_equal_oracle(frame):
     from hybkinectfu_b200 import synth
     cfg = small_config(64)
     cam = synth.Camera().scaled(cfg.cols, cfg.rows)
@@ -69,68 +68,42 @@ def test_preprocess_kernels_equal_oracle(frame, variant):
     v2, n2 = O.down(v1, False), O.down(n1, True)
     h = frame.emu_frame_create(cfg.cols, cfg.rows)
     try:
-        _preprocess(frame, h, cfg, mm, variant)
+        _preprocess(frame, h, cfg, mm)
         for i, (name, want) in enumerate(zip(["raw", "trunc", "filtered", "v0", "n0", "v1", "n1", "v2", "n2"], [raw, tr, fl, v0, n0, v1, n1, v2, n2])):
             assert n_mismatch(want, _buffer(frame, h, i, want.shape)) == 0, name
     finally:
         frame.emu_frame_destroy(C.c_void_p(h))
 
 
-def _integrate_sequence(lib, cfg, poses, span, flags):
+def _integrate_sequence(lib, cfg, poses):
     from hybkinectfu_b200 import synth
     R = cfg.resolution
     cam = synth.Camera().scaled(cfg.cols, cfg.rows)
     vol = np.zeros((R, R, R, 2), np.float32)
     want = np.zeros_like(vol)
-    nbf, nbc = (R + 15) // 16, (R + 63) // 64
-    fine = np.zeros((nbf ** 3 + 31) // 32, np.uint32)
-    coarse = np.zeros((nbc ** 3 + 31) // 32, np.uint32)
     items = [0, 0]
     h = lib.emu_frame_create(cfg.cols, cfg.rows)
     try:
         for p in poses:
             mm = synth.render_depth_mm(p, cam)
-            _preprocess(lib, h, cfg, mm, 0)
+            _preprocess(lib, h, cfg, mm)
             inv = np.ascontiguousarray(O.mat44_inverse(p.astype(np.float32)), np.float32).reshape(16)
             cnt = lib.emu_integrate(C.c_void_p(h), vol.ctypes.data_as(C.c_void_p), R, _f(cfg.volume_size), _f(cfg.weight_max),
                                     inv.ctypes.data_as(C.c_void_p), _f(cfg.sdf_trunc), _f(cfg.max_integrate_dist), _f(cfg.cx), _f(cfg.cy),
-                                    _f(cfg.fx), _f(cfg.fy), span, fine.ctypes.data_as(C.c_void_p) if flags else None,
-                                    coarse.ctypes.data_as(C.c_void_p) if flags else None)
+                                    _f(cfg.fx), _f(cfg.fy))
             items[0] += cnt & 0xffffffff; items[1] += cnt >> 32
             O.integrate(want, cfg, O.trunc(O.decode_mm(mm), cfg.trunc_min, cfg.trunc_max), p.astype(np.float32))
     finally:
         lib.emu_frame_destroy(C.c_void_p(h))
-    return vol, want, fine, coarse, items
+    return vol, want, items
 
 
-@pytest.mark.parametrize("span,flags", [(1, False), (3, True)], ids=["default", "HKF_INT_SPAN+flags"])
-def test_integration_kernels_equal_oracle(frame, span, flags):
+def test_integration_kernels_equal_oracle(frame):
     from hybkinectfu_b200 import synth
     cfg = small_config(64)
-    vol, want, fine, coarse, items = _integrate_sequence(frame, cfg, synth.trajectory(200)[::7][:2], span, flags)
+    vol, want, items = _integrate_sequence(frame, cfg, synth.trajectory(200)[::7][:2])
     assert (want[..., 1] > 0).sum() > 10000 and items[1] > 0
     assert n_mismatch(vol, want) == 0
-
-
-def test_flags_of_the_item_pass_cover_every_negative_voxel_and_the_skipping_march_is_exact(frame, ray):
-    """the HKF_RAY_SKIP chain end to end on the CPU: bitmaps written by k_integrate_items<FLAGS> -> k_raycast<SKIP>"""
-    from hybkinectfu_b200 import synth
-    cfg = small_config(128)
-    R = cfg.resolution
-    poses = synth.trajectory(200)[::9][:2]
-    vol, want, fine, coarse, items = _integrate_sequence(frame, cfg, poses, 1, True)
-    assert n_mismatch(vol, want) == 0
-    need_f, need_c = O.ray_flags(want, R, 16).ravel().astype(bool), O.ray_flags(want, R, 64).ravel().astype(bool)
-    have_f = np.unpackbits(fine.view(np.uint8), bitorder="little")[:need_f.size].astype(bool)
-    have_c = np.unpackbits(coarse.view(np.uint8), bitorder="little")[:need_c.size].astype(bool)
-    assert need_f.sum() > 0 and not (need_f & ~have_f).any() and not (need_c & ~have_c).any()
-    assert have_f.sum() < have_f.size            # something is left to skip
-    for pose in (poses[-1], synth.trajectory(200)[40]):
-        pose = np.asarray(pose, np.float32)
-        v0, n0 = O.raycast(vol, cfg, pose)
-        v1, n1 = _raycast_emulated(ray, vol, cfg, pose, 1, 1, fine, coarse)
-        assert (n0[..., :3] != 0).any(-1).sum() > 500
-        assert bits_equal(v0, v1) and bits_equal(n0, n1)
 
 
 def test_odd_image_size_and_non_power_of_two_volume(frame, ray):
@@ -149,17 +122,16 @@ def test_odd_image_size_and_non_power_of_two_volume(frame, ray):
     v0 = O.vertices(fl, O.cam_of(cfg)); n0 = O.normals(v0)
     v1, n1 = O.down(v0, False), O.down(n0, True)
     v2, n2 = O.down(v1, False), O.down(n1, True)
-    for variant in (0, 1):
-        h = frame.emu_frame_create(cols, rows)
-        try:
-            _preprocess(frame, h, cfg, mm, variant)
-            for i, (name, want) in enumerate(zip(["raw", "trunc", "filtered", "v0", "n0", "v1", "n1", "v2", "n2"], [raw, tr, fl, v0, n0, v1, n1, v2, n2])):
-                assert n_mismatch(want, _buffer(frame, h, i, want.shape)) == 0, (variant, name)
-        finally:
-            frame.emu_frame_destroy(C.c_void_p(h))
-    vol, want, fine, coarse, items = _integrate_sequence(frame, cfg, traj[::9][:2], 3, True)
+    h = frame.emu_frame_create(cols, rows)
+    try:
+        _preprocess(frame, h, cfg, mm)
+        for i, (name, want) in enumerate(zip(["raw", "trunc", "filtered", "v0", "n0", "v1", "n1", "v2", "n2"], [raw, tr, fl, v0, n0, v1, n1, v2, n2])):
+            assert n_mismatch(want, _buffer(frame, h, i, want.shape)) == 0, name
+    finally:
+        frame.emu_frame_destroy(C.c_void_p(h))
+    vol, want, items = _integrate_sequence(frame, cfg, traj[::9][:2])
     assert items[0] > 0 and items[1] > 0 and n_mismatch(vol, want) == 0
     pose = traj[20].astype(np.float32)
     a, b = O.raycast(want, cfg, pose)
-    c, d = _raycast_emulated(ray, want, cfg, pose, 0, 0)
+    c, d = _raycast_emulated(ray, want, cfg, pose, 0)
     assert (b[..., :3] != 0).any(-1).sum() > 500 and bits_equal(a, c) and bits_equal(b, d)

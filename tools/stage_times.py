@@ -62,17 +62,6 @@ def main():
         timed(f"icp sums only level {l}", lambda l=l: ctx.lib.hkf_cal_point_to_plane_err_solver_params(
             ctx._h, l, capi.Mat44.from_np(pose), capi.Mat44.from_np(np.linalg.inv(pose)), cfg.level_camera(l), 0.1, 0.2))
     timed("sdf sums only", lambda: ctx.lib.hkf_cal_sdf_solver_params(ctx._h, cfg.camera(), capi.Mat44.from_np(pose)))
-    import ctypes as C
-    for l in (2, 1, 0):
-        ctx.lib.hkf_cal_point_to_plane_err_solver_params(ctx._h, l, capi.Mat44.from_np(pose), capi.Mat44.from_np(np.linalg.inv(pose)), cfg.level_camera(l), 0.1, 0.2)
-        ctx.sync()
-        dbg = np.zeros(8, np.int64)
-        ctx.lib.hkf_download(ctx._h, 100, 0, dbg.ctypes.data, 64)
-        print(f"k_icp<sums> level {l} last-block SM cycles: tile {dbg[0]}  fence+ticket {dbg[1]}  second-stage {dbg[2]}  tail {dbg[3]}")
-    ctx.icp_track(); ctx.sync()
-    dbg = np.zeros(8, np.int64)
-    ctx.lib.hkf_download(ctx._h, 100, 0, dbg.ctypes.data, 64)
-    print(f"k_icp<fused> level 0 last-block SM cycles: tile {dbg[0]}  fence+ticket {dbg[1]}  second-stage {dbg[2]}  solve+commit {dbg[3]}  (warp 0: llt/transform step {dbg[4]}, warp 1: determinant gate {dbg[5]})")
     nupd = ctx.count_updates(pose)
     print(f"N_upd {nupd} ({100.0*nupd/R**3:.1f}%)  integrate algorithmic GB/s {(16*nupd+4*640*480)/t['int']/1e3:.0f}")
     print(f"sum of stages {t['pre']+t['icp']+t['int']+t['ray']:.1f} us -> {1e6/(t['pre']+t['icp']+t['int']+t['ray']):.0f} fps")
