@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhkf_b200.so")
+LIB_PATH = os.environ.get("HKF_LIB") or os.path.join(_HERE, "libhkf_b200.so")      # HKF_LIB: a profiling build of the same library
 
 
 class HkfError(RuntimeError):

@@ -158,7 +158,7 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     CREATE_CUDA(cudaMemset(c->vol, 0, nvox * sizeof(float2)));
     // at most four work items per 4 x 128 voxel brick: one per general chunk, or one for its free chunks (integrate.cu)
     c->int_capacity = 4u * (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
-    CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint2)));
+    CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint4)));
     c->sm_count = prop.multiProcessorCount;
     if (p->max_triangles) CREATE_CUDA(cudaMalloc(&c->tris, (size_t)p->max_triangles * sizeof(HkfTriangle)));
     CREATE_CUDA(cudaMalloc(&c->st, sizeof(HkfDeviceState)));
@@ -223,6 +223,9 @@ static void* buf_ptr(hkf_ctx* c, int buffer, unsigned level, size_t* nbytes)
     case HKF_BUF_SOLVER_SUMS: *nbytes = HKF_SUMS * sizeof(float); return c->st->sums;
     case HKF_BUF_POSE: *nbytes = 16 * sizeof(float); return c->st->pose;
     case HKF_BUF_RAYCAST_KEYS: *nbytes = n0 * sizeof(unsigned long long); return c->ray_keys;
+#ifdef HKF_ICP_STAMPS
+    case 100: *nbytes = sizeof(c->st->stamps); return c->st->stamps;      // profiling build only
+#endif
     default: return nullptr;
     }
 }

@@ -56,6 +56,10 @@ struct HkfDeviceState {
     unsigned long long upd_count;
     float sums[HKF_SUMS + 5]; // reduced 27 sums (+ padding)
     int   sdf_done;          // SDF tracker: converged flag (|x| < 1e-3)
+#ifdef HKF_ICP_STAMPS          /* profiling build only (make stamps): %globaltimer stamps of the tracking launches */
+    unsigned long long stamps[32][8];
+    unsigned stamp_it;
+#endif
     unsigned int_items[4];   // integration work-item counters [parity][free, general] (double-buffered: one pair is appended to while the other is cleared)
 };
 
@@ -122,9 +126,10 @@ struct hkf_ctx {
     unsigned max_blocks = 0;
     // volume slab
     float2* vol = nullptr;
-    uint2* int_items = nullptr;        // integration work items (row, 128-voxel segment, interval)
+    uint4* int_items = nullptr;        // integration work items (integrate.cu: make_free_item / make_general_item)
     unsigned int_capacity = 0;
     int int_parity = 0;
+    bool int_attr_set[2][2]{};         // cudaFuncSetAttribute done for k_integrate<FROM_STATE, COUNT_ONLY> on this context's device
     int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes
     unsigned own_z0 = 0, own_z1 = 0;   // owned planes

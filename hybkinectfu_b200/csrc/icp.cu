@@ -24,12 +24,11 @@
 //    threads b and b+256, accumulates them in that order and stores their sum: the last block to finish (one ticket
 //    atomic per block) reads [27][<=256] values in one round trip and folds them with the remaining levels of the
 //    reference's tree;
-//  * warp 0 then runs the Cholesky solve (rows spread over its lanes, solve_warp.cuh), the Euler/shake gate and the
-//    pose update (trig and the small matrix products spread over its lanes as well) while warp 1 evaluates the
-//    determinant gate concurrently; 16 lanes commit the new working transform.
+//  * warp 0 then runs the Cholesky solve (one lane), the Euler/shake gate and the pose update (trig and the small matrix
+//    products spread over its lanes) while warp 1 evaluates the determinant gate concurrently (hkf_solver.h); 16 lanes
+//    commit the new working transform.
 #include "hkf_internal.cuh"
 #include "hkf_solver.h"
-#include "solve_warp.cuh"
 #include "reduce27.cuh"
 
 struct IcpArgs {
@@ -45,6 +44,13 @@ struct IcpArgs {
     float cur[16], last_inv[16];   // only used when !FROM_STATE
     ShardPeers peers; unsigned seq;   // peer-memory sharded mode (P2P): exchange of the partial sums inside this kernel
 };
+
+#ifdef HKF_ICP_STAMPS
+__device__ __forceinline__ unsigned long long icp_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define ICP_STAMP(slot) do { if (threadIdx.x == 0) st->stamps[st->stamp_it & 31][slot] = icp_now(); } while (0)
+#else
+#define ICP_STAMP(slot) do { } while (0)
+#endif
 
 #define ICP_TILES 2
 #define ICP_THREADS (ICP_TILES * 256)
@@ -154,6 +160,9 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     __shared__ int s_flag[5];                  // 0: tracking live, 1: last block, 2: singular, 3: step result, 4: peer timeout
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tl = threadIdx.x >> 8, t = threadIdx.x & 255;
+#ifdef HKF_ICP_STAMPS
+    const unsigned long long t_entry = icp_now();
+#endif
     pdl_launch_dependents();
     const int nblocks = (int)gridDim.x;                                   // = min(256, ntiles)
     const int rounds = (A.ntiles - (int)blockIdx.x + 2 * 256 - 1) / (2 * 256);   // tiles b + 256 k < ntiles, two k per round
@@ -173,7 +182,13 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     load_pixel();
 
     // ---- everything below depends on the previous launch (pose, status, ticket, partials)
+#ifdef HKF_ICP_STAMPS
+    const unsigned long long t_loaded = icp_now();
+#endif
     pdl_wait();
+#ifdef HKF_ICP_STAMPS
+    const unsigned long long t_waited = icp_now();
+#endif
     if (FROM_STATE) {
         if (threadIdx.x < 32) s_m[threadIdx.x] = __ldcg(threadIdx.x < 16 ? &st->cur[threadIdx.x] : &st->last_inv[threadIdx.x - 16]);
         if (threadIdx.x == 32) s_flag[0] = (__ldcg(&st->track_status) == HKF_TRACK_OK);
@@ -225,6 +240,10 @@ k_icp(IcpArgs A, HkfDeviceState* st)
     }
     __syncthreads();
     if (!s_flag[1]) return;
+#ifdef HKF_ICP_STAMPS
+    if (threadIdx.x == 0) { st->stamps[st->stamp_it & 31][0] = t_entry; st->stamps[st->stamp_it & 31][1] = t_loaded; st->stamps[st->stamp_it & 31][2] = t_waited; }
+#endif
+    ICP_STAMP(3);
     __threadfence();
     {
         // rows 2 per warp, all 16 loads in flight; lane owns entries lane + 32 m, the remaining levels 128/64/32 and
@@ -254,16 +273,31 @@ k_icp(IcpArgs A, HkfDeviceState* st)
             return;
         }
     }
+    ICP_STAMP(4);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + HKF_SUMS) st->sums[threadIdx.x - 64] = s_sums[threadIdx.x - 64];
     if (threadIdx.x == 64) st->ticket = 0;
     if (!SOLVE) return;
     // ---- the solve (hkf_icp_step, operation for operation) on warp 0 while warp 1 evaluates the determinant gate: Cholesky
-    // with rows on lanes 0-6, the three sin/cos pairs on lanes 0-2, the 3x3 products on lanes 0-8, the shake gate on lane 0
+    // on lane 0, the three sin/cos pairs on lanes 0-2, the 3x3 products on lanes 0-8, the shake gate on lane 0
     // next to the 4x4 product T * cur on lanes 16-31
     __shared__ float s_R[3][9], s_Rxy[9], s_Rf[9], s_c2[16];
     if (warp == 0) {
+        // The Cholesky solve stays on ONE lane: its divisions and square roots form a dependent chain that the lane's own
+        // instruction-level parallelism already overlaps column by column.  Spreading the rows over lanes (shuffles for the
+        // pivot row, bit-identical results) was measured SLOWER on B200: 3.0 instead of 2.5 us per iteration
+        // (profiles/r2_icp_stamps_*.txt) - the shuffle latency lands on the critical path.
+        __shared__ float s_x[6];
+        if (lane == 0) {
+            float Am[36], bv[6], xs[6];
+            hkf_unpack27(s_sums, Am, bv);
+            hkf_llt_solve6(Am, bv, xs);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s_x[i] = xs[i];
+        }
+        __syncwarp();
         float x[6];
-        hkf_llt_solve6_warp(s_sums, lane, x);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = s_x[i];
         if (lane < 3) {
             float R[9];
             hkf_rot_axis(lane, lane == 0 ? x[0] : lane == 1 ? x[1] : x[2], R);
@@ -298,11 +332,12 @@ k_icp(IcpArgs A, HkfDeviceState* st)
             acc = __fadd_rn(acc, __fmul_rn(t3r, cur[3 * 4 + j]));
             s_c2[e] = acc;
         }
-    } else if (warp == 1) {
-        const float det = hkf_det6_warp(s_sums, lane);
-        if (lane == 0) s_flag[2] = ((double)det < 1E-10) ? 1 : 0;       // hkf_icp_singular
+    } else if (threadIdx.x == 32) {
+        s_flag[2] = hkf_icp_singular(s_sums) ? 1 : 0;
     }
+    ICP_STAMP(5);
     __syncthreads();
+    ICP_STAMP(6);
     // det(AtA) < 1e-10 is tested first (CameraPoseFinderICP.cpp:138), then the shake gate
     const int status = s_flag[2] ? HKF_TRACK_SINGULAR : s_flag[3] != HKF_SOLVE_OK ? HKF_TRACK_SHAKE : HKF_TRACK_OK;
     if (status != HKF_TRACK_OK) {
@@ -321,6 +356,10 @@ k_icp(IcpArgs A, HkfDeviceState* st)
 #pragma unroll
         for (int i = 0; i < 16; ++i) st->pose_inv[i] = inv[i];
     }
+#ifdef HKF_ICP_STAMPS
+    __syncthreads();
+    if (threadIdx.x == 0) { st->stamps[st->stamp_it & 31][7] = icp_now(); st->stamp_it++; }
+#endif
 }
 
 // start of a frame's tracking: cur = pose, last_inv = pose^-1 (CameraPoseFinderICP.cpp:62-63)

@@ -8,19 +8,24 @@
 // and an atomicAdd per thread per call.
 //
 // This design (HBM-bound by construction, no tensor cores; the history of measurements is in DESIGN.md 3.4 and
-// profiles/r1_integrate_*):
+// profiles/r1_integrate_*, profiles/r2_integrate_*):
 //  * storage is packed {f32 tsdf, f32 weight} (8 B) in [z][y][x] order, x fastest; a lane owns voxel x = chunk + lane,
 //    so every warp load/store moves 256 contiguous bytes;
 //  * pass 1 (k_integrate_items) intersects every group of 4 voxel rows (straight lines in camera space) with the view
-//    frustum and the frame's depth range analytically, then classifies each 32-voxel chunk of the interval against
-//    per-tile depth extrema published by the preprocess: dead (behind every visible surface), free (in front of every
-//    visible surface, all touched pixels integrable: tsdf = 1 exactly) or general, and writes two compact work lists;
-//  * pass 2 (k_integrate): persistent warps stride over the lists.  Free bricks are a pure streaming read-modify-write
-//    (no projection, no depth read, 16 loads in flight per warp).  General chunks (4 rows x 32 voxels) request their
-//    voxels first and then project.  The first ncu capture of a straightforward kernel showed it ISSUE-bound (74 %
-//    issue-active, 21 % DRAM: ~170 instructions per voxel, dominated by three IEEE divisions, f64 rounding and
-//    int<->float conversions on the quarter-rate XU pipe), so the projection decides everything it can from cheap
-//    approximations and only falls back to the reference's exact sequence where they cannot prove the result:
+//    frustum and the frame's depth range analytically, then classifies each 32-voxel chunk of the interval - one thread
+//    per chunk - against per-tile depth extrema published by the preprocess: dead (behind every visible surface), free
+//    (in front of every visible surface, all touched pixels integrable: tsdf = 1 exactly) or general, and writes two
+//    compact work lists;
+//  * pass 2 (k_integrate): persistent warps stride over BOTH lists at once.  The two kinds of work bound differently:
+//    free bricks are a pure streaming read-modify-write (no projection, no depth read: HBM-bound), general chunks
+//    (4 rows x 32 voxels, every voxel projected) are issue-bound (~60 instructions per 32 voxels).  Round 1 ran them one
+//    after the other (52 % DRAM throughput: the general phase starved the memory system, the free phase the issue
+//    slots).  Now every warp keeps the rows of its next free bricks in flight as bulk asynchronous copies
+//    (cp.async.bulk global -> shared memory, completion on an mbarrier: one elected lane, 4 instructions per 4 KB brick,
+//    no registers held) WHILE it projects general chunks, and turns to a brick when its bytes have landed.  The ncu
+//    A/B of the two designs is profiles/r2_integrate_*.txt.
+//  * the projection decides everything it can from cheap approximations and only falls back to the reference's exact
+//    sequence where they cannot prove the result:
 //      - pixel index: one MUFU.RCP shared by both axes gives the pixel coordinate to < 2e-4 px; unless it lies within
 //        2^-11 px of a rounding boundary the reference's integer is already decided (float->int through the 1.5*2^23
 //        magic constant: FMA-pipe only, no XU conversions);
@@ -125,23 +130,40 @@ __device__ __forceinline__ void load_pose_inv(const IntegrateArgs& A, const HkfD
     }
 }
 
-// work item: .x = y/4 | zrel << 10 | segment << 22 ; .y = first | last << 8 (voxel offsets inside the 128-voxel
-// segment that can be updated) | mask of chunks to project << 16 | mask of free-space chunks << 20
-__device__ __forceinline__ uint2 make_item(int yg, int zrel, int seg, int lo_rel, int hi_rel, unsigned gen, unsigned fre)
+// Work items (16 bytes; everything pass 2 would otherwise have to derive per item is precomputed once here):
+//   .x  voxel index / 4 of the item's first voxel in the stored slab (row y0 of plane zrel, x = the brick's first voxel
+//       for a free item, the chunk's first voxel for a general item); rows are R voxels apart
+//   .y  y0/4 | zrel << 10 | (first voxel x / 32) << 22           (general items: the voxel coordinates to project)
+//   .z  first | last << 8: offsets that can be updated, relative to the item's first voxel (0..127 / 0..31)
+//   .w  free items: mask of free chunks | first copied voxel offset << 8 | bytes per row of the bulk copy << 16
+__device__ __forceinline__ uint4 make_free_item(const IntegrateArgs& A, int yg, int zrel, int seg, int lo_rel, int hi_rel, unsigned fre)
 {
-    return make_uint2((unsigned)yg | ((unsigned)zrel << 10) | ((unsigned)seg << 22),
-                      (unsigned)lo_rel | ((unsigned)hi_rel << 8) | (gen << 16) | (fre << 20));
+    const unsigned xb = (unsigned)seg * INT_SEG;
+    const unsigned cf = (unsigned)__ffs((int)fre) - 1u, cl = (fre & 8u) ? 3u : (fre & 4u) ? 2u : (fre & 2u) ? 1u : 0u;
+    const unsigned x1 = min(xb + 32u * cl + 32u, (unsigned)A.R);           // R is a multiple of 4: 32-byte granules
+    const unsigned vox = ((unsigned)zrel * (unsigned)A.R + (unsigned)yg * INT_G) * (unsigned)(A.R / 4) + xb / 4;
+    return make_uint4(vox, (unsigned)yg | ((unsigned)zrel << 10) | ((xb / 32u) << 22), (unsigned)lo_rel | ((unsigned)hi_rel << 8),
+                      fre | ((32u * cf) << 8) | (((x1 - xb - 32u * cf) * 8u) << 16));
+}
+__device__ __forceinline__ uint4 make_general_item(const IntegrateArgs& A, int yg, int zrel, int seg, int lo_rel, int hi_rel, int c)
+{
+    const unsigned xc = (unsigned)seg * INT_SEG + 32u * (unsigned)c;
+    const unsigned vox = ((unsigned)zrel * (unsigned)A.R + (unsigned)yg * INT_G) * (unsigned)(A.R / 4) + xc / 4;
+    const int lo = max(lo_rel - 32 * c, 0), hi = min(hi_rel - 32 * c, 31);
+    return make_uint4(vox, (unsigned)yg | ((unsigned)zrel << 10) | ((xc / 32u) << 22), (unsigned)lo | ((unsigned)hi << 8), 0u);
 }
 
-// Pass 1 (thread per group of 4 voxel rows): the group's conservative interval, cut into 32-voxel chunks that are
-// classified against the frame's per-tile depth extrema, and the surviving 4 x 128 voxel bricks appended to two
-// compact work lists (one warp-aggregated atomic per list per 32 groups): bricks made of free-space chunks only
-// grow from the front of `items`, bricks with chunks that need projecting grow from the back.
+// Pass 1 (thread per group of 4 voxel rows, then thread per (group, 128-voxel segment)): the group's conservative
+// interval, cut into 32-voxel chunks that are classified against the frame's per-tile depth extrema, and the surviving
+// chunks appended to two compact work lists (one warp-aggregated atomic per list per warp): the free-space chunks of a
+// 4 x 128 voxel brick form ONE item growing from the front of `items`, every general chunk is an item of its own growing
+// from the back.  (A thread per CHUNK was measured too: four times the parallelism, but every thread repeats the
+// per-brick set-up - 12.6 M instead of 8.4 M warp instructions, 25.7 instead of 20.3 us, profiles/r2_integrate_a_*.)
 //
 // Chunk classification.  The voxel centres of a 4-row x 32-voxel chunk form a planar rectangle; while Z > 0 its
 // image is the convex hull of its four projected corners, and depth along it is extremal at a corner.  The
-// bounding box of the corners, grown by 1.5 px, touches at most 2 tiles per tile row at the level whose tile width
-// covers it.  From the depth extrema of those tiles:
+// bounding box of the corners, grown by 1.5 px, touches at most INT_SPAN + 1 tiles per tile row at the level whose tile
+// width covers it.  From the depth extrema of those tiles:
 //   dead : the nearest corner is farther than trunc behind the largest valid depth -> "sdf > -trunc"
 //          (integrateVolume.cu:64) fails for every voxel, the chunk is dropped;
 //   free : the box lies in the image interior, every pixel of the tiles is valid and < fMaxIntegrateDist, and the
@@ -155,10 +177,11 @@ __device__ __forceinline__ uint2 make_item(int yg, int zrel, int seg, int lo_rel
 // instead of 21.7 M with 1, integration 144.8 -> 142.5 us (profiles/r2_experimental.log).
 #define INT_SPAN 3
 template <bool FROM_STATE>
-__global__ void __launch_bounds__(256)
-k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __restrict__ items, unsigned capacity, int parity)
+__global__ void __launch_bounds__(256, 5)
+k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __restrict__ items, unsigned capacity, int parity)
 {
     __shared__ int s_lo[INT_GB], s_hi[INT_GB];
+    __shared__ int s_any;
     hkf_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int RG = A.R / INT_G;
@@ -168,6 +191,8 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
     if (FROM_STATE && st->track_status != HKF_TRACK_OK) return;   // "camera lost": no integration (HybKinectfu.cpp:123-147)
     float m[12];
     load_pose_inv(A, st, FROM_STATE, m);
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
 
     // ---- phase A: one thread per row group computes the group's interval
     if (threadIdx.x < INT_GB) {
@@ -181,8 +206,10 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
             if (!group_interval(A, m, wy0, wy1, wz, __uint_as_float(A.B.base[0]), x_lo, x_hi)) { x_lo = 1; x_hi = 0; }
         }
         s_lo[threadIdx.x] = x_lo; s_hi[threadIdx.x] = x_hi;
+        if (x_lo <= x_hi) s_any = 1;
     }
     __syncthreads();
+    if (!s_any) return;                                            // nothing of this block's rows can be updated
 
     // ---- phase B: one thread per (row group, 128-voxel segment) classifies the segment's four chunks
     const float thr_free = A.trunc * 1.000002f + 2e-4f, thr_dead = A.trunc + 2e-4f;
@@ -246,9 +273,6 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
                 pu0 = qu0; pu1 = qu1; pv0 = qv0; pv1 = qv1; pz0 = qz0; pz1 = qz1;
             }
         }
-        // Work lists: the free-space chunks of a brick form ONE item (pure streaming, 16 loads in flight) that grows
-        // from the front of `items`; every general chunk (4 rows x 32 voxels, all four rows need projecting) is an item
-        // of its own growing from the back, so pass 2 never spends an instruction on a dead or free chunk slot.
         const unsigned ng = (unsigned)__popc(gm);
         const bool isf = fm != 0;
         unsigned incl = ng;                                        // inclusive warp scan of the general-chunk counts
@@ -263,9 +287,9 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint2* __res
         }
         baseg = __shfl_sync(0xffffffffu, baseg, 0) + (incl - ng); basef = __shfl_sync(0xffffffffu, basef, 0);
         const int lo_rel = xa - seg * INT_SEG, hi_rel = xe - seg * INT_SEG;
-        if (isf) items[basef + __popc(bf & ((1u << lane) - 1))] = make_item(yg, zrel, seg, lo_rel, hi_rel, 0u, fm);
+        if (isf) items[basef + __popc(bf & ((1u << lane) - 1))] = make_free_item(A, yg, zrel, seg, lo_rel, hi_rel, fm);
         for (unsigned m2 = gm; m2; m2 &= m2 - 1)
-            items[capacity - 1 - baseg++] = make_item(yg, zrel, seg, lo_rel, hi_rel, m2 & (0u - m2), 0u);
+            items[capacity - 1 - baseg++] = make_general_item(A, yg, zrel, seg, lo_rel, hi_rel, __ffs((int)m2) - 1);
     }
 }
 
@@ -284,16 +308,64 @@ __device__ __forceinline__ void update_voxel(float2* p, const float2 old, float 
     if (tn != old.x || wn != old.y) *p = make_float2(tn, wn);
 }
 
-// Pass 2: persistent warps stride over the work items; a lane owns voxels x = seg*128 + 32 c + lane of each row, so
-// every warp load/store instruction moves 256 contiguous bytes.
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared memory with completion on an mbarrier.  One 4 KB
+// stage per WARP: the warp's elected lane arms the barrier with the byte count and issues one copy per voxel row; all
+// lanes later wait on the barrier's phase.  One stage is enough: the next brick is requested the moment the current one
+// has been read, and the warp then spends ~2 us projecting general chunks - longer than a DRAM round trip.
+// tests/emu runs the same code with the copy as a memcpy.
+#define INT_STAGE_VOX (INT_G * INT_SEG)              // 4 rows x 128 voxels = 4 KB
+#define INT_WARPS (INT_THREADS / 32)
+#define INT_SMEM_BYTES (INT_WARPS * INT_STAGE_VOX * 8 + INT_WARPS * 8)
+
+#ifdef HKF_EMULATE_DEVICE
+__device__ __forceinline__ void mbar_init(unsigned long long* bar) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long*, unsigned) {}
+__device__ __forceinline__ void mbar_fence_init() {}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+#endif
+
+// Pass 2: persistent warps stride over both work lists; a lane owns voxels x = first + 32 c + lane of each row, so
+// every warp load/store instruction moves 256 contiguous bytes.  Per warp: the rows of its next free brick are always
+// in flight as bulk copies; between two bricks the warp projects its share of general chunks (in proportion to the
+// lengths of the two lists, so that both run out together).
 template <bool FROM_STATE, bool COUNT_ONLY>
 __global__ void __launch_bounds__(INT_THREADS, 4)
 k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict__ vol, HkfDeviceState* __restrict__ st,
-            const uint2* __restrict__ items, unsigned capacity, int parity)
+            const uint4* __restrict__ items, unsigned capacity, int parity)
 {
+    HKF_DYN_SMEM(unsigned long long, dyn);
     hkf_pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const int R = A.R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned R = (unsigned)A.R;
     const unsigned n_free = st->int_items[parity * 2 + 0], n_gen = st->int_items[parity * 2 + 1];
     const unsigned wid = (blockIdx.x * INT_THREADS + threadIdx.x) >> 5;
     const unsigned nwarps = (gridDim.x * INT_THREADS) >> 5;
@@ -301,8 +373,77 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
     const float trunc = A.trunc, thr_one = A.trunc * 1.000002f, wmax = A.wmax;
     unsigned local_count = 0;
 
-    // ---- general chunks (the heavier items first): 4 rows x 32 voxels, every voxel is projected
-    if (wid < n_gen) {
+    // this warp's stage and barrier
+    float2* const stage = reinterpret_cast<float2*>(dyn) + (size_t)warp * INT_STAGE_VOX;
+    unsigned long long* const bar = dyn + (size_t)INT_WARPS * INT_STAGE_VOX + warp;
+    if (!COUNT_ONLY) {
+        if (lane == 0) { mbar_init(bar); mbar_fence_init(); }
+        __syncwarp();
+    }
+
+    // ---- free bricks.  fi = next brick to consume, fp = next brick to request (both strided by nwarps)
+    unsigned fi = wid, fp = wid, phase = 0;
+    auto free_issue = [&]() {
+        if (fp < n_free) {
+            if (lane == 0) {
+                const uint4 it = __ldg(items + fp);
+                const unsigned off = (it.w >> 8) & 0xffu, bytes = it.w >> 16;
+                const float2* src = vol + ((size_t)it.x * 4u + off);
+                mbar_expect_tx(bar, INT_G * bytes);
+#pragma unroll
+                for (int r = 0; r < INT_G; ++r) bulk_g2s(stage + r * INT_SEG + off, src + (size_t)r * R, bytes, bar);
+            }
+            fp += nwarps;
+#ifdef HKF_EMULATE_DEVICE
+            __syncwarp();                     // the host build copies synchronously on lane 0's thread
+#endif
+        }
+    };
+    auto free_consume = [&]() {
+        const uint4 cur = __ldg(items + fi);
+        const int rel = lane - (int)(cur.z & 0xffu);
+        const unsigned span = ((cur.z >> 8) & 0xffu) - (cur.z & 0xffu);
+        const unsigned fre = cur.w & 15u;
+        bool live[INT_NC];
+#pragma unroll
+        for (int c = 0; c < INT_NC; ++c) live[c] = (fre & (1u << c)) && ((unsigned)(rel + 32 * c) <= span);
+        if (COUNT_ONLY) {
+#pragma unroll
+            for (int c = 0; c < INT_NC; ++c) local_count += live[c] ? (unsigned)INT_G : 0u;
+        } else {
+            float2* __restrict__ vp = vol + ((size_t)cur.x * 4u + (unsigned)lane);
+            const float2* sp = stage + lane;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (int r = 0; r < INT_G; ++r)
+#pragma unroll
+                for (int c = 0; c < INT_NC; ++c)
+                    if (live[c]) {
+                        // tsdf = 1 (free space), weight 1: t' = fma(t, w, 1) / (w + 1); exactly 1 when t == 1 (the common
+                        // case: free space stays free) and when the voxel is new (t = w = 0)
+                        const float2 old = sp[r * INT_SEG + 32 * c];
+                        const float w1 = __fadd_rn(old.y, 1.0f);
+                        const float wn = fminf(w1, wmax);
+                        if (old.x == 1.0f) {
+                            if (wn != old.y) vp[(size_t)r * R + 32 * c] = make_float2(1.0f, wn);
+                        } else {
+                            const float tn = (old.x == 0.0f && old.y == 0.0f) ? 1.0f : __fdiv_rn(__fmaf_rn(old.x, old.y, 1.0f), w1);
+                            vp[(size_t)r * R + 32 * c] = make_float2(tn, wn);      // tn != old.x here or the bits are rewritten as they were
+                        }
+                    }
+            __syncwarp();                     // every lane has read the stage: it may be refilled
+        }
+        fi += nwarps;
+        if (!COUNT_ONLY) free_issue();
+    };
+    if (!COUNT_ONLY) free_issue();
+    const unsigned my_free = wid < n_free ? (n_free - wid + nwarps - 1) / nwarps : 0u;
+    const unsigned my_gen = wid < n_gen ? (n_gen - wid + nwarps - 1) / nwarps : 0u;
+    unsigned credit = 0;
+
+    // ---- general chunks: 4 rows x 32 voxels, every voxel is projected
+    if (my_gen) {
         float m[12];
         load_pose_inv(A, st, FROM_STATE, m);
         const int cols = A.cols;
@@ -310,16 +451,13 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
         const float ntrunc = -A.trunc;
         const float MAGIC = 12582912.0f;              // 1.5 * 2^23: adding it leaves the nearest integer in the mantissa
         const float edge = 0.5f - 0.00048828125f;     // within 2^-11 px of a rounding boundary -> the exact sequence decides
-        uint2 nxt = __ldg(items + (capacity - 1 - wid));
+        uint4 nxt = __ldg(items + (capacity - 1 - wid));
 #pragma unroll 1
         for (unsigned item = wid; item < n_gen; item += nwarps) {
-            const uint2 cur = nxt;
+            const uint4 cur = nxt;
             if (item + nwarps < n_gen) nxt = __ldg(items + (capacity - 1 - (item + nwarps)));      // prefetch the next item
-            const int y0 = (int)(cur.x & 0x3ffu) * INT_G, zrel = (int)((cur.x >> 10) & 0xfffu);
-            const int c = __ffs((int)((cur.y >> 16) & 15u)) - 1;                 // the chunk of the segment
-            const int xb = (int)(cur.x >> 22) * INT_SEG + 32 * c;
-            const bool inr = (unsigned)(lane + 32 * c - (int)(cur.y & 0xffu)) <= ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
-            float2* __restrict__ vp = vol + ((size_t)(zrel * R + y0) * R + xb + lane);
+            const bool inr = (unsigned)(lane - (int)(cur.z & 0xffu)) <= ((cur.z >> 8) & 0xffu) - (cur.z & 0xffu);
+            float2* __restrict__ vp = vol + ((size_t)cur.x * 4u + (unsigned)lane);
             // The voxels are requested first: the DRAM round trip then overlaps the projection arithmetic and the depth
             // read instead of following them (a few voxels that turn out not to be updated are read in vain).
             float2 old[INT_G];
@@ -328,8 +466,9 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                 old[r] = make_float2(0.f, 0.f);
                 if (!COUNT_ONLY && inr) old[r] = vp[(size_t)r * R];
             }
-            const float wz = __fmul_rn(__fadd_rn((float)(zrel + A.z_lo), 0.5f), cell);
-            const float wx = __fmul_rn((float)(xb + lane) + 0.5f, cell);
+            const int y0 = (int)(cur.y & 0x3ffu) * INT_G;
+            const float wz = __fmul_rn(__fadd_rn((float)((int)((cur.y >> 10) & 0xfffu) + A.z_lo), 0.5f), cell);
+            const float wx = __fmul_rn((float)((int)(cur.y >> 22) * 32 + lane) + 0.5f, cell);
             // the x and z parts of the three camera-space sums are shared by the four rows only in exact arithmetic: the
             // reference's association is fma(wz, m_3, fma(wx, m_1, wy*m_2)) + m_4 per voxel, kept as is
             float Z[INT_G];
@@ -368,41 +507,14 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                 if (COUNT_ONLY) local_count += live ? 1u : 0u;
                 else if (live) update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
             }
+            // a free brick whenever the general list has advanced by its share (my_free : my_gen)
+            credit += my_free;
+            while (credit >= my_gen && fi < n_free) { credit -= my_gen; free_consume(); }
         }
     }
+    // ---- the free bricks that are left (all of them when this warp had no general chunk)
+    while (fi < n_free) free_consume();
 
-    // ---- free-space bricks: a pure streaming read-modify-write, 16 x 256 B in flight per warp
-#pragma unroll 1
-    for (unsigned item = wid; item < n_free; item += nwarps) {
-        const uint2 cur = __ldg(items + item);
-        const int y0 = (int)(cur.x & 0x3ffu) * INT_G, zrel = (int)((cur.x >> 10) & 0xfffu);
-        const int xb = (int)(cur.x >> 22) * INT_SEG;
-        const int rel = lane - (int)(cur.y & 0xffu);
-        const unsigned span = ((cur.y >> 8) & 0xffu) - (cur.y & 0xffu);
-        const unsigned fre = (cur.y >> 20) & 15u;
-        float2* __restrict__ vp = vol + ((size_t)(zrel * R + y0) * R + xb + lane);
-        bool live[INT_NC];
-#pragma unroll
-        for (int c = 0; c < INT_NC; ++c) live[c] = (fre & (1u << c)) && ((unsigned)(rel + 32 * c) <= span);
-        if (COUNT_ONLY) {
-#pragma unroll
-            for (int c = 0; c < INT_NC; ++c) local_count += live[c] ? (unsigned)INT_G : 0u;
-        } else {
-            float2 old[INT_G][INT_NC];
-#pragma unroll
-            for (int r = 0; r < INT_G; ++r)
-#pragma unroll
-                for (int c = 0; c < INT_NC; ++c) {
-                    old[r][c] = make_float2(0.f, 0.f);
-                    if (live[c]) old[r][c] = vp[(size_t)r * R + 32 * c];
-                }
-#pragma unroll
-            for (int r = 0; r < INT_G; ++r)
-#pragma unroll
-                for (int c = 0; c < INT_NC; ++c)
-                    if (live[c]) update_voxel(vp + (size_t)r * R + 32 * c, old[r][c], 1e30f, trunc, thr_one, wmax);
-        }
-    }
     if (COUNT_ONLY) {
         for (int o = 16; o > 0; o >>= 1) local_count += __shfl_down_sync(0xffffffffu, local_count, o);
         if (lane == 0 && local_count) atomicAdd(&st->upd_count, (unsigned long long)local_count);
@@ -435,8 +547,13 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
     const dim3 g1(div_up(ngroups, INT_GB)), b1(256);
     hkf_launch_pdl(k_integrate_items<FROM_STATE>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
-    hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY>, dim3(c->sm_count * 4), dim3(INT_THREADS), 0, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
-                   (const uint2*)c->int_items, c->int_capacity, parity);
+    // function attributes are per device: set once per context (dynamic shared memory above the 48 KB default)
+    if (!c->int_attr_set[COUNT_ONLY ? 1 : 0][FROM_STATE ? 1 : 0]) {
+        HKF_CUDA(c, cudaFuncSetAttribute(k_integrate<FROM_STATE, COUNT_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INT_SMEM_BYTES));
+        c->int_attr_set[COUNT_ONLY ? 1 : 0][FROM_STATE ? 1 : 0] = true;
+    }
+    hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY>, dim3(c->sm_count * 4), dim3(INT_THREADS), (size_t)INT_SMEM_BYTES, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
+                   (const uint4*)c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }

@@ -100,7 +100,7 @@ extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S,
     HkfDeviceState st;
     memset(&st, 0, sizeof(st));
     const unsigned capacity = 4u * (unsigned)R * (unsigned)(R / 4) * div_up((unsigned)R, 128);
-    std::vector<uint2> items(capacity);
+    std::vector<uint4> items(capacity);
     const int ngroups = R * (R / INT_G);
     const dim3 g1(div_up((unsigned)ngroups, INT_GB)), b1(256);
     emu_launch(g1, b1, [&]() { k_integrate_items<false>(A, &st, items.data(), capacity, 0); });

@@ -1,6 +1,5 @@
 // icp_emu.cpp — host emulation of the ICP kernel of hybkinectfu_b200/csrc/icp.cu: k_icp in its wrapper-parity form (the
-// 27 sums of one iteration against the oracle) and in its fused form (sums + the warp-parallel 6x6 solve of
-// solve_warp.cuh + gates + pose update, iteration after iteration, against the loop `oracle sums -> host solve`).
+// 27 sums of one iteration against the oracle) and in its fused form (sums + the last block's 6x6 solve + gates + pose update, iteration after iteration, against the loop `oracle sums -> host solve`).
 // Test infrastructure; the product library never links this.
 #include "emu_shim.h"
 #include "emu_block.h"

@@ -1,6 +1,6 @@
 """Host emulation of the ICP kernel source (tests/emu): k_icp against the oracle's 27 sums at every pyramid level, and the
-FUSED form of the same kernel - sums, the warp-parallel 6x6 Cholesky solve and LU determinant of csrc/solve_warp.cuh, the
-gates and the pose update, one launch per iteration - against the reference loop `oracle sums -> host solve`
+FUSED form of the same kernel - sums, the last block's 6x6 Cholesky solve and LU determinant, the gates and the pose
+update spread over two warps, one launch per iteration - against the reference loop `oracle sums -> host solve`
 (hkf_solver.h on the CPU), bit for bit, failure paths included."""
 import ctypes as C
 import os
@@ -101,7 +101,7 @@ def _fused(scene, level, iters, angle_shake, maps):
 
 @pytest.mark.parametrize("level,iters", [(2, 10), (1, 5), (0, 2)])
 def test_fused_kernel_equals_the_iteration_loop(scene, level, iters):
-    """the last block's warp-parallel solve (rows on lanes, shuffles) gives the bits of the single-thread hkf_solver.h"""
+    """the last block's solve / gates / commit spread over its warps give the bits of the host-side hkf_solver.h loop"""
     cfg = scene["cfg"]
     maps = [scene[k][level] for k in ("NV", "NN", "MV", "MN")]
     c0, s0, st0 = _reference_loop(scene, level, iters, cfg.icp_angle_shake, maps)
