@@ -143,8 +143,8 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     // solver partials: one slot per 16x16 pixel block of level 0 (the reference's gbuf geometry,
     // src/cuda/CudaDeviceDataMan.h:43)
     c->max_blocks = div_up(c->cols[0], 16) * div_up(c->rows[0], 16);
-    // (the ICP kernel stores [27][256] leaf-pair sums, the SDF kernel [27][tiles] tile sums)
-    CREATE_CUDA(cudaMalloc(&c->partials, (size_t)HKF_SUMS * (c->max_blocks > 256 ? c->max_blocks : 256) * sizeof(float)));
+    // (the ICP kernels store [27][256] leaf-pair sums - k_icp_frame two such buffers -, the SDF kernel [27][tiles] tile sums)
+    CREATE_CUDA(cudaMalloc(&c->partials, (size_t)HKF_SUMS * (c->max_blocks > 512 ? c->max_blocks : 512) * sizeof(float)));
 
     unsigned R = p->volume_resolution;
     unsigned z0 = p->slab_z0, z1 = p->slab_z1;

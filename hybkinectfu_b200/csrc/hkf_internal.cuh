@@ -48,7 +48,7 @@ struct HkfDeviceState {
     int   frame_valid;       // 0 until the first frame has been integrated
     unsigned dmax_bits;      // max valid truncated depth of the current frame (float bits)
     unsigned ticket;         // last-block-done counter for the solver kernels
-    unsigned gen;            // (spare)
+    unsigned gen;            // arrival counter of k_icp_frame (monotonic within a frame, cleared when tracking begins)
     unsigned comp_go;        // raycast compositing: epoch that block 0 has released to the other blocks
     unsigned mc_count;       // marching-cubes triangle counter
     unsigned mc_ncand;       // marching-cubes candidate-cell counter
@@ -124,6 +124,7 @@ struct hkf_ctx {
     // solver scratch: [27][nblocks] partials for the largest level
     float* partials = nullptr;
     unsigned max_blocks = 0;
+    bool icp_coop = true;              // k_icp_frame: cooperative launch attribute accepted (cleared on the first refusal)
     // volume slab
     float2* vol = nullptr;
     uint4* int_items = nullptr;        // integration work items (integrate.cu: make_free_item / make_general_item)

@@ -225,7 +225,7 @@ __global__ void k_pyramids_fused(const float4* __restrict__ v0, const float4* __
     if (track_begin != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0) {
         HkfDeviceState* st = track_begin;
         if (threadIdx.x < 16) { st->cur[threadIdx.x] = st->pose[threadIdx.x]; st->last_inv[threadIdx.x] = st->pose_inv[threadIdx.x]; }
-        if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->sdf_done = 0; }
+        if (threadIdx.x == 0) { st->track_status = HKF_TRACK_OK; st->ticket = 0; st->gen = 0; st->sdf_done = 0; }
     }
     unsigned X = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned Y = blockIdx.y * blockDim.y + threadIdx.y;
