@@ -51,7 +51,8 @@ class RayCasterParams(C.Structure):
 class InitParams(C.Structure):
     _fields_ = [("depth_camera", CameraParams), ("pyramid_levels", C.c_uint32), ("volume_resolution", C.c_uint32),
                 ("volume_size", C.c_float), ("weight_max", C.c_float), ("max_triangles", C.c_uint32),
-                ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("slab_halo", C.c_uint32)]
+                ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("slab_halo", C.c_uint32),
+                ("use_color", C.c_uint32), ("rgb_camera", CameraParams)]
 
 
 class FrameParams(C.Structure):
@@ -59,12 +60,13 @@ class FrameParams(C.Structure):
                 ("integrate", IntegrateParams), ("raycast", RayCasterParams),
                 ("icp_dist_thres", C.c_float), ("icp_norm_sin_thres", C.c_float), ("icp_dist_shake", C.c_float),
                 ("icp_angle_shake", C.c_float), ("sdf_max_iter", C.c_uint32), ("sdf_dist_shake", C.c_float),
-                ("sdf_angle_shake", C.c_float)]
+                ("sdf_angle_shake", C.c_float), ("use_color", C.c_uint32), ("color_angle_weight", C.c_uint32)]
 
 
 # enum HkfBuffer
 BUF_RAW_DEPTH, BUF_TRUNC_DEPTH, BUF_FILTERED_DEPTH, BUF_NEW_VERTICES, BUF_NEW_NORMALS, BUF_MODEL_VERTICES, \
-    BUF_MODEL_NORMALS, BUF_VOLUME, BUF_SOLVER_SUMS, BUF_TRIANGLES, BUF_POSE, BUF_RAYCAST_KEYS = range(12)
+    BUF_MODEL_NORMALS, BUF_VOLUME, BUF_SOLVER_SUMS, BUF_TRIANGLES, BUF_POSE, BUF_RAYCAST_KEYS, BUF_RAW_RGB, \
+    BUF_RAYCAST_RGB, BUF_VOLUME_COLOR = range(15)
 TRACK_OK, TRACK_SINGULAR, TRACK_SHAKE = 0, 1, 2
 
 # every symbol include/hkf.h declares (checked by tests/test_abi.py against the header text)
@@ -78,6 +80,7 @@ EXPORTS = [
     "hkf_set_pose", "hkf_icp_track", "hkf_sdf_track", "hkf_integrate_tracked", "hkf_raycast_tracked",
     "hkf_frame_result", "hkf_count_integrate_updates", "hkf_shard_unique_id", "hkf_shard_init",
     "hkf_shard_composite_raycast", "hkf_shard_ipc_handles", "hkf_shard_connect", "hkf_preprocess_next", "hkf_swap_frame",
+    "hkf_upload_color",
 ]
 
 _lib = None
@@ -111,6 +114,7 @@ def load() -> C.CDLL:
     lib.hkf_launch_count.argtypes = [P]
     lib.hkf_launch_count.restype = C.c_uint64
     lib.hkf_upload_depth_mm.argtypes = [P, C.c_void_p, C.c_int]
+    lib.hkf_upload_color.argtypes = [P, C.c_void_p, C.c_int]
     lib.hkf_trunc_depth.argtypes = [P, C.c_float, C.c_float]
     lib.hkf_bilateral_filter_depth.argtypes = [P, C.c_float, C.c_float]
     lib.hkf_calculate_new_vertices.argtypes = [P, C.POINTER(CameraParams)]
@@ -175,6 +179,8 @@ class Config:
     slab_z0: int = 0
     slab_z1: int = 0
     slab_halo: int = 0
+    use_color: int = 0              # _switch_params.useRGBData (the rgb camera = the depth camera, as in config.ini)
+    color_angle_weight: int = 0     # _switch_params.colorAngleWeight
 
     @property
     def ray_increment(self) -> float:
@@ -186,13 +192,13 @@ class Config:
 
     def init_params(self) -> InitParams:
         return InitParams(self.camera(), self.pyramid_levels, self.resolution, self.volume_size, self.weight_max,
-                          self.max_triangles, self.slab_z0, self.slab_z1, self.slab_halo)
+                          self.max_triangles, self.slab_z0, self.slab_z1, self.slab_halo, self.use_color, self.camera())
 
     def frame_params(self) -> FrameParams:
         return FrameParams(self.trunc_min, self.trunc_max, self.sigma_pixel, self.sigma_depth,
                            IntegrateParams(self.sdf_trunc, self.max_integrate_dist), RayCasterParams(self.ray_increment),
                            self.icp_dist_thres, self.icp_norm_sin_thres, self.icp_dist_shake, self.icp_angle_shake,
-                           self.sdf_max_iter, self.sdf_dist_shake, self.sdf_angle_shake)
+                           self.sdf_max_iter, self.sdf_dist_shake, self.sdf_angle_shake, self.use_color, self.color_angle_weight)
 
     def level_shape(self, level: int):
         return self.rows >> level, self.cols >> level
@@ -263,6 +269,11 @@ class Context:
             return raw.view(np.float32).reshape(-1, 3, 6)
         if buf == BUF_RAYCAST_KEYS:
             return raw.view(np.uint64).reshape(self.cfg.rows, self.cfg.cols)
+        if buf in (BUF_RAW_RGB, BUF_RAYCAST_RGB):
+            return raw.reshape(self.cfg.rows, self.cfg.cols, 3)
+        if buf == BUF_VOLUME_COLOR:
+            R = self.cfg.resolution
+            return raw.reshape(-1, R, R, 4)
         return raw.view(np.float32)
 
     def upload(self, buf: int, arr: np.ndarray, level: int = 0):
@@ -284,6 +295,12 @@ class Context:
     def upload_depth_mm(self, mm: np.ndarray):
         a = np.ascontiguousarray(mm, dtype=np.uint16)
         self._ck(self.lib.hkf_upload_depth_mm(self._h, a.ctypes.data, 0), "hkf_upload_depth_mm")
+        self.sync()      # `a` may be a temporary
+
+    def upload_color(self, bgr: np.ndarray):
+        a = np.ascontiguousarray(bgr, dtype=np.uint8)
+        assert a.shape == (self.cfg.rows, self.cfg.cols, 3)
+        self._ck(self.lib.hkf_upload_color(self._h, a.ctypes.data, 0), "hkf_upload_color")
         self.sync()      # `a` may be a temporary
 
     def trunc_depth(self):
@@ -325,7 +342,8 @@ class Context:
         cam = self.cfg.camera()
         ip = IntegrateParams(self.cfg.sdf_trunc, self.cfg.max_integrate_dist)
         m = Mat44.from_np(pose)
-        self._ck(self.lib.hkf_integrate_volume(self._h, 0, 0, C.byref(m), C.byref(ip), C.byref(cam), C.byref(cam)), "hkf_integrate_volume")
+        self._ck(self.lib.hkf_integrate_volume(self._h, self.cfg.use_color, self.cfg.color_angle_weight if self.cfg.use_color else 0,
+                                               C.byref(m), C.byref(ip), C.byref(cam), C.byref(cam)), "hkf_integrate_volume")
 
     def count_updates(self, pose) -> int:
         cam = self.cfg.camera()
@@ -339,12 +357,12 @@ class Context:
         cam = self.cfg.camera()
         rp = RayCasterParams(self.cfg.ray_increment)
         m = Mat44.from_np(pose)
-        self._ck(self.lib.hkf_raycasting_volume(self._h, 0, C.byref(m), C.byref(rp), C.byref(cam), self.cfg.trunc_min, self.cfg.trunc_max), "hkf_raycasting_volume")
+        self._ck(self.lib.hkf_raycasting_volume(self._h, self.cfg.use_color, C.byref(m), C.byref(rp), C.byref(cam), self.cfg.trunc_min, self.cfg.trunc_max), "hkf_raycasting_volume")
 
     def marching_cubes(self) -> int:
         # MeshGeneratorMarchingcube::generateMesh threshold 300*S/R (src/MeshGeneratorMarchingcube.cpp:26-27)
         thr = float(np.float32(300) * np.float32(self.cfg.volume_size) / np.float32(self.cfg.resolution))
-        self._ck(self.lib.hkf_marchingcube(self._h, 0, thr), "hkf_marchingcube")
+        self._ck(self.lib.hkf_marchingcube(self._h, self.cfg.use_color, thr), "hkf_marchingcube")
         n = C.c_uint(0)
         self._ck(self.lib.hkf_triangle_count(self._h, C.byref(n)), "hkf_triangle_count")
         return int(n.value)

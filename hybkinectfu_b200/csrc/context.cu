@@ -68,6 +68,7 @@ static void free_all(hkf_ctx* c)
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->back.new_v[l]); cudaFree(c->back.new_n[l]); }
     cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
+    cudaFree(c->color); cudaFree(c->raw_rgb); cudaFree(c->raycast_rgb);
     cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->depth_mm_pinned) cudaFreeHost(c->depth_mm_pinned);
@@ -156,6 +157,17 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * R * R;
     CREATE_CUDA(cudaMalloc(&c->vol, nvox * sizeof(float2)));
     CREATE_CUDA(cudaMemset(c->vol, 0, nvox * sizeof(float2)));
+    if (p->use_color) {
+        if (!(c->z_lo == 0 && c->z_hi == R)) { g_create_err = "use_color is not available with z-slabs"; free_all(c); delete c; return HKF_ERR_ARG; }
+        if (p->rgb_camera.cols == 0 || p->rgb_camera.rows == 0) { g_create_err = "use_color needs an rgb camera size"; free_all(c); delete c; return HKF_ERR_ARG; }
+        const size_t nrgb = (size_t)p->rgb_camera.cols * p->rgb_camera.rows * 3;
+        CREATE_CUDA(cudaMalloc(&c->color, nvox * sizeof(uchar4)));
+        CREATE_CUDA(cudaMemset(c->color, 0, nvox * sizeof(uchar4)));
+        CREATE_CUDA(cudaMalloc(&c->raw_rgb, nrgb));
+        CREATE_CUDA(cudaMemset(c->raw_rgb, 0, nrgb));
+        CREATE_CUDA(cudaMalloc(&c->raycast_rgb, n0 * 3));
+        CREATE_CUDA(cudaMemset(c->raycast_rgb, 0, n0 * 3));
+    }
     // at most four work items per 4 x 128 voxel brick: one per general chunk, or one for its free chunks (integrate.cu)
     c->int_capacity = 4u * (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
     CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint4)));
@@ -195,6 +207,7 @@ extern "C" int hkf_reset_volume(hkf_ctx* c)
     if (!c) return HKF_ERR_ARG;
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution;
     HKF_CUDA(c, cudaMemsetAsync(c->vol, 0, nvox * sizeof(float2), c->stream));
+    if (c->color) HKF_CUDA(c, cudaMemsetAsync(c->color, 0, nvox * sizeof(uchar4), c->stream));
     HKF_CUDA(c, cudaMemsetAsync(c->st, 0, sizeof(HkfDeviceState), c->stream));
     for (int l = 0; l < c->levels; ++l) {
         size_t nb = (size_t)c->cols[l] * c->rows[l] * sizeof(float4);
@@ -223,6 +236,9 @@ static void* buf_ptr(hkf_ctx* c, int buffer, unsigned level, size_t* nbytes)
     case HKF_BUF_SOLVER_SUMS: *nbytes = HKF_SUMS * sizeof(float); return c->st->sums;
     case HKF_BUF_POSE: *nbytes = 16 * sizeof(float); return c->st->pose;
     case HKF_BUF_RAYCAST_KEYS: *nbytes = n0 * sizeof(unsigned long long); return c->ray_keys;
+    case HKF_BUF_RAW_RGB: if (!c->raw_rgb) return nullptr; *nbytes = (size_t)c->ip.rgb_camera.cols * c->ip.rgb_camera.rows * 3; return c->raw_rgb;
+    case HKF_BUF_RAYCAST_RGB: if (!c->raycast_rgb) return nullptr; *nbytes = n0 * 3; return c->raycast_rgb;
+    case HKF_BUF_VOLUME_COLOR: if (!c->color) return nullptr; *nbytes = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution * sizeof(uchar4); return c->color;
 #ifdef HKF_ICP_STAMPS
     case 100: *nbytes = sizeof(c->st->stamps); return c->st->stamps;      // profiling build only
 #endif
@@ -298,6 +314,15 @@ extern "C" int hkf_set_pose(hkf_ctx* c, const HkfMat44* pose)
     hkf_mat44_inverse(pose->m, p.inv);      // host, float cofactors: Mat44::getInverse (src/cuda/Mat.h:319-444)
     k_set_pose<<<1, 32, 0, c->stream>>>(c->st, p);
     HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+extern "C" int hkf_upload_color(hkf_ctx* c, const uint8_t* rgb3, int is_device)
+{
+    if (!c || !rgb3) return HKF_ERR_ARG;
+    if (!c->raw_rgb) { c->err = "context was created without use_color"; return HKF_ERR_STATE; }
+    const size_t nb = (size_t)c->ip.rgb_camera.cols * c->ip.rgb_camera.rows * 3;
+    HKF_CUDA(c, cudaMemcpyAsync(c->raw_rgb, rgb3, nb, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     return HKF_OK;
 }
 

@@ -127,10 +127,14 @@ struct hkf_ctx {
     bool icp_coop = true;              // k_icp_frame: cooperative launch attribute accepted (cleared on the first refusal)
     // volume slab
     float2* vol = nullptr;
+    // colour path (use_color): voxel colours as a plane of their own, the frame's colour image, the raycast colour map
+    uchar4* color = nullptr;
+    unsigned char* raw_rgb = nullptr;      // uchar3 [rgb rows][rgb cols]
+    unsigned char* raycast_rgb = nullptr;  // uchar3 [rows][cols]
     uint4* int_items = nullptr;        // integration work items (integrate.cu: make_free_item / make_general_item)
     unsigned int_capacity = 0;
     int int_parity = 0;
-    bool int_attr_set[2][2]{};         // cudaFuncSetAttribute done for k_integrate<FROM_STATE, COUNT_ONLY> on this context's device
+    bool int_attr_set[3][2]{};         // cudaFuncSetAttribute done for k_integrate<FROM_STATE, {plain, COUNT_ONLY, COLOR}> on this context's device
     int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes
     unsigned own_z0 = 0, own_z1 = 0;   // owned planes

@@ -63,6 +63,16 @@ struct IntegrateArgs {
     DepthBounds B;      // depth extrema of this frame per pixel tile (hkf_internal.cuh)
 };
 
+// colour integration (has_color): the frame's colour image, the new frame's level-0 normals (angle weighting), the
+// voxel colour plane
+struct IntegrateColor {
+    uchar4* color_vol;
+    const unsigned char* rgb;       // uchar3 [rgb_rows][rgb_cols]
+    const float4* normals;
+    int rgb_cols, rgb_rows;
+    int angled;
+};
+
 #define INT_G 4                        // voxel rows (consecutive y, same z) per work item
 #define INT_NC 4                       // 32-voxel chunks per row of a work item: an item is a 4 x 128 voxel brick
 #define INT_SEG (32 * INT_NC)
@@ -176,7 +186,8 @@ __device__ __forceinline__ uint4 make_general_item(const IntegrateArgs& A, int y
 // tile row): finer tiles = tighter depth extrema.  Measured on the bench scene: 19.0 M general voxel slots with 3
 // instead of 21.7 M with 1, integration 144.8 -> 142.5 us (profiles/r2_experimental.log).
 #define INT_SPAN 3
-template <bool FROM_STATE>
+// NOFREE (colour integration): every updated voxel needs its colour pixel, so the projection-free class is not used.
+template <bool FROM_STATE, bool NOFREE>
 __global__ void __launch_bounds__(256, 5)
 k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __restrict__ items, unsigned capacity, int parity)
 {
@@ -264,7 +275,7 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __res
                         const float dmx = __uint_as_float(mx), dmn = __uint_as_float(~mninv);   // NaN if no tile was read
                         const bool interior = u0 >= 1.0f && u1 <= (float)(A.cols - 2) && v0 >= 1.0f && v1 <= (float)(A.rows - 2);
                         if (zn >= dmx + thr_dead || dmn >= A.maxdist) cls = 0;     // behind everything / nothing integrable there
-                        else if (interior && dmn > 0.f && dmx < A.maxdist && dmn - zf >= thr_free) cls = 2;
+                        else if (!NOFREE && interior && dmn > 0.f && dmx < A.maxdist && dmn - zf >= thr_free) cls = 2;
                     }
                 }
                 if (cls == 1) gm |= 1u << c;
@@ -357,10 +368,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // every warp load/store instruction moves 256 contiguous bytes.  Per warp: the rows of its next free brick are always
 // in flight as bulk copies; between two bricks the warp projects its share of general chunks (in proportion to the
 // lengths of the two lists, so that both run out together).
-template <bool FROM_STATE, bool COUNT_ONLY>
+//
+// COLOR (has_color; pass 1 ran with NOFREE, so the free list is empty): a voxel is also dropped when its colour pixel
+//   cu = (int)(X*525/Z + 320), cv = (int)(Y*525/Z + 240)     (mul, div.rn, add, cvt.rzi: integrateVolume.cu:56-57, the
+//                                                              hard-coded intrinsics are the reference's)
+// is outside [1, rgb_cols-2] x [1, rgb_rows-2]; an updated voxel blends its colour (tsdfVolume.h:57-74 as compiled)
+//   wc = 2, or 2 * fminf(|n.z| / 0.75, 1) with angle weighting (n = the new frame's normal at the depth pixel)
+//   c' = (uchar) trunc(fminf(fma(wc, c_pixel, w * c_old) / (wc + w), 255))        (w = the voxel's OLD weight)
+template <bool FROM_STATE, bool COUNT_ONLY, bool COLOR>
 __global__ void __launch_bounds__(INT_THREADS, 4)
 k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict__ vol, HkfDeviceState* __restrict__ st,
-            const uint4* __restrict__ items, unsigned capacity, int parity)
+            const uint4* __restrict__ items, unsigned capacity, int parity, IntegrateColor CA)
 {
     HKF_DYN_SMEM(unsigned long long, dyn);
     hkf_pdl_enter();
@@ -473,6 +491,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
             // reference's association is fma(wz, m_3, fma(wx, m_1, wy*m_2)) + m_4 per voxel, kept as is
             float Z[INT_G];
             int idx[INT_G];
+            int cidx[INT_G];                  // COLOR: index of the colour pixel, -1 = outside the rgb image
 #pragma unroll
             for (int r = 0; r < INT_G; ++r) {
                 const float wy = __fmul_rn(__fadd_rn((float)(y0 + r), 0.5f), cell);
@@ -496,6 +515,14 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                 }
                 in = in && ((unsigned)(iu - 1) < ulim) && ((unsigned)(iv - 1) < vlim);
                 idx[r] = in ? iv * cols + iu : -1;
+                if (COLOR) {
+                    cidx[r] = -1;
+                    if (in) {
+                        const int cu = __float2int_rz(__fadd_rn(__fdiv_rn(__fmul_rn(X, 525.0f), Z[r]), 320.0f));
+                        const int cv = __float2int_rz(__fadd_rn(__fdiv_rn(__fmul_rn(Y, 525.0f), Z[r]), 240.0f));
+                        if (!(cu >= CA.rgb_cols - 1 || cv >= CA.rgb_rows - 1 || cu < 1 || cv < 1)) cidx[r] = cv * CA.rgb_cols + cu;
+                    }
+                }
             }
             float d[INT_G];
 #pragma unroll
@@ -503,9 +530,29 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
 #pragma unroll
             for (int r = 0; r < INT_G; ++r) {
                 const float sdf = __fsub_rn(d[r], Z[r]);
-                const bool live = (d[r] != 0.f) && (d[r] < A.maxdist) && (sdf > ntrunc);
+                bool live = (d[r] != 0.f) && (d[r] < A.maxdist) && (sdf > ntrunc);
+                if (COLOR) live = live && cidx[r] >= 0;
                 if (COUNT_ONLY) local_count += live ? 1u : 0u;
-                else if (live) update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
+                else if (live) {
+                    update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
+                    if (COLOR) {
+                        float wc = 2.0f;
+                        if (CA.angled) {
+                            const float q = fminf(__fdiv_rn(fabsf(__ldg(&CA.normals[idx[r]].z)), 0.75f), 1.0f);
+                            wc = __fadd_rn(q, q);
+                        }
+                        uchar4* cp = CA.color_vol + ((size_t)cur.x * 4u + (unsigned)lane + (size_t)r * R);
+                        const uchar4 oc = *cp;
+                        const unsigned char* px = CA.rgb + (size_t)cidx[r] * 3;
+                        const float den = __fadd_rn(wc, old[r].y);
+                        uchar4 nc;
+                        nc.x = (unsigned char)__float2uint_rz(fminf(__fdiv_rn(__fmaf_rn(wc, (float)__ldg(px + 0), __fmul_rn(old[r].y, (float)oc.x)), den), 255.0f));
+                        nc.y = (unsigned char)__float2uint_rz(fminf(__fdiv_rn(__fmaf_rn(wc, (float)__ldg(px + 1), __fmul_rn(old[r].y, (float)oc.y)), den), 255.0f));
+                        nc.z = (unsigned char)__float2uint_rz(fminf(__fdiv_rn(__fmaf_rn(wc, (float)__ldg(px + 2), __fmul_rn(old[r].y, (float)oc.z)), den), 255.0f));
+                        nc.w = 0;
+                        *cp = nc;
+                    }
+                }
             }
             // a free brick whenever the general list has advanced by its share (my_free : my_gen)
             credit += my_free;
@@ -537,23 +584,33 @@ static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* 
 }
 
 #ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
+static bool fill_color(hkf_ctx* c, const HkfCameraParams* rgb_cam, int angled, IntegrateColor* CA)
+{
+    if (!c->color || !c->raw_rgb) { c->err = "context was created without use_color"; return false; }
+    if (rgb_cam->cols != c->ip.rgb_camera.cols || rgb_cam->rows != c->ip.rgb_camera.rows) { c->err = "rgb camera size mismatch"; return false; }
+    CA->color_vol = c->color; CA->rgb = c->raw_rgb; CA->normals = c->new_n[0];
+    CA->rgb_cols = (int)rgb_cam->cols; CA->rgb_rows = (int)rgb_cam->rows; CA->angled = angled ? 1 : 0;
+    return true;
+}
+
 // both passes, on the context's stream
-template <bool FROM_STATE, bool COUNT_ONLY>
-static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
+template <bool FROM_STATE, bool COUNT_ONLY, bool COLOR>
+static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A, const IntegrateColor& CA = IntegrateColor{})
 {
     const int ngroups = (A.z_hi - A.z_lo) * (A.R / INT_G);
     const int parity = c->int_parity;
     c->int_parity ^= 1;
     const dim3 g1(div_up(ngroups, INT_GB)), b1(256);
-    hkf_launch_pdl(k_integrate_items<FROM_STATE>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
+    hkf_launch_pdl(k_integrate_items<FROM_STATE, COLOR>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
     HKF_LAUNCH_CHECK(c);
     // function attributes are per device: set once per context (dynamic shared memory above the 48 KB default)
-    if (!c->int_attr_set[COUNT_ONLY ? 1 : 0][FROM_STATE ? 1 : 0]) {
-        HKF_CUDA(c, cudaFuncSetAttribute(k_integrate<FROM_STATE, COUNT_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INT_SMEM_BYTES));
-        c->int_attr_set[COUNT_ONLY ? 1 : 0][FROM_STATE ? 1 : 0] = true;
+    const int variant = COLOR ? 2 : COUNT_ONLY ? 1 : 0;
+    if (!c->int_attr_set[variant][FROM_STATE ? 1 : 0]) {
+        HKF_CUDA(c, cudaFuncSetAttribute(k_integrate<FROM_STATE, COUNT_ONLY, COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INT_SMEM_BYTES));
+        c->int_attr_set[variant][FROM_STATE ? 1 : 0] = true;
     }
-    hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY>, dim3(c->sm_count * 4), dim3(INT_THREADS), (size_t)INT_SMEM_BYTES, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
-                   (const uint4*)c->int_items, c->int_capacity, parity);
+    hkf_launch_pdl(k_integrate<FROM_STATE, COUNT_ONLY, COLOR>, dim3(c->sm_count * 4), dim3(INT_THREADS), (size_t)INT_SMEM_BYTES, c->stream, A, (const float*)c->trunc_depth, c->vol, c->st,
+                   (const uint4*)c->int_items, c->int_capacity, parity, CA);
     HKF_LAUNCH_CHECK(c);
     return HKF_OK;
 }
@@ -562,21 +619,30 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A)
 extern "C" int hkf_integrate_volume(hkf_ctx* c, int has_color, int use_angle_weight_color, const HkfMat44* transform,
                                     const HkfIntegrateParams* ip, const HkfCameraParams* cam, const HkfCameraParams* rgb_cam)
 {
-    (void)rgb_cam;
     if (!c || !transform || !ip || !cam) return HKF_ERR_ARG;
-    if (has_color || use_angle_weight_color) { c->err = "colour integration is out of scope (use_color=0)"; return HKF_ERR_ARG; }
     if (cam->cols != c->cols[0] || cam->rows != c->rows[0]) { c->err = "camera size mismatch"; return HKF_ERR_ARG; }
     float inv[16];
     hkf_mat44_inverse(transform->m, inv);      // host, float cofactors: cudaIntegrateVolume line 84
     IntegrateArgs A; fill_args(c, inv, ip, cam, &A);
-    return launch_integrate<false, false>(c, A);
+    if (has_color) {
+        IntegrateColor CA;
+        if (!rgb_cam) return HKF_ERR_ARG;
+        if (!fill_color(c, rgb_cam, use_angle_weight_color, &CA)) return HKF_ERR_STATE;
+        return launch_integrate<false, false, true>(c, A, CA);
+    }
+    return launch_integrate<false, false, false>(c, A);
 }
 
 extern "C" int hkf_integrate_tracked(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
     IntegrateArgs A; fill_args(c, nullptr, &fp->integrate, &c->ip.depth_camera, &A);
-    return launch_integrate<true, false>(c, A);
+    if (fp->use_color) {
+        IntegrateColor CA;
+        if (!fill_color(c, &c->ip.rgb_camera, (int)fp->color_angle_weight, &CA)) return HKF_ERR_STATE;
+        return launch_integrate<true, false, true>(c, A, CA);
+    }
+    return launch_integrate<true, false, false>(c, A);
 }
 
 extern "C" int hkf_count_integrate_updates(hkf_ctx* c, const HkfMat44* transform, const HkfIntegrateParams* ip,
@@ -589,7 +655,7 @@ extern "C" int hkf_count_integrate_updates(hkf_ctx* c, const HkfMat44* transform
     // count over OWNED planes only
     A.z_lo = (int)c->own_z0; A.z_hi = (int)c->own_z1;
     HKF_CUDA(c, cudaMemsetAsync(&c->st->upd_count, 0, sizeof(unsigned long long), c->stream));
-    int rc = launch_integrate<false, true>(c, A);
+    int rc = launch_integrate<false, true, false>(c, A);
     if (rc != HKF_OK) return rc;
     HKF_CUDA(c, cudaMemcpyAsync(n_upd, &c->st->upd_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     HKF_CUDA(c, cudaStreamSynchronize(c->stream));

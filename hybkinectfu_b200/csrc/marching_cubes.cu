@@ -29,6 +29,7 @@ struct McArgs {
     float threshold;
     HkfTriangle* tris;
     unsigned max_tris;
+    const uchar4* color;     // has_color: the voxel colour plane (corner colours = interpolateColor at the lattice corners)
 };
 
 __device__ __forceinline__ void mc_vertex(const float* p1, const float* p2, float d1, float d2, float* out)
@@ -40,6 +41,25 @@ __device__ __forceinline__ void mc_vertex(const float* p1, const float* p2, floa
     const float mu = __fdiv_rn(m1, __fsub_rn(d2, d1));
 #pragma unroll
     for (int k = 0; k < 3; ++k) out[k] = __fmaf_rn(__fsub_rn(p2[k], p1[k]), mu, p1[k]);
+}
+
+// the colour half of vertexInterp (marchingcube.cu:5-26 as compiled): c / 255 as a multiplication by (float)(1.0/255) at a
+// snapped end point, otherwise fma((float)(c2 - c1), mu, (float)c1) / 255 with an IEEE division
+__device__ __forceinline__ void mc_vertex_color(unsigned c1, unsigned c2, float d1, float d2, float* out)
+{
+    const float m1 = __fsub_rn(0.0f, d1);
+    const float k = 0.0039215688593685626984f;
+    const bool snap1 = fabsf(m1) < 0.00001f;
+    const bool snap2 = !snap1 && fabsf(__fsub_rn(0.0f, d2)) < 0.00001f;
+    const bool flat = !snap1 && !snap2 && fabsf(__fsub_rn(d1, d2)) < 0.00001f;
+    const float mu = __fdiv_rn(m1, __fsub_rn(d2, d1));
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const int a = (int)((c1 >> (8 * ch)) & 0xffu), b = (int)((c2 >> (8 * ch)) & 0xffu);
+        if (snap1 || flat) out[ch] = __fmul_rn((float)a, k);
+        else if (snap2) out[ch] = __fmul_rn((float)b, k);
+        else out[ch] = __fdiv_rn(__fmaf_rn((float)(b - a), mu, (float)a), 255.0f);
+    }
 }
 
 // Cheap rejection of cell (x, y, z) on its raw 3x3x3 neighbourhood (the union of the eight corners' 2x2x2 voxel sets),
@@ -107,7 +127,7 @@ k_mc_candidates(McArgs A, unsigned* __restrict__ cand, unsigned cap, unsigned* _
 }
 
 // Pass B (or the whole extraction when CANDIDATES is false): the reference's cell evaluation.
-template <bool SLAB, bool CANDIDATES>
+template <bool SLAB, bool CANDIDATES, bool COLOR = false>
 __global__ void __launch_bounds__(256)
 k_marching_cubes(McArgs A, unsigned* __restrict__ counter, const unsigned* __restrict__ cand, const unsigned* __restrict__ ncand)
 {
@@ -201,6 +221,12 @@ k_marching_cubes(McArgs A, unsigned* __restrict__ counter, const unsigned* __res
             const int ea[12] = { 2, 3, 1, 0, 6, 7, 5, 4, 2, 3, 1, 0 };
             const int eb[12] = { 3, 1, 0, 2, 7, 5, 4, 6, 6, 7, 5, 4 };
             unsigned slot = wbase + (unsigned)(incl - ntri);
+            unsigned col[8];
+            if (COLOR) {
+                // the corner interpolations succeeded for the SDF, so they succeed for the colour (same eight weight tests)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) col[c] = vol_interp_color(V, A.color, pos[c][0], pos[c][1], pos[c][2]);
+            }
 #pragma unroll 1
             for (int k = 0; k < 16; k += 3) {
                 const unsigned e0 = (unsigned)((packed >> (4 * k)) & 0xF);
@@ -211,9 +237,15 @@ k_marching_cubes(McArgs A, unsigned* __restrict__ counter, const unsigned* __res
                     mc_vertex(pos[ea[e0]], pos[eb[e0]], dist[ea[e0]], dist[eb[e0]], t.v0.pos);
                     mc_vertex(pos[ea[e1]], pos[eb[e1]], dist[ea[e1]], dist[eb[e1]], t.v1.pos);
                     mc_vertex(pos[ea[e2]], pos[eb[e2]], dist[ea[e2]], dist[eb[e2]], t.v2.pos);
-                    t.v0.color[0] = t.v0.color[1] = t.v0.color[2] = 0.f;
-                    t.v1.color[0] = t.v1.color[1] = t.v1.color[2] = 0.f;
-                    t.v2.color[0] = t.v2.color[1] = t.v2.color[2] = 0.f;
+                    if (COLOR) {
+                        mc_vertex_color(col[ea[e0]], col[eb[e0]], dist[ea[e0]], dist[eb[e0]], t.v0.color);
+                        mc_vertex_color(col[ea[e1]], col[eb[e1]], dist[ea[e1]], dist[eb[e1]], t.v1.color);
+                        mc_vertex_color(col[ea[e2]], col[eb[e2]], dist[ea[e2]], dist[eb[e2]], t.v2.color);
+                    } else {
+                        t.v0.color[0] = t.v0.color[1] = t.v0.color[2] = 0.f;
+                        t.v1.color[0] = t.v1.color[1] = t.v1.color[2] = 0.f;
+                        t.v2.color[0] = t.v2.color[1] = t.v2.color[2] = 0.f;
+                    }
                     A.tris[slot] = t;
                 }
                 ++slot;
@@ -225,7 +257,7 @@ k_marching_cubes(McArgs A, unsigned* __restrict__ counter, const unsigned* __res
 extern "C" int hkf_marchingcube(hkf_ctx* c, int has_color, float threshold)
 {
     if (!c) return HKF_ERR_ARG;
-    if (has_color) { c->err = "colour marching cubes is out of scope (use_color=0)"; return HKF_ERR_ARG; }
+    if (has_color && !c->color) { c->err = "context was created without use_color"; return HKF_ERR_STATE; }
     if (!c->tris) { c->err = "max_triangles is 0"; return HKF_ERR_STATE; }
     HKF_CUDA(c, cudaSetDevice(c->device));
     if (!g_tables_uploaded[c->device & 63]) {
@@ -237,6 +269,7 @@ extern "C" int hkf_marchingcube(hkf_ctx* c, int has_color, float threshold)
     A.V = make_volview(c);
     A.z0 = (int)c->own_z0; A.z1 = (int)c->own_z1;
     A.threshold = threshold; A.tris = c->tris; A.max_tris = c->ip.max_triangles;
+    A.color = has_color ? c->color : nullptr;
     const bool slab = !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution);
     const int grid = c->sm_count * 8;
     // candidate list: one entry per 16 cells is far more than the shell around a surface needs; if a volume ever
@@ -246,6 +279,7 @@ extern "C" int hkf_marchingcube(hkf_ctx* c, int has_color, float threshold)
         // candidate ids are 32-bit cell numbers: a slab of more than 2^32 owned cells (R = 2048 on one context) takes the
         // single-pass kernel, which indexes by (row, x)
         if (slab) k_marching_cubes<true, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
+        else if (has_color) k_marching_cubes<false, false, true><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
         else k_marching_cubes<false, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
         HKF_LAUNCH_CHECK(c);
         return HKF_OK;
@@ -267,11 +301,13 @@ extern "C" int hkf_marchingcube(hkf_ctx* c, int has_color, float threshold)
         const int g2 = (int)div_up(c->st_host->mc_ncand, 256);
         if (g2 > 0) {
             if (slab) k_marching_cubes<true, true><<<g2, 256, 0, c->stream>>>(A, &c->st->mc_count, c->mc_cand, &c->st->mc_ncand);
+            else if (has_color) k_marching_cubes<false, true, true><<<g2, 256, 0, c->stream>>>(A, &c->st->mc_count, c->mc_cand, &c->st->mc_ncand);
             else k_marching_cubes<false, true><<<g2, 256, 0, c->stream>>>(A, &c->st->mc_count, c->mc_cand, &c->st->mc_ncand);
             HKF_LAUNCH_CHECK(c);
         }
     } else {
         if (slab) k_marching_cubes<true, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
+        else if (has_color) k_marching_cubes<false, false, true><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
         else k_marching_cubes<false, false><<<grid, 256, 0, c->stream>>>(A, &c->st->mc_count, nullptr, nullptr);
         HKF_LAUNCH_CHECK(c);
     }

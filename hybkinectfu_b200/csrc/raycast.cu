@@ -34,6 +34,10 @@ struct RaycastArgs {
     float pose[16];
     int own_z0, own_z1, rank;
     const ShardMailbox* mailbox; int nranks; unsigned epoch;   // peer-memory mode: epoch of this raycast
+    // has_color (raycastingVolume.cu:101-106): the voxel colour plane and raycast_rgb; nullptr = depth only.  The colour
+    // of a hit is interpolated at the refined vertex BEFORE the gradient is evaluated and is written whenever that
+    // interpolation succeeds, even if the gradient then fails and the pixel's vertex / normal stay zero.
+    const uchar4* color_vol; unsigned char* color_out;
 };
 
 // FAST: R is a power of two and the stored planes hold at most 2^32 voxels (the host checks both) - the cheaper
@@ -44,7 +48,8 @@ struct RaycastArgs {
 // and measured SLOWER on B200 - 120 us against 78 us for this kernel (profiles/r2_experimental.log): the flag lookups sit
 // in front of every sample load and lengthen the dependent chain of a march that is latency-bound, not traffic-bound.
 // It has been removed.
-template <bool FROM_STATE, bool SLAB, bool FAST>
+// COLOR: has_color (whole volumes only); a separate instantiation so that the depth-only kernels keep their registers.
+template <bool FROM_STATE, bool SLAB, bool FAST, bool COLOR = false>
 __global__ void __launch_bounds__(256)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
@@ -58,6 +63,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
     const size_t pix = (size_t)y * A.cols + x;
     float4 ov = make_float4(0.f, 0.f, 0.f, 0.f), on = ov;
     unsigned long long key = ~0ull;
+    if (COLOR) { A.color_out[pix * 3 + 0] = 0; A.color_out[pix * 3 + 1] = 0; A.color_out[pix * 3 + 2] = 0; }
 
     const float* P = FROM_STATE ? st->pose : A.pose;
     const float m11 = P[0], m12 = P[1], m13 = P[2], ox = P[3];
@@ -197,6 +203,12 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                         if (vol_interp_sdf<SLAB>(V, lx, ly, lz, ft) != 1) break;
                         const float alpha = __fsub_rn(tc, __fdiv_rn(__fmul_rn(A.inc, ftdt), __fsub_rn(ftdt, ft)));
                         wx = __fmaf_rn(dx, alpha, ox); wy = __fmaf_rn(dy, alpha, oy); wz = __fmaf_rn(dz, alpha, oz);
+                        if (COLOR) {
+                            const unsigned c3 = vol_interp_color(V, A.color_vol, wx, wy, wz);
+                            if (c3 != HKF_NO_COLOR) {
+                                A.color_out[pix * 3 + 0] = (unsigned char)c3; A.color_out[pix * 3 + 1] = (unsigned char)(c3 >> 8); A.color_out[pix * 3 + 2] = (unsigned char)(c3 >> 16);
+                            }
+                        }
                         // gradientForPoint(volume, last_world_pos, vertex)
                         const int hx = vol_w2v(V, lx), hy = vol_w2v(V, ly), hz = vol_w2v(V, lz);
                         if (hx <= 1 || hx >= R - 2) break;
@@ -243,6 +255,7 @@ static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParam
     if (pose) memcpy(A->pose, pose, 64); else memset(A->pose, 0, 64);
     A->own_z0 = (int)c->own_z0; A->own_z1 = (int)c->own_z1; A->rank = c->rank;
     A->mailbox = nullptr; A->nranks = c->nranks; A->epoch = 0;
+    A->color_vol = nullptr; A->color_out = nullptr;
     if (c->p2p) { A->mailbox = c->mailbox; A->epoch = ++c->shard_epoch; }
 }
 
@@ -257,14 +270,18 @@ extern "C" int hkf_raycasting_volume(hkf_ctx* c, int has_color, const HkfMat44* 
                                      const HkfCameraParams* cam, float near_plane, float far_plane)
 {
     if (!c || !transform || !rp || !cam) return HKF_ERR_ARG;
-    if (has_color) { c->err = "colour raycast is out of scope (use_color=0)"; return HKF_ERR_ARG; }
+    if (has_color && !c->color) { c->err = "context was created without use_color"; return HKF_ERR_STATE; }
     if (cam->cols != c->cols[0] || cam->rows != c->rows[0]) { c->err = "camera size mismatch"; return HKF_ERR_ARG; }
     RaycastArgs A; fill_ray_args(c, transform->m, rp, cam, near_plane, far_plane, &A);
+    if (has_color) { A.color_vol = c->color; A.color_out = c->raycast_rgb; }
     dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
     const bool fast = is_fast(c);
     if (is_slab(c)) {
         if (fast) k_raycast<false, true, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
         else k_raycast<false, true, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+    } else if (has_color) {
+        if (fast) k_raycast<false, false, true, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
+        else k_raycast<false, false, false, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
     } else {
         if (fast) k_raycast<false, false, true><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
         else k_raycast<false, false, false><<<g, b, 0, c->stream>>>(A, c->model_v[0], c->model_n[0], c->ray_keys, c->st);
@@ -277,12 +294,19 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
     RaycastArgs A; fill_ray_args(c, nullptr, &fp->raycast, &c->ip.depth_camera, fp->trunc_min, fp->trunc_max, &A);
+    if (fp->use_color) {
+        if (!c->color) { c->err = "context was created without use_color"; return HKF_ERR_STATE; }
+        A.color_vol = c->color; A.color_out = c->raycast_rgb;
+    }
     dim3 b(256), g(div_up(A.cols, 16), div_up(A.rows, 16));
     const HkfDeviceState* st = c->st;
     const bool fast = is_fast(c);
     if (is_slab(c)) {
         if (fast) hkf_launch_pdl(k_raycast<true, true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
         else hkf_launch_pdl(k_raycast<true, true, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
+    } else if (fp->use_color) {
+        if (fast) hkf_launch_pdl(k_raycast<true, false, true, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
+        else hkf_launch_pdl(k_raycast<true, false, false, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
     } else {
         if (fast) hkf_launch_pdl(k_raycast<true, false, true>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);
         else hkf_launch_pdl(k_raycast<true, false, false>, g, b, 0, c->stream, A, c->model_v[0], c->model_n[0], c->ray_keys, st);

@@ -83,4 +83,52 @@ __device__ __forceinline__ int vol_interp_sdf(const VolView& V, float px, float 
     dist = acc;
     return 1;
 }
+// tsdfvolume::interpolateColor (src/cuda/tsdfVolume.h:122-148) over the separate colour plane: the same cell, the same
+// eight observed-weight tests and the same term order as interpolateSDF, applied to the three colour bytes as floats;
+// each channel is truncated (cvt.rzi.u32.f32).  Returns c0 | c1 << 8 | c2 << 16, or HKF_NO_COLOR where the reference
+// returns false (whole volumes only).
+#define HKF_NO_COLOR 0xffffffffu
+__device__ __forceinline__ unsigned vol_interp_color(const VolView& V, const uchar4* __restrict__ color, float px, float py, float pz)
+{
+    int gx = vol_w2v(V, px), gy = vol_w2v(V, py), gz = vol_w2v(V, pz);
+    const int R = V.R;
+    if (gx <= 0 || gx >= R - 1) return HKF_NO_COLOR;
+    if (gy <= 0 || gy >= R - 1) return HKF_NO_COLOR;
+    if (gz <= 0 || gz >= R - 1) return HKF_NO_COLOR;
+    const float cell = V.cell;
+    const float vx = __fmul_rn(__fadd_rn((float)gx, 0.5f), cell);
+    const float vy = __fmul_rn(__fadd_rn((float)gy, 0.5f), cell);
+    const float vz = __fmul_rn(__fadd_rn((float)gz, 0.5f), cell);
+    gx = (px < vx) ? gx - 1 : gx;
+    gy = (py < vy) ? gy - 1 : gy;
+    gz = (pz < vz) ? gz - 1 : gz;
+    const float a = __fdiv_rn(__fmaf_rn(__fadd_rn((float)gx, 0.5f), -cell, px), cell);
+    const float b = __fdiv_rn(__fmaf_rn(__fadd_rn((float)gy, 0.5f), -cell, py), cell);
+    const float c = __fdiv_rn(__fmaf_rn(__fadd_rn((float)gz, 0.5f), -cell, pz), cell);
+    const size_t i0 = vol_index(V, gx, gy, gz);
+    const size_t sy = (size_t)R, sz = (size_t)R * R;
+    const size_t off[8] = { 0, sz, sy, sz + sy, 1, sz + 1, sy + 1, sz + sy + 1 };      // 000,001,010,011,100,101,110,111 (x y z)
+    uchar4 col[8];
+    bool seen = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { seen = seen && (__ldg(&V.vol[i0 + off[k]].y) != 0.f); col[k] = __ldg(color + i0 + off[k]); }
+    if (!seen) return HKF_NO_COLOR;
+    const float ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b), ic = __fsub_rn(1.0f, c);
+    unsigned packed = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (float)(ch == 0 ? col[k].x : ch == 1 ? col[k].y : col[k].z);
+        float acc = __fmaf_rn(ic, __fmul_rn(ib, __fmul_rn(ia, v[0])), __fmul_rn(c, __fmul_rn(ib, __fmul_rn(ia, v[1]))));
+        acc = __fmaf_rn(ic, __fmul_rn(b, __fmul_rn(ia, v[2])), acc);
+        acc = __fmaf_rn(c, __fmul_rn(b, __fmul_rn(ia, v[3])), acc);
+        acc = __fmaf_rn(ic, __fmul_rn(ib, __fmul_rn(a, v[4])), acc);
+        acc = __fmaf_rn(c, __fmul_rn(ib, __fmul_rn(a, v[5])), acc);
+        acc = __fmaf_rn(ic, __fmul_rn(b, __fmul_rn(a, v[6])), acc);
+        acc = __fmaf_rn(c, __fmul_rn(b, __fmul_rn(a, v[7])), acc);
+        packed |= (__float2uint_rz(acc) & 0xffu) << (8 * ch);
+    }
+    return packed;
+}
 #endif

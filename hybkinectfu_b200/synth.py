@@ -98,6 +98,55 @@ def render_depth_mm(pose: np.ndarray, cam: Camera, noise_sigma_mm: float = 0.0, 
     return mm.astype(np.uint16)
 
 
+# surface colours (B, G, R like the OpenCV frames of the reference, src/HybKinectfu.cpp:90-91): planes, then spheres
+SURFACE_BGR = ((90, 180, 200), (220, 160, 90), (120, 220, 120), (80, 80, 230), (60, 240, 240))
+
+
+def render_color(pose: np.ndarray, cam: Camera) -> np.ndarray:
+    """uint8 [rows][cols][3] colour image of the same analytic scene from the same camera (the reference registers
+    colour to depth): every surface has a base colour, darkened on a 0.1 m checkerboard of the hit point and shaded
+    with a smooth ramp along world x; pixels without a hit are black.  Deterministic double-precision NumPy."""
+    u = np.arange(cam.cols, dtype=np.float64)
+    v = np.arange(cam.rows, dtype=np.float64)
+    uu, vv = np.meshgrid(u, v)
+    dc = np.stack([(uu - cam.cx) / cam.fx, (vv - cam.cy) / cam.fy, np.ones_like(uu)], axis=-1)
+    R, o = pose[:3, :3], pose[:3, 3]
+    d = dc @ R.T
+    best = np.full(uu.shape, np.inf)
+    surf = np.full(uu.shape, -1, dtype=np.int64)
+    k = 0
+    for axis, off in PLANES:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = (off - o[axis]) / d[..., axis]
+        s = np.where((s > 1e-9) & np.isfinite(s), s, np.inf)
+        surf = np.where(s < best, k, surf)
+        best = np.minimum(best, s)
+        k += 1
+    for centre, rad in SPHERES:
+        oc = o - np.asarray(centre)
+        a = np.sum(d * d, axis=-1)
+        b = 2.0 * (d @ oc)
+        c = float(oc @ oc) - rad * rad
+        disc = b * b - 4 * a * c
+        with np.errstate(invalid="ignore"):
+            sq = np.sqrt(np.where(disc >= 0, disc, np.nan))
+            s1 = (-b - sq) / (2 * a)
+            s2 = (-b + sq) / (2 * a)
+        s = np.where(s1 > 1e-9, s1, s2)
+        s = np.where((disc >= 0) & (s > 1e-9), s, np.inf)
+        surf = np.where(s < best, k, surf)
+        best = np.minimum(best, s)
+        k += 1
+    hit = np.isfinite(best)
+    p = o + d * np.where(hit, best, 0.0)[..., None]
+    cell = np.floor(p / 0.1 + 1e-6).astype(np.int64)
+    check = ((cell[..., 0] + cell[..., 1] + cell[..., 2]) & 1).astype(np.float64)
+    shade = (1.0 - 0.4 * check) * (0.75 + 0.25 * np.clip(p[..., 0] / 2.0, 0.0, 1.0))
+    base = np.asarray(SURFACE_BGR, dtype=np.float64)[np.clip(surf, 0, len(SURFACE_BGR) - 1)]
+    img = np.where(hit[..., None], np.rint(base * shade[..., None]), 0.0)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
 def render_sequence(n: int, cam: Camera, phase: float = 0.0, noise_sigma_mm: float = 0.0):
     poses = trajectory(n, phase)
     rng = np.random.default_rng(0)

@@ -66,6 +66,13 @@ typedef struct HkfInitParams {
     /* z-slab: this context stores planes [slab_z0 - halo, slab_z1 + halo) ∩ [0,R) and owns
      * [slab_z0, slab_z1).  slab_z0 = slab_z1 = 0 means "the whole volume". */
     uint32_t slab_z0, slab_z1, slab_halo;
+    /* colour path (the reference's default mode, config.ini:2 use_color=1): a non-zero use_color allocates the voxel
+     * colour plane (uchar4 [z][y][x], kept apart from the packed {tsdf,weight} stream so that depth-only runs never
+     * touch it; the reference stores a uchar3 inside its 12-byte Voxel, src/cuda/tsdfVolume.h:14-19), raw_rgb
+     * (rgb_camera.cols x rgb_camera.rows, CudaDeviceDataMan.h:30) and raycast_rgb (depth camera size, :31).
+     * Not available together with z-slabs. */
+    uint32_t use_color;
+    HkfCameraParams rgb_camera;     /* _rgb_camera_params */
 } HkfInitParams;
 
 /* Per-frame parameters for the fused paths: the remaining AppParams PODs the per-frame
@@ -77,6 +84,7 @@ typedef struct HkfFrameParams {
     HkfRayCasterParams raycast;
     float icp_dist_thres, icp_norm_sin_thres, icp_dist_shake, icp_angle_shake;   /* IcpParams */
     uint32_t sdf_max_iter; float sdf_dist_shake, sdf_angle_shake;                /* SDFTrackerParams */
+    uint32_t use_color, color_angle_weight; /* _switch_params.useRGBData / colorAngleWeight (src/HybKinectfu.cpp:134-135,149) */
 } HkfFrameParams;
 
 typedef struct hkf_ctx hkf_ctx;
@@ -114,7 +122,10 @@ enum HkfBuffer {
     HKF_BUF_SOLVER_SUMS = 8,      /* 27 f32: rigid_align_buf_reduced */
     HKF_BUF_TRIANGLES = 9,        /* HkfTriangle[n], n = hkf_triangle_count() */
     HKF_BUF_POSE = 10,            /* 16 f32: device-resident current pose */
-    HKF_BUF_RAYCAST_KEYS = 11     /* u64 [rows][cols]: nearest-hit compositing keys (sharded mode) */
+    HKF_BUF_RAYCAST_KEYS = 11,    /* u64 [rows][cols]: nearest-hit compositing keys (sharded mode) */
+    HKF_BUF_RAW_RGB = 12,         /* uchar3 [rgb rows][rgb cols]: raw_rgb, channel order as uploaded (OpenCV BGR in the reference) */
+    HKF_BUF_RAYCAST_RGB = 13,     /* uchar3 [rows][cols]: raycast_rgb */
+    HKF_BUF_VOLUME_COLOR = 14     /* uchar4 [z][y][x]: Voxel.color of every stored voxel (.w unused) */
 };
 
 /* ------------------------------------------------------------------ 1. lifetime, buffers */
@@ -140,6 +151,9 @@ uint64_t hkf_launch_count(const hkf_ctx* ctx);
  * the reference's exact (float)((double)mm*0.001) arithmetic.  `depth_mm` may also be a device
  * pointer (is_device != 0), in which case no copy is made. */
 int  hkf_upload_depth_mm(hkf_ctx* ctx, const uint16_t* depth_mm, int is_device);
+/* the colour half of HybKinectfu::copyFrameToGPU (src/HybKinectfu.cpp:80-95): 3 interleaved bytes per pixel of the
+ * rgb camera's image, host or device pointer (contexts created with use_color) */
+int  hkf_upload_color(hkf_ctx* ctx, const uint8_t* rgb3, int is_device);
 
 /* ------------------------------------------------------------------ 2. wrapper parity layer */
 /* cudaTruncDepth, src/cuda/DataPreprocesser.cu:80-88 */
@@ -164,8 +178,11 @@ int hkf_cal_point_to_plane_err_solver_params(hkf_ctx* ctx, unsigned pyramid_leve
 /* cudaCalSDFSolverParams, src/cuda/CalSDFErrSolverParams.cu:110-138 */
 int hkf_cal_sdf_solver_params(hkf_ctx* ctx, const HkfCameraParams* depth_camera_params,
         const HkfMat44* cur_transform);
-/* cudaIntegrateVolume, src/cuda/integrateVolume.cu:78-97.  has_color / use_angle_weight_color
- * must be 0 (colour path is out of scope) -> HKF_ERR_ARG otherwise. */
+/* cudaIntegrateVolume, src/cuda/integrateVolume.cu:78-97.  has_color: the voxel colours are blended as well
+ * (tsdfVolume.h:57-74) from raw_rgb at the pixel the reference computes with its hard-coded 525 / 320 / 240
+ * intrinsics (integrateVolume.cu:56-62; kept, because parity is defined by the reference), and a
+ * voxel whose colour pixel lies outside the rgb image is not updated at all.  The colour is read AFTER that bounds test
+ * (the reference's source reads first; its compiled code does not). */
 int hkf_integrate_volume(hkf_ctx* ctx, int has_color, int use_angle_weight_color,
         const HkfMat44* transform, const HkfIntegrateParams* integrate_params,
         const HkfCameraParams* depth_camera_params, const HkfCameraParams* rgb_camera_params);

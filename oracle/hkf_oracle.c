@@ -60,6 +60,13 @@ static inline int f2i_rz(float f)
     if (f <= -2147483648.0f) return (-2147483647 - 1);
     return (int)f;
 }
+/* cvt.rzi.u32.f32 (F2I.U32.TRUNC): NaN -> 0, negative -> 0, saturating */
+static inline unsigned f2u_rz(float f)
+{
+    if (f != f || f <= 0.f) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (unsigned)f;
+}
 static inline float project1(float v, float f, float z, float c) { return (v * f) / z + c; }
 /* Mat44 * float4 row, two contractions (see CalPointToPlaneErrSolverParams PTX) */
 static inline float row4_lead_first(const float* m, float x, float y, float z, float w)
@@ -183,8 +190,13 @@ void orc_down_normals(const float* in, float* out, int in_cols, int in_rows)
 }
 
 /* ------------------------------------------------------------------ integration */
-uint64_t orc_integrate(float* vol, int R, float S, float wmax, const float* depth, const OrcCamera* cam,
-                       const float pose[16], float sdf_trunc, float max_dist, int z0, int z1)
+/* has_color (color != NULL): src/cuda/integrateVolume.cu:52-72 + tsdfVolume.h:57-74 as compiled for sm_100 (SASS of
+ * oracle/_ref/integrateVolume.o): colour pixel (int)(X*525/Z + 320), (int)(Y*525/Z + 240) in float with a truncating
+ * convert, voxel skipped when it falls outside [1, rgb_cols-2] x [1, rgb_rows-2]; weight 2 or 2*fminf(|n.z|/0.75, 1);
+ * c' = trunc(fminf(fma(wc, c_pixel, w_old * c_old) / (wc + w_old), 255)). */
+uint64_t orc_integrate_color(float* vol, uint8_t* color, int R, float S, float wmax, const float* depth, const float* normals4,
+                             const uint8_t* rgb, int rgb_cols, int rgb_rows, int angled, const OrcCamera* cam,
+                             const float pose[16], float sdf_trunc, float max_dist, int z0, int z1)
 {
     float inv[16];
     hm_mat44_inverse(pose, inv);                 /* cudaIntegrateVolume: transform.getInverse() on the host */
@@ -198,6 +210,7 @@ uint64_t orc_integrate(float* vol, int R, float S, float wmax, const float* dept
             const float wy = ((float)y + 0.5f) * cell;
             const float ty1 = wy * inv[1], ty2 = wy * inv[5], ty3 = wy * inv[9];
             float* rowp = vol + 2 * (((size_t)z * R + y) * R);
+            uint8_t* crow = color ? color + 4 * (((size_t)z * R + y) * R) : NULL;
             for (int x = 0; x < R; ++x) {
                 const float wx = ((float)x + 0.5f) * cell;
                 const float Z = fmaf(wz, inv[10], fmaf(wx, inv[8], ty3)) + inv[11];
@@ -209,6 +222,12 @@ uint64_t orc_integrate(float* vol, int R, float S, float wmax, const float* dept
                 if (u >= cols - 1 || v >= rows - 1 || u < 1 || v < 1) continue;
                 const float d = depth[(size_t)v * cols + u];
                 if (d == 0.f) continue;
+                int cu = 0, cv = 0;
+                if (color) {
+                    cu = f2i_rz((X * 525.0f) / Z + 320.0f);
+                    cv = f2i_rz((Y * 525.0f) / Z + 240.0f);
+                    if (cu >= rgb_cols - 1 || cv >= rgb_rows - 1 || cu < 1 || cv < 1) continue;
+                }
                 if (!(d < max_dist)) continue;
                 const float sdf = d - Z;
                 if (!(sdf > -sdf_trunc)) continue;
@@ -217,11 +236,28 @@ uint64_t orc_integrate(float* vol, int R, float S, float wmax, const float* dept
                 float w1 = w + 1.0f;
                 rowp[2 * x] = fmaf(t, w, tsdf) / w1;
                 rowp[2 * x + 1] = fminf(w1, wmax);
+                if (color) {
+                    float wc = 2.0f;
+                    if (angled) { const float q = fminf(fabsf(normals4[4 * ((size_t)v * cols + u) + 2]) / 0.75f, 1.0f); wc = q + q; }
+                    const uint8_t* px = rgb + 3 * ((size_t)cv * rgb_cols + cu);
+                    const float den = wc + w;
+                    for (int k = 0; k < 3; ++k) {
+                        const float nc = fminf(fmaf(wc, (float)px[k], w * (float)crow[4 * x + k]) / den, 255.0f);
+                        crow[4 * x + k] = (uint8_t)f2u_rz(nc);
+                    }
+                    crow[4 * x + 3] = 0;
+                }
                 total++;
             }
         }
     }
     return total;
+}
+
+uint64_t orc_integrate(float* vol, int R, float S, float wmax, const float* depth, const OrcCamera* cam,
+                       const float pose[16], float sdf_trunc, float max_dist, int z0, int z1)
+{
+    return orc_integrate_color(vol, NULL, R, S, wmax, depth, NULL, NULL, 0, 0, 0, cam, pose, sdf_trunc, max_dist, z0, z1);
 }
 
 /* ------------------------------------------------------------------ ICP sums */
@@ -374,6 +410,41 @@ static int interp_sdf(const VolView* V, float px, float py, float pz, float* dis
     *dist = acc;
     return 1;
 }
+/* tsdfvolume::interpolateColor (src/cuda/tsdfVolume.h:122-148): same cell and term order, per colour byte, truncated */
+static int interp_color(const VolView* V, const uint8_t* color, float px, float py, float pz, uint8_t out[3])
+{
+    int gx = w2v(V, px), gy = w2v(V, py), gz = w2v(V, pz);
+    int R = V->R;
+    if (gx <= 0 || gx >= R - 1) return 0;
+    if (gy <= 0 || gy >= R - 1) return 0;
+    if (gz <= 0 || gz >= R - 1) return 0;
+    float cell = V->cell;
+    float vx = ((float)gx + 0.5f) * cell, vy = ((float)gy + 0.5f) * cell, vz = ((float)gz + 0.5f) * cell;
+    gx = (px < vx) ? gx - 1 : gx;
+    gy = (py < vy) ? gy - 1 : gy;
+    gz = (pz < vz) ? gz - 1 : gz;
+    float a = fmaf((float)gx + 0.5f, -cell, px) / cell;
+    float b = fmaf((float)gy + 0.5f, -cell, py) / cell;
+    float c = fmaf((float)gz + 0.5f, -cell, pz) / cell;
+    static const int off[8][3] = { {0,0,0},{0,0,1},{0,1,0},{0,1,1},{1,0,0},{1,0,1},{1,1,0},{1,1,1} };
+    const uint8_t* cp[8];
+    for (int k = 0; k < 8; ++k) {
+        if (voxel(V, gx + off[k][0], gy + off[k][1], gz + off[k][2])[1] == 0.f) return 0;
+        cp[k] = color + 4 * (((size_t)(gz + off[k][2]) * R + (gy + off[k][1])) * R + (gx + off[k][0]));
+    }
+    float ia = 1.0f - a, ib = 1.0f - b, ic = 1.0f - c;
+    for (int ch = 0; ch < 3; ++ch) {
+        float acc = fmaf(ic, ib * (ia * (float)cp[0][ch]), c * (ib * (ia * (float)cp[1][ch])));
+        acc = fmaf(ic, b * (ia * (float)cp[2][ch]), acc);
+        acc = fmaf(c, b * (ia * (float)cp[3][ch]), acc);
+        acc = fmaf(ic, ib * (a * (float)cp[4][ch]), acc);
+        acc = fmaf(c, ib * (a * (float)cp[5][ch]), acc);
+        acc = fmaf(ic, b * (a * (float)cp[6][ch]), acc);
+        acc = fmaf(c, b * (a * (float)cp[7][ch]), acc);
+        out[ch] = (uint8_t)f2u_rz(acc);
+    }
+    return 1;
+}
 int orc_interpolate_sdf(const float* vol, int R, float S, float px, float py, float pz, float* dist)
 {
     VolView V = volview(vol, R, S);
@@ -418,7 +489,7 @@ static Ray ray_setup(const OrcCamera* cam, const float pose[16], float S, float 
 /* the (+ -> -) pair (last sample at l*, this sample at p*, parameter t): refinement, vertex, normal
    (src/cuda/raycastingVolume.cu:65-119); leaves the pixel zero on any failure */
 static void ray_hit(const VolView* V, const Ray* r, float inc, float t, float px, float py, float pz, float lx, float ly, float lz,
-                    float* ov, float* on)
+                    float* ov, float* on, const uint8_t* color, uint8_t* oc)
 {
     const int R = V->R;
     float ftdt, ft;
@@ -426,6 +497,8 @@ static void ray_hit(const VolView* V, const Ray* r, float inc, float t, float px
     if (!interp_sdf(V, lx, ly, lz, &ft)) return;
     float alpha = t - (inc * ftdt) / (ftdt - ft);
     float wx = fmaf(r->dx, alpha, r->ox), wy = fmaf(r->dy, alpha, r->oy), wz = fmaf(r->dz, alpha, r->oz);
+    /* has_color (raycastingVolume.cu:101-106): written when the interpolation succeeds, whatever the gradient does next */
+    if (color) { uint8_t c3[3]; if (interp_color(V, color, wx, wy, wz, c3)) { oc[0] = c3[0]; oc[1] = c3[1]; oc[2] = c3[2]; } }
     /* gradientForPoint(volume, last_world_pos, vertex) */
     int hx = w2v(V, lx), hy = w2v(V, ly), hz = w2v(V, lz);
     if (hx <= 1 || hx >= R - 2) return;
@@ -452,6 +525,12 @@ static void ray_hit(const VolView* V, const Ray* r, float inc, float t, float px
 void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float inc,
                  float near_plane, float far_plane, float* out_v4, float* out_n4)
 {
+    orc_raycast_color(vol, NULL, R, S, cam, pose, inc, near_plane, far_plane, out_v4, out_n4, NULL);
+}
+
+void orc_raycast_color(const float* vol, const uint8_t* color, int R, float S, const OrcCamera* cam, const float pose[16], float inc,
+                       float near_plane, float far_plane, float* out_v4, float* out_n4, uint8_t* out_rgb3)
+{
     VolView V = volview(vol, R, S);
     const int cols = (int)cam->cols, rows = (int)cam->rows;
 #pragma omp parallel for schedule(dynamic, 4)
@@ -461,6 +540,8 @@ void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const f
             float* on = out_n4 + 4 * ((size_t)y * cols + x);
             ov[0] = ov[1] = ov[2] = ov[3] = 0.f;
             on[0] = on[1] = on[2] = on[3] = 0.f;
+            uint8_t* oc = color ? out_rgb3 + 3 * ((size_t)y * cols + x) : NULL;
+            if (oc) { oc[0] = oc[1] = oc[2] = 0; }
             const Ray r = ray_setup(cam, pose, S, near_plane, far_plane, x, y);
             if (!r.live) continue;
             float t = r.tmin, last_sdf = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
@@ -469,7 +550,7 @@ void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const f
                 int gx = clampi(w2v(&V, px), 0, R - 1), gy = clampi(w2v(&V, py), 0, R - 1), gz = clampi(w2v(&V, pz), 0, R - 1);
                 float sdf = voxel(&V, gx, gy, gz)[0];
                 if (last_sdf > 0.0f && sdf < 0.0f) {
-                    ray_hit(&V, &r, inc, t, px, py, pz, lx, ly, lz, ov, on);
+                    ray_hit(&V, &r, inc, t, px, py, pz, lx, ly, lz, ov, on, color, oc);
                     break;
                 }
                 last_sdf = sdf; lx = px; ly = py; lz = pz;

@@ -38,6 +38,12 @@ void orc_down_normals(const float* in, float* out, int in_cols, int in_rows);
 uint64_t orc_integrate(float* vol, int R, float S, float wmax, const float* trunc_depth, const OrcCamera* cam,
                        const float pose[16], float sdf_trunc, float max_dist, int z0, int z1);
 
+/* the same with has_color (src/cuda/integrateVolume.cu:52-72, tsdfVolume.h:57-74): color = uint8 [R][R][R][4] (3 used),
+ * normals4 = the new frame's level-0 normal map (angle weighting), rgb = uint8 [rgb_rows][rgb_cols][3] */
+uint64_t orc_integrate_color(float* vol, uint8_t* color, int R, float S, float wmax, const float* trunc_depth, const float* normals4,
+                             const uint8_t* rgb, int rgb_cols, int rgb_rows, int angled, const OrcCamera* cam,
+                             const float pose[16], float sdf_trunc, float max_dist, int z0, int z1);
+
 /* src/cuda/CalPointToPlaneErrSolverParams.cu:7-129 + device_functions.h:11-55: the 27 sums with the
  * reference's exact two-stage float reduction trees (16x16 blocks, then 512-strided). */
 void orc_icp_sums(const float* new_v, const float* new_n, const float* model_v, const float* model_n,
@@ -48,12 +54,19 @@ void orc_icp_sums(const float* new_v, const float* new_n, const float* model_v, 
 void orc_raycast(const float* vol, int R, float S, const OrcCamera* cam, const float pose[16], float ray_inc,
                  float near_plane, float far_plane, float* out_v4, float* out_n4);
 
+/* has_color: also raycast_rgb (uint8 [rows][cols][3]), src/cuda/raycastingVolume.cu:101-106 + tsdfVolume.h:122-148 */
+void orc_raycast_color(const float* vol, const uint8_t* color, int R, float S, const OrcCamera* cam, const float pose[16], float ray_inc,
+                       float near_plane, float far_plane, float* out_v4, float* out_n4, uint8_t* out_rgb3);
+
 /* src/cuda/CalSDFErrSolverParams.cu:7-138 */
 void orc_sdf_sums(const float* vol, int R, float S, const float* trunc_depth, const OrcCamera* cam,
                   const float cur[16], float out27[27]);
 
 /* src/cuda/marchingcube.cu:5-164 (colour off). tris: float[max][3][6] (pos, colour=0). Returns the count. */
 uint32_t orc_marching_cubes(const float* vol, int R, float S, float threshold, float* tris, uint32_t max_tris);
+
+/* has_color: vertex colours as vertexInterp computes them (marchingcube.cu:5-26, 44-75) */
+uint32_t orc_marching_cubes_color(const float* vol, const uint8_t* color, int R, float S, float threshold, float* tris, uint32_t max_tris);
 
 /* tsdfvolume::interpolateSDF (src/cuda/tsdfVolume.h:98-120,151-174). returns 0/1 */
 int orc_interpolate_sdf(const float* vol, int R, float S, float px, float py, float pz, float* dist);

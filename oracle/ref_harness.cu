@@ -15,7 +15,9 @@
 //  (i)  pyramids: the four cudaDownSample* wrappers launch <<<block,grid>>> swapped
 //       (src/cuda/sample.cu:72,84,96,109).  We include sample.cu in this TU and launch the
 //       unmodified pryDown*Kernel ourselves with a correct config into padded buffers.
-//  (ii) use_color is always 0.
+//  (ii) colour: off unless ref_set_color() switches it on.  The reference's SOURCE reads the colour pixel before its bounds
+//       test (src/cuda/integrateVolume.cu:58-62); the code nvcc 12.9 generates for sm_100 sinks the three byte loads below
+//       every test (checked in the SASS of _ref/integrateVolume.o), so the compiled oracle never reads out of bounds.
 //  (iii) the MC triangle counter is cleared before each cudaMarchingcube call.
 #include <cstdio>
 #include <cstring>
@@ -48,7 +50,8 @@ struct RefParams {
 enum RefBuffer {
     REF_RAW_DEPTH = 0, REF_TRUNC_DEPTH = 1, REF_FILTERED_DEPTH = 2,
     REF_NEW_VERTICES = 3, REF_NEW_NORMALS = 4, REF_MODEL_VERTICES = 5, REF_MODEL_NORMALS = 6,
-    REF_VOLUME = 7 /* AoS Voxel 12 B */, REF_ICP_REDUCED = 8, REF_TRIANGLES = 9
+    REF_VOLUME = 7 /* AoS Voxel 12 B */, REF_ICP_REDUCED = 8, REF_TRIANGLES = 9,
+    REF_VOLUME_COLOR = 10 /* uchar4 per voxel (.w = 0) */, REF_RAYCAST_RGB = 11, REF_RAW_RGB = 12 /* uchar3 maps */
 };
 
 static bool g_inited = false;
@@ -133,6 +136,25 @@ extern "C" int ref_init(const RefParams* p)
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { fprintf(stderr, "ref_init: %s\n", cudaGetErrorString(e)); return -2; }
     return 0;
+}
+
+// colour mode (src/HybKinectfu.cpp:134-135,149; src/MeshGeneratorMarchingcube.cpp:26)
+extern "C" void ref_set_color(int use_color, int angle_weight)
+{
+    AP()->_switch_params.useRGBData = use_color != 0;
+    AP()->_switch_params.colorAngleWeight = angle_weight != 0;
+}
+// the colour half of HybKinectfu::copyFrameToGPU (src/HybKinectfu.cpp:80-95): 3 bytes per pixel, rgb camera size
+extern "C" void ref_upload_rgb(const uint8_t* rgb3)
+{
+    unsigned cols = AP()->_rgb_camera_params.cols, rows = AP()->_rgb_camera_params.rows;
+    Color3uMap2D cpu(CPU, cols, rows);
+    for (unsigned r = 0; r < rows; ++r)
+        for (unsigned c = 0; c < cols; ++c) {
+            const uint8_t* q = rgb3 + 3 * ((size_t)r * cols + c);
+            cpu.at(c, r) = make_uchar3(q[0], q[1], q[2]);
+        }
+    DM()->raw_rgb.copyDataFrom(cpu);
 }
 
 extern "C" void ref_reset_volume()
@@ -226,20 +248,21 @@ extern "C" void ref_integrate(const float pose[16])
     Mat44 p(pose);
     // silence the wrapper's per-call cout
     std::streambuf* old = std::cout.rdbuf(nullptr);
-    cudaIntegrateVolume(false, false, p, AP()->_integrate_params, AP()->_depth_camera_params, AP()->_rgb_camera_params);
+    cudaIntegrateVolume(AP()->_switch_params.useRGBData, AP()->_switch_params.colorAngleWeight, p, AP()->_integrate_params,
+                        AP()->_depth_camera_params, AP()->_rgb_camera_params);
     std::cout.rdbuf(old);
 }
 extern "C" void ref_raycast(const float pose[16])
 {
     Mat44 p(pose);
-    cudaRaycastingVolume(false, p, AP()->_raycast_params, AP()->_depth_camera_params,
+    cudaRaycastingVolume(AP()->_switch_params.useRGBData, p, AP()->_raycast_params, AP()->_depth_camera_params,
                          AP()->_depth_prepocess_params.fMinTrunc, AP()->_depth_prepocess_params.fMaxTrunc);
 }
 extern "C" unsigned ref_marchingcube()
 {
     DM()->marchingcube_data.clearData();
     // MeshGeneratorMarchingcube::generateMesh threshold (src/MeshGeneratorMarchingcube.cpp:26-27)
-    cudaMarchingcube(false, 300 * AP()->_volume_params.fVolumeMeterSize / AP()->_volume_params.nResolution);
+    cudaMarchingcube(AP()->_switch_params.useRGBData, 300 * AP()->_volume_params.fVolumeMeterSize / AP()->_volume_params.nResolution);
     return DM()->marchingcube_data.triangleNums();
 }
 
@@ -255,6 +278,8 @@ static size_t map_bytes(int buffer, unsigned level, void** dptr)
     case REF_MODEL_VERTICES: *dptr = d->model_vertices_pyramid[level].ptr(); return sizeof(float4) * d->model_vertices_pyramid[level].cols() * d->model_vertices_pyramid[level].rows();
     case REF_MODEL_NORMALS: *dptr = d->model_normals_pyramid[level].ptr(); return sizeof(float4) * d->model_normals_pyramid[level].cols() * d->model_normals_pyramid[level].rows();
     case REF_ICP_REDUCED: *dptr = d->rigid_align_buf_reduced.ptr(); return sizeof(float) * 27;
+    case REF_RAYCAST_RGB: *dptr = d->raycast_rgb.ptr(); return sizeof(uchar3) * d->raycast_rgb.cols() * d->raycast_rgb.rows();
+    case REF_RAW_RGB: *dptr = d->raw_rgb.ptr(); return sizeof(uchar3) * d->raw_rgb.cols() * d->raw_rgb.rows();
     default: *dptr = nullptr; return 0;
     }
 }
@@ -269,6 +294,11 @@ __global__ void ref_volume_to_float2(const Voxel* vox, float2* out, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = make_float2(vox[i].tsdf, vox[i].weight);
+}
+__global__ void ref_volume_to_color(const Voxel* vox, uchar4* out, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_uchar4(vox[i].color.x, vox[i].color.y, vox[i].color.z, 0);
 }
 __global__ void ref_volume_from_float2(Voxel* vox, const float2* in, size_t n)
 {
@@ -289,6 +319,17 @@ extern "C" long ref_download(int buffer, unsigned level, void* dst, size_t cap)
         cudaMemcpy(dst, tmp, n * sizeof(float2), cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         return (long)(n * sizeof(float2));
+    }
+    if (buffer == REF_VOLUME_COLOR) {
+        int R = AP()->_volume_params.nResolution;
+        size_t n = (size_t)R * R * R;
+        if (cap < n * sizeof(uchar4)) return -1;
+        uchar4* tmp; cudaMalloc(&tmp, n * sizeof(uchar4));
+        VolAccess va(DM()->volume);
+        ref_volume_to_color<<<1184, 256>>>(va.raw(), tmp, n);
+        cudaMemcpy(dst, tmp, n * sizeof(uchar4), cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        return (long)(n * sizeof(uchar4));
     }
     if (buffer == REF_TRIANGLES) {
         MarchingcubeData cpu = DM()->marchingcube_data.clone(CPU);

@@ -144,6 +144,42 @@ def integrate(vol, cfg, depth, pose, z0=0, z1=None) -> int:
                                    _fp(p), C.c_float(cfg.sdf_trunc), C.c_float(cfg.max_integrate_dist), z0, z1))
 
 
+def integrate_color(vol, color, cfg, depth, normals, bgr, pose, angled) -> int:
+    """has_color integration: vol f32 [R][R][R][2] and color u8 [R][R][R][4] are updated in place"""
+    R = cfg.resolution
+    cam = cam_of(cfg)
+    p = np.ascontiguousarray(pose, dtype=np.float32).reshape(16)
+    assert color.dtype == np.uint8 and color.flags["C_CONTIGUOUS"] and bgr.dtype == np.uint8 and bgr.flags["C_CONTIGUOUS"]
+    lib = cpu()
+    lib.orc_integrate_color.restype = C.c_uint64
+    return int(lib.orc_integrate_color(_fp(vol), color.ctypes.data_as(C.c_void_p), R, C.c_float(cfg.volume_size), C.c_float(cfg.weight_max),
+                                       _fp(depth), _fp(normals), bgr.ctypes.data_as(C.c_void_p), cfg.cols, cfg.rows, int(angled),
+                                       C.byref(cam), _fp(p), C.c_float(cfg.sdf_trunc), C.c_float(cfg.max_integrate_dist), 0, R))
+
+
+def raycast_color(vol, color, cfg, pose):
+    cam = cam_of(cfg)
+    v = np.empty((cfg.rows, cfg.cols, 4), np.float32)
+    n = np.empty_like(v)
+    rgb = np.empty((cfg.rows, cfg.cols, 3), np.uint8)
+    p = np.ascontiguousarray(pose, np.float32).reshape(16)
+    cpu().orc_raycast_color(_fp(vol), color.ctypes.data_as(C.c_void_p), cfg.resolution, C.c_float(cfg.volume_size), C.byref(cam), _fp(p),
+                            C.c_float(cfg.ray_increment), C.c_float(cfg.trunc_min), C.c_float(cfg.trunc_max), _fp(v), _fp(n),
+                            rgb.ctypes.data_as(C.c_void_p))
+    return v, n, rgb
+
+
+def marching_cubes_color(vol, color, cfg, max_tris=None):
+    max_tris = max_tris or cfg.max_triangles
+    tris = np.zeros((max_tris, 3, 6), np.float32)
+    thr = np.float32(300) * np.float32(cfg.volume_size) / np.float32(cfg.resolution)
+    lib = cpu()
+    lib.orc_marching_cubes_color.restype = C.c_uint32
+    n = int(lib.orc_marching_cubes_color(_fp(vol), color.ctypes.data_as(C.c_void_p), cfg.resolution, C.c_float(cfg.volume_size),
+                                         C.c_float(float(thr)), _fp(tris), C.c_uint32(max_tris)))
+    return n, tris[:min(n, max_tris)]
+
+
 def icp_sums(nv, nn, mv, mn, cam: OrcCamera, cur, last_inv, dist_thres, sin_thres):
     out = np.zeros(27, np.float32)
     a = np.ascontiguousarray(cur, np.float32).reshape(16)
@@ -248,7 +284,7 @@ class CpuTracker:
 
 # ---------------------------------------------------------------- reference CUDA build (GPU box only)
 REF_RAW_DEPTH, REF_TRUNC_DEPTH, REF_FILTERED_DEPTH, REF_NEW_VERTICES, REF_NEW_NORMALS, REF_MODEL_VERTICES, \
-    REF_MODEL_NORMALS, REF_VOLUME, REF_ICP_REDUCED, REF_TRIANGLES = range(10)
+    REF_MODEL_NORMALS, REF_VOLUME, REF_ICP_REDUCED, REF_TRIANGLES, REF_VOLUME_COLOR, REF_RAYCAST_RGB, REF_RAW_RGB = range(13)
 
 
 def ref_available() -> bool:
@@ -277,6 +313,7 @@ class Ref:
         rc = self.lib.ref_init(C.byref(p))
         if rc != 0:
             raise RuntimeError(f"ref_init failed: {rc}")
+        self.lib.ref_set_color(0, 0)
 
     def _shape(self, buf, level):
         rows, cols = self.cfg.level_shape(level)
@@ -289,6 +326,11 @@ class Ref:
             return (R, R, R, 2), np.float32
         if buf == REF_ICP_REDUCED:
             return (27,), np.float32
+        if buf == REF_VOLUME_COLOR:
+            R = self.cfg.resolution
+            return (R, R, R, 4), np.uint8
+        if buf in (REF_RAYCAST_RGB, REF_RAW_RGB):
+            return (self.cfg.rows, self.cfg.cols, 3), np.uint8
         raise ValueError(buf)
 
     def download(self, buf, level=0):
@@ -319,6 +361,14 @@ class Ref:
     def upload_depth_mm(self, mm):
         a = np.ascontiguousarray(mm, np.uint16)
         self.lib.ref_upload_depth_mm(a.ctypes.data_as(C.c_void_p))
+
+    def set_color(self, use_color, angle_weight=0):
+        self.lib.ref_set_color(int(use_color), int(angle_weight))
+
+    def upload_rgb(self, bgr):
+        a = np.ascontiguousarray(bgr, np.uint8)
+        assert a.shape == (self.cfg.rows, self.cfg.cols, 3)
+        self.lib.ref_upload_rgb(a.ctypes.data_as(C.c_void_p))
 
     def preprocess(self, mm):
         self.upload_depth_mm(mm)

@@ -12,6 +12,9 @@ Fixtures (small on purpose: 192x144 frames, 64^3 / 128^3 volumes over 2 m):
   stages_small.npz    every per-stage buffer for one frame, volume after 3 integrations, raycast maps,
                       model pyramids, ICP sums per level, SDF sums, marching-cubes triangles
   pipeline_small.npz  per-frame poses + status of the full ICP and SDF pipelines, final volume digest
+  color_small.npz     `python tests/golden/make_golden.py <outdir> color`: the colour path (use_color=1, with and
+                      without angle weighting): volume + voxel colours after 3 integrations, raycast maps + raycast_rgb,
+                      marching-cubes triangles with vertex colours
 """
 import hashlib
 import os
@@ -49,6 +52,56 @@ def canon_tris(t):
     p = np.ascontiguousarray(t[:, :, :3]).reshape(len(t), 9)
     key = np.lexsort(p.T[::-1])
     return p[key]
+
+
+def canon_tris_color(t):
+    """order-independent form of a coloured triangle soup: rows of 18 floats (pos, colour per vertex), sorted"""
+    if len(t) == 0:
+        return np.zeros((0, 18), np.float32)
+    p = np.ascontiguousarray(t).reshape(len(t), 18)
+    key = np.lexsort(p.T[::-1])
+    return p[key]
+
+
+def color_sequence(n_frames, stride=4):
+    cfg, cam = small_config()
+    poses = synth.trajectory(200)[::stride][:n_frames]
+    return np.stack([synth.render_color(p, cam) for p in poses])
+
+
+def main_color(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    frames, poses = small_sequence(4)
+    bgr = color_sequence(4)
+    cfg, cam = small_config(64)
+    g = {"frames": frames, "poses": poses, "bgr": bgr}
+    for angled in (0, 1):
+        ref = O.Ref(cfg)
+        ref.set_color(1, angled)
+        ref.reset_volume()
+        for i in range(3):
+            ref.preprocess(frames[i])
+            ref.upload_rgb(bgr[i])
+            ref.integrate(poses[i])
+        g[f"new_n0_{angled}"] = ref.download(O.REF_NEW_NORMALS, 0)
+        g[f"trunc_{angled}"] = ref.download(O.REF_TRUNC_DEPTH)
+        g[f"vol_{angled}"] = ref.download(O.REF_VOLUME)
+        g[f"vol_color_{angled}"] = ref.download(O.REF_VOLUME_COLOR)
+        ref.raycast(poses[2])
+        g[f"model_v0_{angled}"] = ref.download(O.REF_MODEL_VERTICES, 0)
+        g[f"model_n0_{angled}"] = ref.download(O.REF_MODEL_NORMALS, 0)
+        g[f"raycast_rgb_{angled}"] = ref.download(O.REF_RAYCAST_RGB)
+        n = ref.marching_cubes()
+        tris = ref.download(O.REF_TRIANGLES)
+        assert len(tris) == n
+        g[f"mc_count_{angled}"] = np.array([n], np.int64)
+        g[f"mc_tris_sorted_{angled}"] = canon_tris_color(tris)
+        ref.set_color(0, 0)
+        ref.check()
+        print(f"color (angled={angled}): coloured voxels", int((g[f"vol_color_{angled}"][..., :3] != 0).any(-1).sum()),
+              "observed", int((g[f"vol_{angled}"][..., 1] > 0).sum()), "raycast rgb px", int((g[f"raycast_rgb_{angled}"] != 0).any(-1).sum()),
+              "triangles", n)
+    np.savez_compressed(os.path.join(outdir, "color_small.npz"), **g)
 
 
 def digest(a):
@@ -124,6 +177,10 @@ def main(outdir):
         print(name, "status", sts, "mc", n, "terr(mm)", [round(float(np.linalg.norm(ps[i][:3, 3] - poses[i][:3, 3]) * 1e3), 2) for i in range(len(frames))])
     np.savez_compressed(os.path.join(outdir, "pipeline_small.npz"), **h)
 
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "color":
+    main_color(sys.argv[1])
+    sys.exit(0)
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))

@@ -244,7 +244,7 @@ def test_abi_argument_errors():
         m = capi.Mat44.from_np(np.eye(4))
         ip = capi.IntegrateParams(0.04, 2.0)
         cam = cfg.camera()
-        assert lib.hkf_integrate_volume(h, 1, 0, C.byref(m), C.byref(ip), C.byref(cam), C.byref(cam)) == 1   # colour: out of scope
+        assert lib.hkf_integrate_volume(h, 1, 0, C.byref(m), C.byref(ip), C.byref(cam), C.byref(cam)) == 4   # colour on a context created without use_color: HKF_ERR_STATE
         bad = capi.CameraParams(10, 10, 1, 1, 1, 1)
         assert lib.hkf_integrate_volume(h, 0, 0, C.byref(m), C.byref(ip), C.byref(bad), C.byref(bad)) == 1
         assert lib.hkf_cal_point_to_plane_err_solver_params(h, 7, C.byref(m), C.byref(m), C.byref(cam), 0.1, 0.2) == 1
