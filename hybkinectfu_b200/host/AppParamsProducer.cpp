@@ -100,6 +100,7 @@ HkfFrameParams AppParams::frameParams() const
     f.icp_dist_thres = _icp_params.fDistThres; f.icp_norm_sin_thres = _icp_params.fNormSinThres;
     f.icp_dist_shake = _icp_params.fDistShake; f.icp_angle_shake = _icp_params.fAngleShake;
     f.sdf_max_iter = _sdf_tracker_params.maxIterNums; f.sdf_dist_shake = _sdf_tracker_params.fDistShake; f.sdf_angle_shake = _sdf_tracker_params.fAngleShake;
+    f.use_color = _switch_params.useRGBData ? 1u : 0u; f.color_angle_weight = _switch_params.colorAngleWeight ? 1u : 0u;
     return f;
 }
 
@@ -112,5 +113,9 @@ HkfInitParams AppParams::initParams() const
     p.pyramid_levels = _icp_params.nPyramidLevels;
     p.volume_resolution = _volume_params.nResolution; p.volume_size = _volume_params.fVolumeMeterSize; p.weight_max = _volume_params.fWeightMax;
     p.max_triangles = _marchingcube_params.uMaxTriangles;
+    p.use_color = _switch_params.useRGBData ? 1u : 0u;
+    p.rgb_camera.cols = _rgb_camera_params.cols; p.rgb_camera.rows = _rgb_camera_params.rows;
+    p.rgb_camera.cx = _rgb_camera_params.cx; p.rgb_camera.cy = _rgb_camera_params.cy;
+    p.rgb_camera.fx = _rgb_camera_params.fx; p.rgb_camera.fy = _rgb_camera_params.fy;
     return p;
 }

@@ -93,6 +93,53 @@ void DataSourceProducerSynthetic::renderDepthMm(const double pose[16], const Cam
         }
 }
 
+void DataSourceProducerSynthetic::renderColor(const double pose[16], const CameraParams& cam, uint8_t* out)
+{
+    static const double kBgr[5][3] = { { 90, 180, 200 }, { 220, 160, 90 }, { 120, 220, 120 }, { 80, 80, 230 }, { 60, 240, 240 } };
+    const double inf = std::numeric_limits<double>::infinity();
+    const double o[3] = { pose[3], pose[7], pose[11] };
+    for (unsigned v = 0; v < cam.rows; ++v)
+        for (unsigned u = 0; u < cam.cols; ++u) {
+            const double dc[3] = { ((double)u - (double)cam.cx) / (double)cam.fx, ((double)v - (double)cam.cy) / (double)cam.fy, 1.0 };
+            double d[3];
+            for (int i = 0; i < 3; ++i) d[i] = dc[0] * pose[i * 4 + 0] + dc[1] * pose[i * 4 + 1] + dc[2] * pose[i * 4 + 2];
+            double best = inf;
+            int surf = -1, k = 0;
+            for (const auto& pl : kPlanes) {
+                const int ax = (int)pl[0];
+                const double s = (pl[1] - o[ax]) / d[ax];
+                if (s > 1e-9 && std::isfinite(s) && s < best) { best = s; surf = k; }
+                ++k;
+            }
+            for (const auto& sp : kSpheres) {
+                const double oc[3] = { o[0] - sp[0], o[1] - sp[1], o[2] - sp[2] };
+                const double a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                const double b = 2.0 * (d[0] * oc[0] + d[1] * oc[1] + d[2] * oc[2]);
+                const double c = (oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2]) - sp[3] * sp[3];
+                const double disc = b * b - 4 * a * c;
+                if (disc >= 0) {
+                    const double sq = std::sqrt(disc);
+                    const double s1 = (-b - sq) / (2 * a), s2 = (-b + sq) / (2 * a);
+                    const double s = s1 > 1e-9 ? s1 : s2;
+                    if (s > 1e-9 && s < best) { best = s; surf = k; }
+                }
+                ++k;
+            }
+            uint8_t* px = out + 3 * ((size_t)v * cam.cols + u);
+            if (!std::isfinite(best)) { px[0] = px[1] = px[2] = 0; continue; }
+            double p[3];
+            long long cell = 0;
+            for (int i = 0; i < 3; ++i) { p[i] = o[i] + d[i] * best; cell += (long long)std::floor(p[i] / 0.1 + 1e-6); }
+            const double check = (double)(cell & 1);
+            const double ramp = p[0] / 2.0 < 0.0 ? 0.0 : p[0] / 2.0 > 1.0 ? 1.0 : p[0] / 2.0;
+            const double shade = (1.0 - 0.4 * check) * (0.75 + 0.25 * ramp);
+            for (int i = 0; i < 3; ++i) {
+                const double c = std::nearbyint(kBgr[surf][i] * shade);
+                px[i] = (uint8_t)(c < 0 ? 0 : c > 255 ? 255 : c);
+            }
+        }
+}
+
 static void mat_to_quat(const double* p, double q[4])   // (qx,qy,qz,qw) of the rotation block of a row-major 4x4
 {
     auto R = [&](int i, int j) { return p[i * 4 + j]; };
@@ -131,6 +178,7 @@ bool DataSourceProducerSynthetic::initDataSource()
     _n = P->_synthetic_params.nFrames;
     _phase = P->_synthetic_params.phase;
     _buf.resize((size_t)P->_depth_camera_params.cols * P->_depth_camera_params.rows);
+    if (P->_switch_params.useRGBData) _rgb.resize((size_t)P->_rgb_camera_params.cols * P->_rgb_camera_params.rows * 3);
     _next = 0;
     return _n > 0 && !_buf.empty();
 }
@@ -144,7 +192,12 @@ bool DataSourceProducerSynthetic::readDataFromSource(DepthFrameData& depth_data,
     const double ts = _next / 30.0;
     depth_data.setFrameId(_next); rgb_data.setFrameId(_next);
     depth_data.setFrameData(_buf.data(), (int)P->_depth_camera_params.cols, (int)P->_depth_camera_params.rows, ts);
-    rgb_data.setFrameData(nullptr, 0, 0, ts);
+    if (P->_switch_params.useRGBData) {
+        renderColor(pose, P->_rgb_camera_params, _rgb.data());
+        rgb_data.setFrameData(_rgb.data(), (int)P->_rgb_camera_params.cols, (int)P->_rgb_camera_params.rows, ts);
+    } else {
+        rgb_data.setFrameData(nullptr, 0, 0, ts);
+    }
     ++_next;
     return true;
 }

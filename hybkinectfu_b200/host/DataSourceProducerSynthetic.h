@@ -12,6 +12,8 @@ public:
     // camera -> world pose of frame i of n (row-major 4x4, double)
     static void trajectoryPose(unsigned i, unsigned n, double phase, double volume_size, double trunc_min, double out[16]);
     static void renderDepthMm(const double pose[16], const CameraParams& cam, uint16_t* out);
+    // 3 bytes per pixel (B, G, R like the reference's OpenCV frames) of the same scene: synth.render_color
+    static void renderColor(const double pose[16], const CameraParams& cam, uint8_t* out);
     // "timestamp tx ty tz qx qy qz qw" with the three header lines CameraPoseFinderFromFile skips
     static bool writeTumTrajectory(const std::string& path, unsigned n, double phase, double volume_size, double trunc_min, double fps = 30.0);
     unsigned framesRead() const { return _next; }
@@ -24,4 +26,5 @@ private:
     unsigned _next = 0, _n = 0;
     double _phase = 0.0;
     std::vector<uint16_t> _buf;
+    std::vector<uint8_t> _rgb;
 };

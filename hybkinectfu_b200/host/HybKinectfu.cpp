@@ -17,7 +17,6 @@ bool HybKinectfu::init()
 {
     if (_inited) return false;
     const AppParams* P = AppParams::instance();
-    if (P->_switch_params.useRGBData) { std::cerr << "use_color=1 is outside this path (SURVEY.md 8f rank 4): run with use_color=0" << std::endl; return false; }
     if (!CudaDeviceDataMan::instance()->ctx()) return false;
     if (P->_switch_params.useTrajFromFile) _camera_pose_finder = new CameraPoseFinderFromFile();
     else if (P->_switch_params.useSdfTracker) _camera_pose_finder = new CameraPoseFinderSDF();
@@ -41,6 +40,12 @@ bool HybKinectfu::processNewFrame(const DepthFrameData& depth_frame, const Color
     if ((unsigned)depth_frame.cols() != P->_depth_camera_params.cols || (unsigned)depth_frame.rows() != P->_depth_camera_params.rows) return false;
     // copyFrameToGPU + cudaTruncDepth + cudaBiliearFilterDepth + cudaCalculateNewVertices/Normals (+ new-frame pyramids)
     if (hkf_preprocess(c, depth_frame.mm(), 0, &fp) != HKF_OK) return false;
+    const bool color = P->_switch_params.useRGBData;
+    if (color) {
+        // the colour half of copyFrameToGPU (src/HybKinectfu.cpp:80-95): the frame's 3-byte pixels as they are
+        if (rgb_frame.empty() || (unsigned)rgb_frame.cols() != P->_rgb_camera_params.cols || (unsigned)rgb_frame.rows() != P->_rgb_camera_params.rows) return false;
+        if (hkf_upload_color(c, reinterpret_cast<const uint8_t*>(rgb_frame.data()), 0) != HKF_OK) return false;
+    }
 
     bool ok = _camera_pose_finder->findCameraPose(depth_frame, rgb_frame);
     const bool resident = _camera_pose_finder->poseIsDeviceResident();
@@ -57,9 +62,9 @@ bool HybKinectfu::processNewFrame(const DepthFrameData& depth_frame, const Color
         const Mat44 pose = _camera_pose_finder->getCameraPose();
         const CameraParams& dc = P->_depth_camera_params;
         const CameraParams& rc = P->_rgb_camera_params;
-        if (ok && hkf_integrate_volume(c, 0, 0, pose.abi(), reinterpret_cast<const HkfIntegrateParams*>(&P->_integrate_params),
+        if (ok && hkf_integrate_volume(c, color ? 1 : 0, (color && P->_switch_params.colorAngleWeight) ? 1 : 0, pose.abi(), reinterpret_cast<const HkfIntegrateParams*>(&P->_integrate_params),
                                        reinterpret_cast<const HkfCameraParams*>(&dc), reinterpret_cast<const HkfCameraParams*>(&rc)) != HKF_OK) return false;
-        if (hkf_raycasting_volume(c, 0, pose.abi(), reinterpret_cast<const HkfRayCasterParams*>(&P->_raycast_params),
+        if (hkf_raycasting_volume(c, color ? 1 : 0, pose.abi(), reinterpret_cast<const HkfRayCasterParams*>(&P->_raycast_params),
                                   reinterpret_cast<const HkfCameraParams*>(&dc), P->_depth_prepocess_params.fMinTrunc, P->_depth_prepocess_params.fMaxTrunc) != HKF_OK) return false;
         if (ok && hkf_set_pose(c, pose.abi()) != HKF_OK) return false;          // keep the device copy in step
     }

@@ -15,7 +15,7 @@
 void MeshGeneratorMarchingcube::generateMesh()
 {
     const AppParams* P = AppParams::instance();
-    hkf_marchingcube(CudaDeviceDataMan::instance()->ctx(), 0, 300 * P->_volume_params.fVolumeMeterSize / P->_volume_params.nResolution);
+    hkf_marchingcube(CudaDeviceDataMan::instance()->ctx(), P->_switch_params.useRGBData ? 1 : 0, 300 * P->_volume_params.fVolumeMeterSize / P->_volume_params.nResolution);
 }
 
 bool MeshGeneratorMarchingcube::copyTrianglesToCPU()
@@ -31,7 +31,15 @@ bool MeshGeneratorMarchingcube::copyTrianglesToCPU()
 }
 
 namespace {
-struct Vec3Hash {
+struct CellHash {
+    size_t operator()(const std::array<int32_t, 3>& k) const
+    {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int32_t w : k) { h ^= (uint32_t)w; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
+        return (size_t)h;
+    }
+};
+struct FaceHash {
     size_t operator()(const std::array<uint32_t, 3>& k) const
     {
         uint64_t h = 0x9E3779B97F4A7C15ull;
@@ -39,41 +47,65 @@ struct Vec3Hash {
         return (size_t)h;
     }
 };
-inline uint32_t float_bits(float f) { if (f == 0.f) f = 0.f; uint32_t u; std::memcpy(&u, &f, 4); return u; }   // -0 welds with +0
+inline int sign_of(float v) { return (0 < v) - (v < 0); }                      // sign(), src/cuda/cuda_declar.h:95-97
+// toVirtualVoxelPos (src/utils/mesh/meshData.h:750-753): v * (float)(1.0 / voxelSize) + sign(v) * 0.5, truncated
+inline int32_t virtual_cell(float v, float inv_size) { const float t = v * inv_size; return (int32_t)(t + (float)(sign_of(v) * 0.5)); }
 }
 
-// Canonical order first (marching cubes appends triangles in a nondeterministic order): the soup is sorted by its nine
-// position floats, so vertex numbering and face order - hence the file - depend on the volume only.  Keys are gathered
-// once (the comparator touches 36 contiguous bytes), vertices are numbered through a hash of their bit patterns.
+// The reference's post-processing of the triangle soup, restated (src/MeshGeneratorMarchingcube.cpp:61-97 ->
+// ml::MeshData::mergeCloseVertices(1e-4, approx = true), removeDegeneratedFaces, removeDuplicateFaces;
+// src/utils/mesh/meshData.cpp:41-86,166-314).  The approximate merge is a hash grid of 1e-4 m cells: a vertex joins the
+// FIRST registered vertex found in the 27 cells around its own (x outermost, no distance test), otherwise it
+// registers itself in its cell - so vertices up to two cells apart may merge and the result depends on the order in
+// which the soup is walked.  Marching cubes appends triangles in a nondeterministic order (in the reference too), so
+// the soup is first put in canonical order (sorted by its nine position floats): the mesh - hence the file - is then a
+// deterministic function of the volume, and equals what the reference's code makes of the same ordered soup
+// (tests/test_mesh_reference.py drives the reference's own ml::MeshData next to this).
 void MeshGeneratorMarchingcube::weld(std::vector<HkfTriangle> soup, std::vector<std::array<float, 3>>& vertices,
-                                     std::vector<std::array<unsigned, 3>>& faces)
+                                     std::vector<std::array<unsigned, 3>>& faces, std::vector<std::array<float, 4>>* colors)
 {
     const size_t n = soup.size();
+    std::vector<unsigned> order(n);
+    for (size_t t = 0; t < n; ++t) order[t] = (unsigned)t;
     std::vector<std::array<float, 9>> keys(n);
     for (size_t t = 0; t < n; ++t) {
         const HkfVertex* v = &soup[t].v0;
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) keys[t][i * 3 + j] = v[i].pos[j];
     }
-    std::sort(keys.begin(), keys.end());
-    std::unordered_map<std::array<uint32_t, 3>, unsigned, Vec3Hash> index;
-    index.reserve(n * 2);
+    std::sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+    const float thresh = 0.0001f;
+    const float inv_size = (float)(1.0 / thresh);
+    std::unordered_map<std::array<int32_t, 3>, unsigned, CellHash> grid;
+    grid.reserve(n * 2);
     vertices.clear(); faces.clear();
     vertices.reserve(n); faces.reserve(n);
-    for (const auto& k : keys) {
+    if (colors) { colors->clear(); colors->reserve(n); }
+    for (unsigned t : order) {
+        const HkfVertex* tv = &soup[t].v0;
         std::array<unsigned, 3> f;
         for (int i = 0; i < 3; ++i) {
-            const std::array<float, 3> p = { k[i * 3], k[i * 3 + 1], k[i * 3 + 2] };
-            const std::array<uint32_t, 3> bits = { float_bits(p[0]), float_bits(p[1]), float_bits(p[2]) };
-            auto it = index.find(bits);
-            if (it == index.end()) { it = index.emplace(bits, (unsigned)vertices.size()).first; vertices.push_back(p); }
-            f[i] = it->second;
+            const float* p = tv[i].pos;
+            const std::array<int32_t, 3> cell = { virtual_cell(p[0], inv_size), virtual_cell(p[1], inv_size), virtual_cell(p[2], inv_size) };
+            unsigned id = ~0u;
+            for (int a = -1; a <= 1 && id == ~0u; ++a)
+                for (int b = -1; b <= 1 && id == ~0u; ++b)
+                    for (int c = -1; c <= 1; ++c) {
+                        auto it = grid.find({ cell[0] + a, cell[1] + b, cell[2] + c });
+                        if (it != grid.end()) { id = it->second; break; }
+                    }
+            if (id == ~0u) {
+                id = (unsigned)vertices.size();
+                grid.emplace(cell, id);
+                vertices.push_back({ p[0], p[1], p[2] });
+                if (colors) colors->push_back({ tv[i].color[2], tv[i].color[1], tv[i].color[0], 1.0f });   // (z, y, x, 1): BGR -> RGB, :53-55
+            }
+            f[i] = id;
         }
-        if (f[0] == f[1] || f[1] == f[2] || f[0] == f[2]) continue;                 // degenerate after welding
+        if (f[0] == f[1] || f[1] == f[2] || f[0] == f[2]) continue;                 // removeDegeneratedFaces
         faces.push_back(f);
     }
-    // duplicate faces (same vertex set) are dropped, as ml::MeshData::removeDuplicateFaces does; the first in canonical
-    // order stays
-    std::unordered_map<std::array<uint32_t, 3>, bool, Vec3Hash> seen;
+    // removeDuplicateFaces: same vertex set, the first one stays
+    std::unordered_map<std::array<uint32_t, 3>, bool, FaceHash> seen;
     seen.reserve(faces.size() * 2);
     std::vector<std::array<unsigned, 3>> uniq;
     uniq.reserve(faces.size());
@@ -100,9 +132,10 @@ void MeshGeneratorMarchingcube::vertexNormals(const std::vector<std::array<float
                                               std::vector<std::array<float, 3>>& normals)
 {
     auto unit = [](std::array<float, 3> n) {
-        const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-        if (len < 1e-8f) return std::array<float, 3>{ 0.f, 0.f, 0.f };              // normalize() of src/cuda/cuda_declar.h:89-94
-        return std::array<float, 3>{ n[0] / len, n[1] / len, n[2] / len };
+        const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);       // dot() order x, y, z (cuda_declar.h)
+        if (len < 1e-8) return std::array<float, 3>{ 0.f, 0.f, 0.f };               // normalize() of src/cuda/cuda_declar.h:89-94
+        const float r = (float)(1.0 / len);                                         // v * (1.0 / len): the double quotient narrowed
+        return std::array<float, 3>{ n[0] * r, n[1] * r, n[2] * r };
     };
     normals.assign(v.size(), { 0.f, 0.f, 0.f });
     for (const auto& f : faces) {
@@ -148,8 +181,11 @@ private:
 }
 
 bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std::vector<std::array<float, 3>>& v,
-                                          const std::vector<std::array<unsigned, 3>>& faces, const std::vector<std::array<float, 3>>& normals)
+                                          const std::vector<std::array<unsigned, 3>>& faces, const std::vector<std::array<float, 3>>& normals,
+                                          const std::vector<std::array<float, 4>>* colors)
 {
+    const bool with_c = colors && colors->size() == v.size();
+    auto byte_of = [](float c) { const float x = c * 255.0f + 0.5f; return (unsigned)(x < 0.f ? 0.f : x > 255.f ? 255.f : x); };
     const size_t dot = filename.find_last_of('.');
     std::string ext = dot == std::string::npos ? "" : filename.substr(dot + 1);
     for (auto& ch : ext) ch = (char)std::tolower((unsigned char)ch);
@@ -164,10 +200,12 @@ bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std
     if (ext == "ply") {
         std::fprintf(f, "ply\nformat ascii 1.0\ncomment hybKinectfu marching-cubes mesh\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z\n", v.size());
         if (with_n) std::fprintf(f, "property float nx\nproperty float ny\nproperty float nz\n");
+        if (with_c) std::fprintf(f, "property uchar red\nproperty uchar green\nproperty uchar blue\n");
         std::fprintf(f, "element face %zu\nproperty list uchar int vertex_indices\nend_header\n", faces.size());
         for (size_t i = 0; i < v.size(); ++i) {
-            vec3("", v[i], 9, with_n ? "" : "\n");
-            if (with_n) vec3(" ", normals[i], 6, "\n");
+            vec3("", v[i], 9, (with_n || with_c) ? "" : "\n");
+            if (with_n) vec3(" ", normals[i], 6, with_c ? "" : "\n");
+            if (with_c) { const auto& c = (*colors)[i]; o.str(" "); o.num(byte_of(c[0])); o.str(" "); o.num(byte_of(c[1])); o.str(" "); o.num(byte_of(c[2])); o.str("\n"); }
         }
         for (const auto& t : faces) { o.str("3 "); o.num(t[0]); o.str(" "); o.num(t[1]); o.str(" "); o.num(t[2]); o.str("\n"); o.maybe_flush(); }
     } else if (ext == "off") {
@@ -176,7 +214,10 @@ bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std
         for (const auto& t : faces) { o.str("3 "); o.num(t[0]); o.str(" "); o.num(t[1]); o.str(" "); o.num(t[2]); o.str("\n"); o.maybe_flush(); }
     } else {
         std::fprintf(f, "# hybKinectfu marching-cubes mesh\n# vertices %zu\n# faces %zu\n", v.size(), faces.size());
-        for (const auto& p : v) vec3("v ", p, 9, "\n");
+        for (size_t i = 0; i < v.size(); ++i) {
+            vec3("v ", v[i], 9, with_c ? "" : "\n");
+            if (with_c) { const auto& c = (*colors)[i]; vec3(" ", { c[0], c[1], c[2] }, 6, "\n"); }     // the common "v x y z r g b" extension
+        }
         if (with_n) for (const auto& n : normals) vec3("vn ", n, 6, "\n");
         for (const auto& t : faces) {
             o.str("f ");
@@ -195,8 +236,9 @@ bool MeshGeneratorMarchingcube::writeMesh(const std::string& filename, const std
 bool MeshGeneratorMarchingcube::saveMesh(const std::string& filename)
 {
     if (!copyTrianglesToCPU()) { std::cout << "copy triangles to cpu failed" << std::endl; return false; }
-    weld(_soup, _vertices, _faces);
+    const bool color = AppParams::instance()->_switch_params.useRGBData;
+    weld(_soup, _vertices, _faces, color ? &_colors : nullptr);
     vertexNormals(_vertices, _faces, _normals);
     std::cout << "vertices :\t" << _vertices.size() << "\nfaces :\t" << _faces.size() << std::endl;
-    return writeMesh(filename, _vertices, _faces, _normals);
+    return writeMesh(filename, _vertices, _faces, _normals, color ? &_colors : nullptr);
 }

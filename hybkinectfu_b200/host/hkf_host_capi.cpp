@@ -43,6 +43,11 @@ void hkfhost_synth_render(const double* pose16, unsigned cols, unsigned rows, fl
     CameraParams cam; cam.cols = cols; cam.rows = rows; cam.cx = cx; cam.cy = cy; cam.fx = fx; cam.fy = fy;
     DataSourceProducerSynthetic::renderDepthMm(pose16, cam, out);
 }
+void hkfhost_synth_render_color(const double* pose16, unsigned cols, unsigned rows, float cx, float cy, float fx, float fy, uint8_t* out)
+{
+    CameraParams cam; cam.cols = cols; cam.rows = rows; cam.cx = cx; cam.cy = cy; cam.fx = fx; cam.fy = fy;
+    DataSourceProducerSynthetic::renderColor(pose16, cam, out);
+}
 int hkfhost_write_tum(const char* path, unsigned n, double phase, double volume_size, double trunc_min)
 {
     return DataSourceProducerSynthetic::writeTumTrajectory(path, n, phase, volume_size, trunc_min) ? 0 : 1;
@@ -130,6 +135,27 @@ int hkfhost_weld(const HkfTriangle* soup, unsigned n, const char* obj_path, unsi
     return 0;
 }
 
+// the indexed mesh itself (for the comparison with the reference's ml::MeshData, tests/test_mesh_reference.py): arrays sized
+// by the caller for 3 n vertices / n faces
+int hkfhost_weld_arrays(const HkfTriangle* soup, unsigned n, int use_color, unsigned* n_vertices, unsigned* n_faces,
+                        float* vertices3, float* normals3, float* colors4, unsigned* faces3)
+{
+    std::vector<HkfTriangle> s(soup, soup + n);
+    std::vector<std::array<float, 3>> v, nrm;
+    std::vector<std::array<unsigned, 3>> f;
+    std::vector<std::array<float, 4>> col;
+    MeshGeneratorMarchingcube::weld(s, v, f, use_color ? &col : nullptr);
+    MeshGeneratorMarchingcube::vertexNormals(v, f, nrm);
+    *n_vertices = (unsigned)v.size(); *n_faces = (unsigned)f.size();
+    for (size_t i = 0; i < v.size(); ++i) {
+        std::memcpy(vertices3 + 3 * i, v[i].data(), 12);
+        std::memcpy(normals3 + 3 * i, nrm[i].data(), 12);
+        if (use_color) std::memcpy(colors4 + 4 * i, col[i].data(), 16);
+    }
+    for (size_t i = 0; i < f.size(); ++i) std::memcpy(faces3 + 3 * i, f[i].data(), 12);
+    return 0;
+}
+
 // ---- the whole pipeline through MainController / HybKinectfu (needs a B200)
 int hkfhost_init(const char* config_path, int device)
 {
@@ -137,14 +163,25 @@ int hkfhost_init(const char* config_path, int device)
     return 0;
 }
 // process one externally supplied frame through HybKinectfu::processNewFrame
+static int process_frame(const uint16_t* depth_mm, const uint8_t* bgr, unsigned cols, unsigned rows, unsigned frame_id, double timestamp, float* pose_out16, int* status);
 int hkfhost_process(const uint16_t* depth_mm, unsigned cols, unsigned rows, unsigned frame_id, double timestamp, float* pose_out16, int* status)
+{
+    return process_frame(depth_mm, nullptr, cols, rows, frame_id, timestamp, pose_out16, status);
+}
+// the same with a colour frame of the rgb camera's size (use_color=1)
+int hkfhost_process_color(const uint16_t* depth_mm, const uint8_t* bgr, unsigned cols, unsigned rows, unsigned frame_id, double timestamp, float* pose_out16, int* status)
+{
+    return process_frame(depth_mm, bgr, cols, rows, frame_id, timestamp, pose_out16, status);
+}
+static int process_frame(const uint16_t* depth_mm, const uint8_t* bgr, unsigned cols, unsigned rows, unsigned frame_id, double timestamp, float* pose_out16, int* status)
 {
     HybKinectfu* k = MainController::instance()->fusioner();
     if (!k) { g_err = "not initialised"; return 1; }
     DepthFrameData d(frame_id);
     ColorFrameData rgb(frame_id);
     d.setFrameData(depth_mm, (int)cols, (int)rows, timestamp);
-    rgb.setFrameData(nullptr, 0, 0, timestamp);
+    const CameraParams& rc = AppParams::instance()->_rgb_camera_params;
+    if (bgr) rgb.setFrameData(bgr, (int)rc.cols, (int)rc.rows, timestamp); else rgb.setFrameData(nullptr, 0, 0, timestamp);
     if (!k->processNewFrame(d, rgb)) { g_err = std::string("processNewFrame: ") + hkf_last_error(CudaDeviceDataMan::instance()->ctx()); return 2; }
     if (pose_out16) std::memcpy(pose_out16, k->cameraPose().m, 64);
     if (status) *status = k->lastTrackingStatus();

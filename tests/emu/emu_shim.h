@@ -38,6 +38,12 @@ static inline int __float2int_rz(float a)
     if (a <= -2147483648.0f) return (-2147483647 - 1);
     return (int)a;
 }
+static inline unsigned __float2uint_rz(float a)
+{   // cvt.rzi.u32.f32: saturating, NaN -> 0
+    if (a != a || a <= 0.0f) return 0u;
+    if (a >= 4294967296.0f) return 0xffffffffu;
+    return (unsigned)a;
+}
 static inline int __double2int_rz(double a)
 {
     if (a != a) return 0;

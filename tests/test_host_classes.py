@@ -33,15 +33,15 @@ def host():
 
 
 def write_ini(path, cols=192, rows=144, res=128, levels=3, sdf=0, fromfile=0, stepwise=0, record=0, traj_in="", traj_out="", mesh="", frames=200,
-              synthetic=1, dataset=0, source=""):
+              synthetic=1, dataset=0, source="", color=0, angle=0):
     cam = synth.Camera().scaled(cols, rows)
     open(path, "w").write(f"""[switch]
-use_color=0
+use_color={color}
 record_rgbd=0
 read_rgbd_from_rgbddataset={dataset}
 record_trajectory={record}
 read_trajactory_from_file={fromfile}
-color_angle_weight=0
+color_angle_weight={angle}
 use_sdf_tracker={sdf}
 use_synthetic_data={synthetic}
 stepwise_tracking={stepwise}
@@ -138,6 +138,14 @@ def test_synthetic_producer_equals_python_synth(host):
         d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
         assert d.max() <= 1 and (d != 0).mean() < 0.01
     assert np.array_equal(synth.trajectory(50)[0], synth.pose0())
+    # the colour image of the same frames (use_color=1)
+    host.hkfhost_synth_render_color.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    want = synth.trajectory(50, 0.7)[33]
+    img = np.zeros((72, 96, 3), np.uint8)
+    host.hkfhost_synth_render_color(want.ctypes.data, 96, 72, cam.cx, cam.cy, cam.fx, cam.fy, img.ctypes.data)
+    ref = synth.render_color(want, cam)
+    d = np.abs(img.astype(np.int32) - ref.astype(np.int32)).max(-1)
+    assert (d != 0).mean() < 0.02 and img.any()          # float32 intrinsics: a few pixels on checker / surface boundaries
 
 
 def test_trajectory_record_and_replay_round_trip(host, tmp_path):
@@ -452,3 +460,55 @@ def test_main_controller_on_a_tum_format_dataset(host, pipeline, tmp_path):
     _, _, c = run_fused(small_config(128), frames, 2, out)
     assert bits_equal(vol, c.download(capi.BUF_VOLUME))
     c.close()
+
+
+@pytest.mark.gpu
+def test_hybkinectfu_colour_mode_equals_c_abi_path(host, pipeline, tmp_path):
+    """use_color=1 (the reference's default, config.ini:2) through HybKinectfu / MeshGeneratorMarchingcube: the volume,
+    its colours and raycast_rgb equal the C-ABI path fed the same frames; the PLY carries vertex colours"""
+    import dataclasses
+    from conftest import small_config
+    # 640x480: the reference's colour pixel uses hard-coded 525 / 320 / 240 intrinsics (integrateVolume.cu:56-57), so a
+    # scaled-down camera would colour - and, with use_color, integrate - only a strip of the volume
+    cam = synth.Camera()
+    gt = synth.trajectory(200)[::4][:5]
+    frames = np.stack([synth.render_depth_mm(p, cam) for p in gt])
+    bgr = np.stack([synth.render_color(p, cam) for p in gt])
+    ini = tmp_path / "config.ini"
+    write_ini(str(ini), cols=640, rows=480, color=1, angle=1, mesh=str(tmp_path / "mesh.ply"))
+    assert host.hkfhost_init(str(ini).encode(), 0) == 0, host.hkfhost_last_error()
+    host.hkfhost_process_color.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_void_p, C.c_void_p]
+    poses = []
+    for i, mm in enumerate(frames):
+        p = np.zeros((4, 4), np.float32); st = C.c_int()
+        mm = np.ascontiguousarray(mm); im = np.ascontiguousarray(bgr[i])
+        assert host.hkfhost_process_color(mm.ctypes.data, im.ctypes.data, 640, 480, i, i / 30.0, p.ctypes.data, C.byref(st)) == 0, host.hkfhost_last_error()
+        assert st.value == 0
+        poses.append(p)
+    lib = capi.load()
+    h = C.c_void_p(host.hkfhost_ctx())
+    vol = np.zeros((128, 128, 128, 2), np.float32); col = np.zeros((128, 128, 128, 4), np.uint8); rgb = np.zeros((480, 640, 3), np.uint8)
+    assert lib.hkf_download(h, capi.BUF_VOLUME, 0, vol.ctypes.data, vol.nbytes) == vol.nbytes
+    assert lib.hkf_download(h, capi.BUF_VOLUME_COLOR, 0, col.ctypes.data, col.nbytes) == col.nbytes
+    assert lib.hkf_download(h, capi.BUF_RAYCAST_RGB, 0, rgb.ctypes.data, rgb.nbytes) == rgb.nbytes
+    ntri, nv, nf = C.c_uint(), C.c_uint(), C.c_uint()
+    assert host.hkfhost_mesh(str(tmp_path / "mesh.ply").encode(), C.byref(ntri), C.byref(nv), C.byref(nf)) == 0
+    host.hkfhost_release()
+    cfg = dataclasses.replace(capi.Config(resolution=128, max_triangles=400000), use_color=1, color_angle_weight=1)
+    with capi.Context(cfg) as c:
+        c.set_pose(synth.pose0().astype(np.float32))
+        for i, mm in enumerate(frames):
+            c.preprocess(mm); c.upload_color(bgr[i])
+            if i:
+                c.icp_track()
+            c.integrate_tracked(); c.raycast_tracked()
+            p, st = c.frame_result()
+            assert st == 0 and bits_equal(p, poses[i])
+        assert bits_equal(c.download(capi.BUF_VOLUME), vol)
+        assert (c.download(capi.BUF_VOLUME_COLOR) == col).all() and col[..., :3].any()
+        assert (c.download(capi.BUF_RAYCAST_RGB) == rgb).all() and rgb.any()
+        assert c.marching_cubes() == ntri.value
+    lines = open(tmp_path / "mesh.ply").read().splitlines()
+    assert "property uchar red" in lines and f"element vertex {nv.value}" in lines
+    body = lines[lines.index("end_header") + 1:]
+    assert len(body[0].split()) == 9 and any(int(x) > 0 for x in body[0].split()[6:])

@@ -1,3 +1,2 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_color.py -m gpu -x -q 2>&1 | tail -15
-timeout 900 python -m pytest tests/test_gpu_stages.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_host_classes.py tests/test_mesh_reference.py -m gpu -x -q -s 2>&1 | tail -15
