@@ -22,35 +22,6 @@
 
 static thread_local std::string g_create_err;
 
-// one block per 32x8-pixel tile publishes the tile's depth extrema (hkf_internal.cuh: DepthBounds)
-__global__ void __launch_bounds__(HKF_TILE_W * HKF_TILE_H)
-k_depth_bounds(const float* __restrict__ d, int cols, int rows, DepthBounds B)
-{
-    __shared__ unsigned s_max[HKF_TILE_W * HKF_TILE_H / 32], s_min[HKF_TILE_W * HKF_TILE_H / 32];
-    const int x = blockIdx.x * HKF_TILE_W + threadIdx.x, y = blockIdx.y * HKF_TILE_H + threadIdx.y;
-    const int tid = threadIdx.y * HKF_TILE_W + threadIdx.x;
-    const bool in = (x < cols && y < rows);
-    const unsigned b = in ? __float_as_uint(fmaxf(d[(size_t)y * cols + x], 0.f)) : 0u;
-    const unsigned mx = __reduce_max_sync(0xffffffffu, b);
-    const unsigned mn = __reduce_min_sync(0xffffffffu, in ? b : 0xffffffffu);
-    if ((tid & 31) == 0) { s_max[tid >> 5] = mx; s_min[tid >> 5] = mn; }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned a = 0, i0 = 0xffffffffu;
-        for (int i = 0; i < HKF_TILE_W * HKF_TILE_H / 32; ++i) { a = max(a, s_max[i]); i0 = min(i0, s_min[i]); }
-        hkf_bounds_publish(B, blockIdx.x, blockIdx.y, a, i0);
-    }
-}
-
-int hkf_depth_bounds(hkf_ctx* c)
-{
-    HKF_CUDA(c, cudaMemsetAsync(c->bounds.base, 0, c->bounds_zero_bytes, c->stream));
-    dim3 b(HKF_TILE_W, HKF_TILE_H), g(c->bounds.tx[0], c->bounds.tiles_y);
-    k_depth_bounds<<<g, b, 0, c->stream>>>(c->trunc_depth, (int)c->cols[0], (int)c->rows[0], c->bounds);
-    HKF_LAUNCH_CHECK(c);
-    return HKF_OK;
-}
-
 extern "C" const char* hkf_last_error(const hkf_ctx* c)
 {
     if (!c) return g_create_err.c_str();
@@ -64,9 +35,9 @@ static void free_all(hkf_ctx* c)
     if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
     if (c->ev_pre_done) cudaEventDestroy(c->ev_pre_done);
     if (c->ev_swap) cudaEventDestroy(c->ev_swap);
-    cudaFree(c->back.depth_mm); cudaFree(c->back.raw_depth); cudaFree(c->back.trunc_depth); cudaFree(c->back.filtered_depth); cudaFree(c->back.bounds.base);
+    cudaFree(c->back.depth_mm); cudaFree(c->back.raw_depth); cudaFree(c->back.trunc_depth); cudaFree(c->back.filtered_depth); cudaFree(c->back.bounds.base); cudaFree(c->back.bounds.tab);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->back.new_v[l]); cudaFree(c->back.new_n[l]); }
-    cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base);
+    cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base); cudaFree(c->bounds.tab);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
     cudaFree(c->color); cudaFree(c->raw_rgb); cudaFree(c->raycast_rgb);
     cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
@@ -121,16 +92,13 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     CREATE_CUDA(cudaMemset(c->filtered_depth, 0, n0 * sizeof(float)));
     {
         DepthBounds& B = c->bounds;
-        B.tiles_y = (int)div_up(c->rows[0], HKF_TILE_H);
-        int off = 4;                                         // [0] = frame maximum, [1..3] padding
-        for (int l = HKF_BOUND_LEVELS - 1; l >= 0; --l) {    // coarse levels first: they are the cleared prefix
-            B.tx[l] = (int)div_up(c->cols[0], HKF_TILE_W << l);
-            B.off_max[l] = off; off += B.tiles_y * B.tx[l];
-            B.off_min[l] = off; off += B.tiles_y * B.tx[l];
-            if (l == 1) c->bounds_zero_bytes = (size_t)off * sizeof(unsigned);
-        }
-        CREATE_CUDA(cudaMalloc(&B.base, (size_t)off * sizeof(unsigned)));
-        CREATE_CUDA(cudaMemset(B.base, 0, (size_t)off * sizeof(unsigned)));
+        B.tx = (int)div_up(c->cols[0], HKF_BT); B.ty = (int)div_up(c->rows[0], HKF_BT);
+        c->bounds_zero_bytes = 4 * sizeof(unsigned);
+        c->bounds_tab_bytes = (size_t)HKF_BKX * HKF_BKY * B.tx * B.ty * sizeof(uint2);
+        CREATE_CUDA(cudaMalloc(&B.base, c->bounds_zero_bytes));
+        CREATE_CUDA(cudaMemset(B.base, 0, c->bounds_zero_bytes));
+        CREATE_CUDA(cudaMalloc(&B.tab, c->bounds_tab_bytes));
+        CREATE_CUDA(cudaMemset(B.tab, 0, c->bounds_tab_bytes));
     }
     CREATE_CUDA(cudaMalloc(&c->ray_keys, 2 * n0 * sizeof(unsigned long long)));   // own keys | composited keys
     CREATE_CUDA(cudaMalloc(&c->ray_payload, n0 * 8 * sizeof(float)));

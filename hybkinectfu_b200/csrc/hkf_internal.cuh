@@ -22,20 +22,25 @@
 
 struct DMat44 { float m[16]; };
 
-// Depth extrema of the current truncated depth map over pixel tiles of 8 rows x (32 << level) columns,
-// level = 0..3.  One unsigned array: [0] = float bits of the frame's largest valid depth, then per level the
-// largest valid depth of each tile (float bits; 0 = no valid pixel) and the INVERTED bits of the smallest depth
-// with invalid pixels counted as 0 (so that zero-initialised storage + atomicMax implements the minimum).
-// Level 0 tiles are owned by exactly one producer block (plain stores); coarser levels are merged with atomics
-// and therefore cleared before each frame.
+// Depth extrema of the current truncated depth map for range queries (integration chunk classification).  Base tiles are
+// 8 x 8 pixels; tab holds, for window sizes of 2^kx x 2^ky base tiles (kx < HKF_BKX, ky < HKF_BKY), the extrema of the
+// window whose top-left tile is (x, y) - a sparse table, so that the extrema over ANY rectangle of up to 32 x 8 tiles
+// (256 x 64 pixels) are the combination of four overlapping power-of-two windows: four 8-byte loads, no loop.
+// An entry is {float bits of the largest valid depth (0 = no valid pixel), INVERTED bits of the smallest depth with
+// invalid pixels counted as 0}.  Level (0,0) is written by the producers of the truncated depth (plain stores: every
+// base tile belongs to one producer block), the other levels by k_bounds_rmq; base[0] = float bits of the frame's
+// largest valid depth (atomicMax, cleared before each frame).
+// (Round 1 / early round 2 kept extrema of 32 x 8 pixel tiles and three coarser levels and looped over up to 4 x 4 of
+// them per chunk: looser bounds and most of the classification pass's instructions, profiles/r2_integrate_*.)
 #define HKF_TILE_W 32
 #define HKF_TILE_H 8
-#define HKF_BOUND_LEVELS 4
+#define HKF_BT 8
+#define HKF_BKX 6
+#define HKF_BKY 4
 struct DepthBounds {
     unsigned* base;
-    int tiles_y;
-    int tx[HKF_BOUND_LEVELS];
-    int off_max[HKF_BOUND_LEVELS], off_min[HKF_BOUND_LEVELS];
+    uint2* tab;          // [(kx * HKF_BKY + ky)][ty][tx]
+    int tx, ty;          // base tiles per row / per column
 };
 
 // device-resident per-frame state shared by the fused kernels
@@ -108,7 +113,8 @@ struct hkf_ctx {
     float* trunc_depth = nullptr;
     float* filtered_depth = nullptr;
     DepthBounds bounds{};             // per-tile depth extrema of the current frame (integration chunk classification)
-    size_t bounds_zero_bytes = 0;     // prefix of bounds.base that is cleared before each frame
+    size_t bounds_zero_bytes = 0;     // prefix of bounds.base that is cleared before each frame (the frame maximum)
+    size_t bounds_tab_bytes = 0;      // size of bounds.tab
     float4* new_v[HKF_MAX_LEVELS]{};
     float4* new_n[HKF_MAX_LEVELS]{};
     float4* model_v[HKF_MAX_LEVELS]{};
@@ -224,22 +230,10 @@ void hkf_shard_release(hkf_ctx* c);
 int hkf_shard_allreduce_sums(hkf_ctx* c);
 int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream = nullptr, bool track_begin = false);
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
+int hkf_bounds_rmq(hkf_ctx* c, const DepthBounds& B, cudaStream_t stream);   // the coarser levels of the range-query table
 
 // ---------------------------------------------------------------- device arithmetic contract
 #if defined(__CUDACC__) || defined(HKF_EMULATE_DEVICE)
-
-// a producer block publishes the extrema (float bits, mn with invalid = 0) of level-0 tile (tx0, ty)
-__device__ __forceinline__ void hkf_bounds_publish(const DepthBounds& B, int tx0, int ty, unsigned mx, unsigned mn)
-{
-    B.base[B.off_max[0] + ty * B.tx[0] + tx0] = mx;
-    B.base[B.off_min[0] + ty * B.tx[0] + tx0] = ~mn;
-#pragma unroll
-    for (int l = 1; l < HKF_BOUND_LEVELS; ++l) {
-        atomicMax(&B.base[B.off_max[l] + ty * B.tx[l] + (tx0 >> l)], mx);
-        atomicMax(&B.base[B.off_min[l] + ty * B.tx[l] + (tx0 >> l)], ~mn);
-    }
-    if (mx) atomicMax(&B.base[0], mx);
-}
 
 // (int)(p + 0.5) as the reference compiles it: the literal 0.5 is a double, so the add is in
 // fp64 and the cast truncates toward zero (src/cuda/DepthCamera.h:39-43;

@@ -172,8 +172,9 @@ __device__ __forceinline__ uint4 make_general_item(const IntegrateArgs& A, int y
 //
 // Chunk classification.  The voxel centres of a 4-row x 32-voxel chunk form a planar rectangle; while Z > 0 its
 // image is the convex hull of its four projected corners, and depth along it is extremal at a corner.  The
-// bounding box of the corners, grown by 1.5 px, touches at most INT_SPAN + 1 tiles per tile row at the level whose tile
-// width covers it.  From the depth extrema of those tiles:
+// bounding box of the corners, grown by 1.5 px, is looked up in the range-query table of 8 x 8 pixel tiles
+// (hkf_internal.cuh: DepthBounds; boxes of more than 256 x 64 pixels stay general).  From the depth extrema of the tiles
+// it touches:
 //   dead : the nearest corner is farther than trunc behind the largest valid depth -> "sdf > -trunc"
 //          (integrateVolume.cu:64) fails for every voxel, the chunk is dropped;
 //   free : the box lies in the image interior, every pixel of the tiles is valid and < fMaxIntegrateDist, and the
@@ -182,10 +183,6 @@ __device__ __forceinline__ uint4 make_general_item(const IntegrateArgs& A, int y
 //   else : general, decided voxel by voxel in pass 2 with the reference's arithmetic.
 #define INT_GB 64                      // row groups per block of pass 1
 
-// A chunk's pixel box may span up to INT_SPAN tile widths of the level it is tested on (up to INT_SPAN+1 tiles per
-// tile row): finer tiles = tighter depth extrema.  Measured on the bench scene: 19.0 M general voxel slots with 3
-// instead of 21.7 M with 1, integration 144.8 -> 142.5 us (profiles/r2_experimental.log).
-#define INT_SPAN 3
 // NOFREE (colour integration): every updated voxel needs its colour pixel, so the projection-free class is not used.
 template <bool FROM_STATE, bool NOFREE>
 __global__ void __launch_bounds__(256, 5)
@@ -257,22 +254,18 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __res
                 if (zn >= 0.05f) {
                     const float u0 = fminf(pu0, qu0) - 1.5f, u1 = fmaxf(pu1, qu1) + 1.5f;
                     const float v0 = fminf(pv0, qv0) - 1.5f, v1 = fmaxf(pv1, qv1) + 1.5f;
-                    const float w = u1 - u0;
-                    const int lvl = w <= (float)(INT_SPAN * HKF_TILE_W) ? 0 : w <= (float)(INT_SPAN * 2 * HKF_TILE_W) ? 1 : w <= (float)(INT_SPAN * 4 * HKF_TILE_W) ? 2
-                                  : w <= (float)(INT_SPAN * 8 * HKF_TILE_W) ? 3 : -1;
-                    const int ty0 = max((int)floorf(v0 * (1.0f / HKF_TILE_H)), 0);
-                    const int ty1 = min((int)floorf(v1 * (1.0f / HKF_TILE_H)), A.B.tiles_y - 1);
-                    if (lvl >= 0 && ty1 - ty0 <= 3) {
-                        const float inv_w = 1.0f / (float)(HKF_TILE_W << lvl);
-                        const int tx0 = max((int)floorf(u0 * inv_w), 0);
-                        const int tx1 = min((int)floorf(u1 * inv_w), A.B.tx[lvl] - 1);
-                        unsigned mx = 0, mninv = 0;
-                        for (int ty = ty0; ty <= ty1; ++ty)
-                            for (int tx = tx0; tx <= tx1; ++tx) {
-                                mx = max(mx, __ldg(A.B.base + A.B.off_max[lvl] + ty * A.B.tx[lvl] + tx));
-                                mninv = max(mninv, __ldg(A.B.base + A.B.off_min[lvl] + ty * A.B.tx[lvl] + tx));
-                            }
-                        const float dmx = __uint_as_float(mx), dmn = __uint_as_float(~mninv);   // NaN if no tile was read
+                    // extrema over the base tiles the box touches: four overlapping power-of-two windows of the table
+                    const int tx0 = max((int)floorf(u0 * (1.0f / HKF_BT)), 0), tx1 = min((int)floorf(u1 * (1.0f / HKF_BT)), A.B.tx - 1);
+                    const int ty0 = max((int)floorf(v0 * (1.0f / HKF_BT)), 0), ty1 = min((int)floorf(v1 * (1.0f / HKF_BT)), A.B.ty - 1);
+                    const int w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
+                    if (w >= 1 && h >= 1 && w <= (1 << (HKF_BKX - 1)) && h <= (1 << (HKF_BKY - 1))) {
+                        const int kx = 31 - __clz(w), ky = 31 - __clz(h);
+                        const uint2* t = A.B.tab + (size_t)(kx * HKF_BKY + ky) * ((size_t)A.B.tx * A.B.ty);
+                        const int xb = tx1 - (1 << kx) + 1, yb = ty1 - (1 << ky) + 1;
+                        const uint2 e0 = __ldg(t + (size_t)ty0 * A.B.tx + tx0), e1 = __ldg(t + (size_t)ty0 * A.B.tx + xb);
+                        const uint2 e2 = __ldg(t + (size_t)yb * A.B.tx + tx0), e3 = __ldg(t + (size_t)yb * A.B.tx + xb);
+                        const unsigned mx = max(max(e0.x, e1.x), max(e2.x, e3.x)), mninv = max(max(e0.y, e1.y), max(e2.y, e3.y));
+                        const float dmx = __uint_as_float(mx), dmn = __uint_as_float(~mninv);
                         const bool interior = u0 >= 1.0f && u1 <= (float)(A.cols - 2) && v0 >= 1.0f && v1 <= (float)(A.rows - 2);
                         if (zn >= dmx + thr_dead || dmn >= A.maxdist) cls = 0;     // behind everything / nothing integrable there
                         else if (!NOFREE && interior && dmn > 0.f && dmx < A.maxdist && dmn - zf >= thr_free) cls = 2;
@@ -399,26 +392,28 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
         __syncwarp();
     }
 
-    // ---- free bricks.  fi = next brick to consume, fp = next brick to request (both strided by nwarps)
-    unsigned fi = wid, fp = wid, phase = 0;
-    auto free_issue = [&]() {
-        if (fp < n_free) {
-            if (lane == 0) {
-                const uint4 it = __ldg(items + fp);
-                const unsigned off = (it.w >> 8) & 0xffu, bytes = it.w >> 16;
-                const float2* src = vol + ((size_t)it.x * 4u + off);
-                mbar_expect_tx(bar, INT_G * bytes);
+    // ---- free bricks.  fi = the brick in flight (next to consume), strided by nwarps; `pend` = its work item.  The item of
+    // the brick after it is fetched at the START of a consume and used at its end, so that neither the consume nor the
+    // next request waits for an item load (7 % of the kernel's stall samples before: profiles/r2_integrate_e_rmq.txt).
+    unsigned fi = wid, phase = 0;
+    uint4 pend = make_uint4(0u, 0u, 0u, 0u);
+    auto free_issue = [&](const uint4& it) {
+        if (lane == 0) {
+            const unsigned off = (it.w >> 8) & 0xffu, bytes = it.w >> 16;
+            const float2* src = vol + ((size_t)it.x * 4u + off);
+            mbar_expect_tx(bar, INT_G * bytes);
 #pragma unroll
-                for (int r = 0; r < INT_G; ++r) bulk_g2s(stage + r * INT_SEG + off, src + (size_t)r * R, bytes, bar);
-            }
-            fp += nwarps;
-#ifdef HKF_EMULATE_DEVICE
-            __syncwarp();                     // the host build copies synchronously on lane 0's thread
-#endif
+            for (int r = 0; r < INT_G; ++r) bulk_g2s(stage + r * INT_SEG + off, src + (size_t)r * R, bytes, bar);
         }
+#ifdef HKF_EMULATE_DEVICE
+        __syncwarp();                         // the host build copies synchronously on lane 0's thread
+#endif
     };
     auto free_consume = [&]() {
-        const uint4 cur = __ldg(items + fi);
+        const uint4 cur = pend;
+        const bool more = fi + nwarps < n_free;
+        uint4 nx = cur;
+        if (more) nx = __ldg(items + (fi + nwarps));
         const int rel = lane - (int)(cur.z & 0xffu);
         const unsigned span = ((cur.z >> 8) & 0xffu) - (cur.z & 0xffu);
         const unsigned fre = cur.w & 15u;
@@ -453,9 +448,13 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
             __syncwarp();                     // every lane has read the stage: it may be refilled
         }
         fi += nwarps;
-        if (!COUNT_ONLY) free_issue();
+        pend = nx;
+        if (!COUNT_ONLY && more) free_issue(nx);
     };
-    if (!COUNT_ONLY) free_issue();
+    if (wid < n_free) {
+        pend = __ldg(items + wid);
+        if (!COUNT_ONLY) free_issue(pend);
+    }
     const unsigned my_free = wid < n_free ? (n_free - wid + nwarps - 1) / nwarps : 0u;
     const unsigned my_gen = wid < n_gen ? (n_gen - wid + nwarps - 1) / nwarps : 0u;
     unsigned credit = 0;

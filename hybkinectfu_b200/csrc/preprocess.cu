@@ -208,6 +208,72 @@ __global__ void k_down(const float4* __restrict__ in, float4* __restrict__ out, 
 
 #define TILE_W 32
 #define TILE_H 8
+
+// ---------------------------------------------------------------- depth range-query table (integration chunk classification)
+// A producer block of 32 x 8 threads (one pixel each: warp = one row of 32 pixels) publishes the extrema of its four
+// 8 x 8 base tiles.  t = the pixel's truncated depth (0 = invalid), in_image = the pixel exists.  Call from all threads;
+// contains two block barriers.  s_ext: 8 words of shared memory.
+__device__ __forceinline__ void hkf_bounds_publish_block(const DepthBounds& B, int block_x, int block_y, float t, bool in_image, unsigned* s_ext)
+{
+    const int tid = threadIdx.y * HKF_TILE_W + threadIdx.x;
+    if (tid < 8) s_ext[tid] = (tid < 4) ? 0u : 0xffffffffu;
+    __syncthreads();
+    unsigned mx = in_image ? __float_as_uint(fmaxf(t, 0.f)) : 0u, mn = in_image ? __float_as_uint(fmaxf(t, 0.f)) : 0xffffffffu;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 7) == 0) { atomicMax(&s_ext[threadIdx.x >> 3], mx); atomicMin(&s_ext[4 + (threadIdx.x >> 3)], mn); }
+    __syncthreads();
+    if (tid < 4) {
+        const int bx = block_x * 4 + tid;
+        if (bx < B.tx && block_y < B.ty) B.tab[(size_t)block_y * B.tx + bx] = make_uint2(s_ext[tid], ~s_ext[4 + tid]);
+        if (s_ext[tid]) atomicMax(&B.base[0], s_ext[tid]);
+    }
+}
+
+// one block per 32x8-pixel tile publishes the depth extrema of its four 8x8 base tiles (hkf_internal.cuh: DepthBounds)
+__global__ void __launch_bounds__(HKF_TILE_W * HKF_TILE_H)
+k_depth_bounds(const float* __restrict__ d, int cols, int rows, DepthBounds B)
+{
+    __shared__ unsigned s_ext[8];
+    const int x = blockIdx.x * HKF_TILE_W + threadIdx.x, y = blockIdx.y * HKF_TILE_H + threadIdx.y;
+    const bool in = (x < cols && y < rows);
+    hkf_bounds_publish_block(B, blockIdx.x, blockIdx.y, in ? d[(size_t)y * cols + x] : 0.f, in, s_ext);
+}
+
+// The coarser levels of the range-query table from the base tiles: block (y, ky) reduces the 2^ky tile rows below y
+// column by column into shared memory, then every thread forms the windows of 2^kx columns that start at its x.
+__global__ void __launch_bounds__(128)
+k_bounds_rmq(DepthBounds B)
+{
+    __shared__ uint2 s_col[512];
+    hkf_pdl_enter();
+    const int y = blockIdx.x, ky = blockIdx.y;
+    const int h = min(1 << ky, B.ty - y);
+    for (int x = threadIdx.x; x < B.tx; x += blockDim.x) {
+        uint2 a = make_uint2(0u, 0u);
+        for (int r = 0; r < h; ++r) {
+            const uint2 e = B.tab[(size_t)(y + r) * B.tx + x];
+            a.x = max(a.x, e.x); a.y = max(a.y, e.y);
+        }
+        s_col[x] = a;
+    }
+    __syncthreads();
+    const size_t plane = (size_t)B.tx * B.ty;
+    for (int x = threadIdx.x; x < B.tx; x += blockDim.x) {
+        uint2 a = make_uint2(0u, 0u);
+        int done = 0;
+#pragma unroll
+        for (int kx = 0; kx < HKF_BKX; ++kx) {
+            const int w = min(1 << kx, B.tx - x);
+            for (; done < w; ++done) { const uint2 e = s_col[x + done]; a.x = max(a.x, e.x); a.y = max(a.y, e.y); }
+            if (kx | ky) B.tab[(size_t)(kx * HKF_BKY + ky) * plane + (size_t)y * B.tx + x] = a;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- fused kernel B: all coarser levels
 // Thread per level-2 pixel: builds its four level-1 pixels (vertices and normals) from the 4x4
 // level-0 block, then the level-2 pixel from those, entirely in registers.  With two levels only
@@ -265,13 +331,12 @@ k_preprocess_tile(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, 
                      float thresh, DepthBounds B)
 {
     HKF_DYN_SMEM(float, smem);
-    __shared__ unsigned s_tmax[TILE_W * TILE_H / 32], s_tmin[TILE_W * TILE_H / 32];
+    __shared__ unsigned s_ext[8];
     const int ap = radius;
     const int tw = TILE_W + 2 * ap, th = TILE_H + 2 * ap;
     float* s_trunc = smem;              // tw*th, 0 outside the image
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
     const int bx0 = blockIdx.x * TILE_W, by0 = blockIdx.y * TILE_H;
-    unsigned local_max = 0, local_min = 0xffffffffu;
     for (int i = tid; i < tw * th; i += TILE_W * TILE_H) {
         int lx = i % tw, ly = i / tw;
         int gx = bx0 - ap + lx, gy = by0 - ap + ly;
@@ -282,22 +347,14 @@ k_preprocess_tile(const uint16_t* __restrict__ mm, float* __restrict__ raw_out, 
             if (lx >= ap && lx < ap + TILE_W && ly >= ap && ly < ap + TILE_H) {
                 raw_out[(size_t)gy * cols + gx] = d;
                 trunc_out[(size_t)gy * cols + gx] = t;
-                local_max = max(local_max, __float_as_uint(t));
-                local_min = min(local_min, __float_as_uint(t));
             }
         }
         s_trunc[i] = t;
     }
-    local_max = __reduce_max_sync(0xffffffffu, local_max);
-    local_min = __reduce_min_sync(0xffffffffu, local_min);
-    if ((tid & 31) == 0) { s_tmax[tid >> 5] = local_max; s_tmin[tid >> 5] = local_min; }
     __syncthreads();
-    if (tid == 0) {
-        unsigned mx = 0, mn = 0xffffffffu;
-        for (int i = 0; i < TILE_W * TILE_H / 32; ++i) { mx = max(mx, s_tmax[i]); mn = min(mn, s_tmin[i]); }
-        hkf_bounds_publish(B, blockIdx.x, blockIdx.y, mx, mn);
-    }
     const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y;
+    // depth extrema of the block's four 8x8 base tiles (thread = its own pixel of the staged tile)
+    hkf_bounds_publish_block(B, blockIdx.x, blockIdx.y, s_trunc[(threadIdx.y + ap) * tw + (threadIdx.x + ap)], x < cols && y < rows, s_ext);
     if (x >= cols || y >= rows) return;
     auto at = [&](int gx, int gy) { return s_trunc[(gy - by0 + ap) * tw + (gx - bx0 + ap)]; };
     float f;
@@ -454,6 +511,23 @@ int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream
     return HKF_OK;
 }
 
+int hkf_bounds_rmq(hkf_ctx* c, const DepthBounds& B, cudaStream_t stream)
+{
+    if (B.tx > 512) { c->err = "image wider than 4096 pixels"; return HKF_ERR_ARG; }
+    hkf_launch_pdl(k_bounds_rmq, dim3(B.ty, HKF_BKY), dim3(128), 0, stream, B);
+    HKF_LAUNCH_CHECK(c);
+    return HKF_OK;
+}
+
+int hkf_depth_bounds(hkf_ctx* c)
+{
+    HKF_CUDA(c, cudaMemsetAsync(c->bounds.base, 0, c->bounds_zero_bytes, c->stream));
+    dim3 b(HKF_TILE_W, HKF_TILE_H), g(div_up(c->cols[0], HKF_TILE_W), div_up(c->rows[0], HKF_TILE_H));
+    k_depth_bounds<<<g, b, 0, c->stream>>>(c->trunc_depth, (int)c->cols[0], (int)c->rows[0], c->bounds);
+    HKF_LAUNCH_CHECK(c);
+    return hkf_bounds_rmq(c, c->bounds, c->stream);
+}
+
 // the fused preprocess of one frame into a given set of per-frame buffers, on a given stream
 static int run_preprocess(hkf_ctx* c, cudaStream_t stream, HkfFrameSet& F, const uint16_t* depth_mm, int is_device, const HkfFrameParams* fp)
 {
@@ -474,6 +548,9 @@ static int run_preprocess(hkf_ctx* c, cudaStream_t stream, HkfFrameSet& F, const
     k_preprocess_tile<<<g, b, smem2, stream>>>(src, F.raw_depth, F.trunc_depth, F.filtered_depth, (int)c->cols[0], (int)c->rows[0], radius,
                                                fp->trunc_min, fp->trunc_max, ss, sd, thresh, F.bounds);
     HKF_LAUNCH_CHECK(c);
+    // coarser levels of the depth range-query table (integration): a tiny launch, in front of the maps so that their blocks
+    // become resident behind it
+    { const int rc = hkf_bounds_rmq(c, F.bounds, stream); if (rc != HKF_OK) return rc; }
     const bool two = c->levels >= 2, three = c->levels >= 3;
     hkf_launch_pdl(k_maps_pyramids, dim3(div_up(c->cols[0], 16), div_up(c->rows[0], 16)), dim3(256), 0, stream, (const float*)F.filtered_depth,
                    F.new_v[0], F.new_n[0], two ? F.new_v[1] : (float4*)nullptr, two ? F.new_n[1] : (float4*)nullptr,
@@ -520,9 +597,10 @@ static int alloc_back(hkf_ctx* c)
         HKF_CUDA(c, cudaMalloc(&B.new_v[l], nb)); HKF_CUDA(c, cudaMalloc(&B.new_n[l], nb));
     }
     B.bounds = c->bounds;
-    size_t nb = ((size_t)c->bounds.off_min[0] + (size_t)c->bounds.tiles_y * c->bounds.tx[0]) * sizeof(unsigned);
-    HKF_CUDA(c, cudaMalloc(&B.bounds.base, nb));
-    HKF_CUDA(c, cudaMemset(B.bounds.base, 0, nb));
+    HKF_CUDA(c, cudaMalloc(&B.bounds.base, c->bounds_zero_bytes));
+    HKF_CUDA(c, cudaMemset(B.bounds.base, 0, c->bounds_zero_bytes));
+    HKF_CUDA(c, cudaMalloc(&B.bounds.tab, c->bounds_tab_bytes));
+    HKF_CUDA(c, cudaMemset(B.bounds.tab, 0, c->bounds_tab_bytes));
     {
         int lo = 0, hi = 0;
         HKF_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));

@@ -68,6 +68,13 @@ static inline unsigned atomicMax(unsigned* p, unsigned v)
     while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return o;
 }
+static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
+static inline unsigned atomicMin(unsigned* p, unsigned v)
+{
+    unsigned o = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (o > v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
 static inline long long clock64() { return 0; }

@@ -9,23 +9,18 @@
 #include "../../hybkinectfu_b200/csrc/integrate.cu"
 
 namespace {
-struct Bounds { DepthBounds B; std::vector<unsigned> store; size_t zero_bytes; };
-// the allocation of hkf_create (context.cu): coarse levels first = the prefix cleared before each frame
+struct Bounds { DepthBounds B; std::vector<unsigned> store; std::vector<uint2> tab; size_t zero_bytes; };
+// the allocation of hkf_create (context.cu): the frame maximum + the range-query table
 Bounds make_bounds(unsigned cols, unsigned rows)
 {
     Bounds b;
     DepthBounds& B = b.B;
-    B.tiles_y = (int)div_up(rows, HKF_TILE_H);
-    int off = 4;
-    b.zero_bytes = 0;
-    for (int l = HKF_BOUND_LEVELS - 1; l >= 0; --l) {
-        B.tx[l] = (int)div_up(cols, HKF_TILE_W << l);
-        B.off_max[l] = off; off += B.tiles_y * B.tx[l];
-        B.off_min[l] = off; off += B.tiles_y * B.tx[l];
-        if (l == 1) b.zero_bytes = (size_t)off * sizeof(unsigned);
-    }
-    b.store.assign((size_t)off, 0u);
+    B.tx = (int)div_up(cols, HKF_BT); B.ty = (int)div_up(rows, HKF_BT);
+    b.zero_bytes = 4 * sizeof(unsigned);
+    b.store.assign(4, 0u);
+    b.tab.assign((size_t)HKF_BKX * HKF_BKY * B.tx * B.ty, make_uint2(0u, 0u));
     B.base = b.store.data();
+    B.tab = b.tab.data();
     return b;
 }
 }
@@ -44,6 +39,7 @@ extern "C" void* emu_frame_create(unsigned cols, unsigned rows)
     f->cols = cols; f->rows = rows;
     f->bounds = make_bounds(cols, rows);
     f->bounds.B.base = f->bounds.store.data();
+    f->bounds.B.tab = f->bounds.tab.data();
     const size_t n0 = (size_t)cols * rows;
     f->raw.assign(n0, 0.f); f->trunc.assign(n0, 0.f); f->filt.assign(n0, 0.f);
     unsigned c = cols, r = rows;
@@ -65,6 +61,7 @@ extern "C" int emu_preprocess(void* h, const uint16_t* mm, float tmin, float tma
     emu_launch(g, b, [&]() {
         k_preprocess_tile(mm, f->raw.data(), f->trunc.data(), f->filt.data(), cols, rows, radius, tmin, tmax, ss, sd, thresh, B);
     });
+    emu_launch(dim3(B.ty, HKF_BKY), dim3(128), [&]() { k_bounds_rmq(B); });
     emu_launch(dim3(div_up(f->cols, 16), div_up(f->rows, 16)), dim3(256), [&]() {
         k_maps_pyramids(f->filt.data(), f->v[0].data(), f->n[0].data(), f->v[1].data(), f->n[1].data(), f->v[2].data(), f->n[2].data(),
                         cols, rows, f->lc[1], f->lr[1], f->lc[2], f->lr[2], cx, cy, fx, fy);
