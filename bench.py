@@ -524,12 +524,61 @@ def run_c4(args, rank, world, local_rank):
     cfg = dataclasses.replace(bench_cfg(args.c4_resolution), max_triangles=1)
     W, K = args.warmup, args.steps
     frames, gt = make_sequence(W + K)
+    dev_frames = torch.from_numpy(frames.view(np.int16)).to(f"cuda:{local_rank}")
+    balance = "none"
     if world > 1:
-        ctx = shard.sharded_context(cfg, rank, world, local_rank)
+        # Slab boundaries from MEASURED work (HKF_SHARD_BALANCE=model keeps the geometric model of shard.plane_work).  The
+        # sequence is run untimed on a layout, with CUDA events around every rank's slab-local work (integration + slab
+        # raycast; the compositing, which waits for the slowest rank, is launched separately) and with the integration's
+        # per-plane work profile switched on.  Cost density of a plane = the profile's shape inside a slab, scaled so
+        # that the slab's planes add up to the slab's measured time; the next layout equalises that cost over the planes
+        # each rank STORES.  Two rounds, then the timed run.
+        import torch.distributed as dist
+        os.environ["HKF_SHARD_MANUAL_COMPOSITE"] = "1"       # the driver launches hkf_shard_composite_raycast itself
+        halo_ = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
+        plane_cost = None
+        rounds = 0 if os.environ.get("HKF_SHARD_BALANCE", "measured") == "model" else int(os.environ.get("HKF_SHARD_BALANCE_ROUNDS", "3"))
+        balance = "geometric model (shard.plane_work)"
+        for rnd in range(rounds + 1):
+            ctx = shard.sharded_context(cfg, rank, world, local_rank, plane_cost=plane_cost)
+            if rnd == rounds:
+                break
+            st_ = torch.cuda.ExternalStream(ctx.lib.hkf_stream(ctx._h), device=local_rank)
+            ctx.profile(True)
+            ctx.set_pose(synth.pose0().astype(np.float32))
+            local_ms = 0.0
+            for i in range(W + K):
+                ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev_frames.data_ptr() + i * frames[0].nbytes, 1, ctx.fp), "hkf_preprocess")
+                if i:
+                    ctx.icp_track()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st_)
+                ctx.integrate_tracked(); ctx.raycast_tracked()
+                e1.record(st_)
+                ctx._ck(ctx.lib.hkf_shard_composite_raycast(ctx._h), "composite")
+                ctx.sync()
+                if i >= W:
+                    local_ms += e0.elapsed_time(e1)
+            prof = shard.gather_plane_profile(ctx, cfg, rank, world, local_rank)
+            ctx.profile(False)
+            info = torch.tensor([local_ms, ctx.cfg.slab_z0, ctx.cfg.slab_z1], dtype=torch.float64, device=f"cuda:{local_rank}")
+            allinfo = [torch.zeros(3, dtype=torch.float64, device=f"cuda:{local_rank}") for _ in range(world)]
+            dist.all_gather(allinfo, info)
+            shape = shard.plane_cost_from_profile(prof)
+            plane_cost = np.zeros(cfg.resolution)
+            for x in allinfo:
+                ms, z0, z1 = float(x[0]), int(x[1]), int(x[2])
+                s0, s1 = max(z0 - halo_, 0), min(z1 + halo_, cfg.resolution)
+                plane_cost[z0:z1] = shape[z0:z1] * (ms / max(shape[s0:s1].sum(), 1e-12))
+            if rank == 0:
+                print(f"[c4 balance] round {rnd}: owned planes {[int(x[2]) - int(x[1]) for x in allinfo]}, slab-local ms per {K} frames "
+                      f"{[round(float(x[0]), 2) for x in allinfo]}", file=sys.stderr, flush=True)
+            ctx.close()
+            dist.barrier()
+            balance = f"measured: {rounds} untimed round(s) of the same sequence, per-slab CUDA-event times x per-plane work profile (hkf_integrate_profile)"
     else:
         ctx = capi.Context(cfg, device=local_rank)
     stream = torch.cuda.ExternalStream(ctx.lib.hkf_stream(ctx._h), device=local_rank)
-    dev_frames = torch.from_numpy(frames.view(np.int16)).to(f"cuda:{local_rank}")
     host_frames = torch.from_numpy(frames.view(np.int16)).pin_memory()
     fbytes = frames[0].nbytes
     p0 = synth.pose0().astype(np.float32)
@@ -563,6 +612,12 @@ def run_c4(args, rank, world, local_rank):
         ctx.sync(); torch.cuda.synchronize(); barrier()
         return ev0.elapsed_time(ev1), ctx.launches() - l0
 
+    # ICP mode of the headline number: replicated tracking (no exchange; ICP is latency-bound, so this is the faster mode
+    # on NVLink-connected B200s) unless HKF_SHARD_ICP says otherwise; the other mode (banded rows + all-reduce of the 27
+    # sums over peer memory) is timed next to it and reported under shard.other_icp_mode
+    replicated = os.environ.get("HKF_SHARD_ICP", "replicated") == "replicated"
+    if world > 1:
+        ctx._ck(ctx.lib.hkf_shard_set_icp_mode(ctx._h, 1 if replicated else 0), "hkf_shard_set_icp_mode")
     timed_pass()                                 # calibration / warm-up of every code path, not reported
     sampler = ClockSampler(local_rank); sampler.start()
     t_start = time.perf_counter()
@@ -570,6 +625,12 @@ def run_c4(args, rank, world, local_rank):
     for _ in range(args.c4_passes):              # a fixed count: every rank must run the same number of passes
         passes.append(timed_pass())
     clocks = sampler.stop()
+    other_ms = None
+    if world > 1:
+        ctx._ck(ctx.lib.hkf_shard_set_icp_mode(ctx._h, 0 if replicated else 1), "hkf_shard_set_icp_mode")
+        timed_pass()
+        other_ms = [timed_pass()[0] for _ in range(3)]
+        ctx._ck(ctx.lib.hkf_shard_set_icp_mode(ctx._h, 1 if replicated else 0), "hkf_shard_set_icp_mode")
     clocks["window"] = f"{len(passes)} passes of {W} untimed + {K} timed steps, back to back"
     pass_ms = np.array([x[0] for x in passes])
     launches = passes[0][1]
@@ -619,9 +680,10 @@ def run_c4(args, rank, world, local_rank):
     peer_map = None
     if world > 1:
         import torch.distributed as dist
-        tt = torch.tensor(np.concatenate([t_pass, t_e2e]), dtype=torch.float64, device=f"cuda:{local_rank}")
+        tt = torch.tensor(np.concatenate([t_pass, t_e2e, np.array(other_ms) * 1e-3]), dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)          # every pass: the slowest rank's time
-        t_pass, t_e2e = tt[:len(t_pass)].cpu().numpy(), tt[len(t_pass):].cpu().numpy()
+        t_other = tt[len(t_pass) + len(t_e2e):].cpu().numpy()
+        t_pass, t_e2e = tt[:len(t_pass)].cpu().numpy(), tt[len(t_pass):len(t_pass) + len(t_e2e)].cpu().numpy()
         g = [torch.zeros(4, dtype=torch.float64, device=f"cuda:{local_rank}") for _ in range(world)]
         dist.all_gather(g, torch.tensor(stage, dtype=torch.float64, device=f"cuda:{local_rank}"))
         all_stage = [x.cpu().tolist() for x in g]
@@ -637,9 +699,17 @@ def run_c4(args, rank, world, local_rank):
     med = _median_index(list(t_pass))
     t = float(t_pass[med])
     halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
-    slabs = shard.balanced_slab_ranges(cfg, world, halo) if world > 1 else shard.slab_ranges(cfg.resolution, 1, 0)
+    slabs = [None] * world
+    if world > 1:
+        import torch.distributed as dist
+        mine = torch.tensor([ctx.cfg.slab_z0, ctx.cfg.slab_z1, max(ctx.cfg.slab_z0 - halo, 0), min(ctx.cfg.slab_z1 + halo, cfg.resolution)],
+                            dtype=torch.int64, device=f"cuda:{local_rank}")
+        gs = [torch.zeros(4, dtype=torch.int64, device=f"cuda:{local_rank}") for _ in range(world)]
+        dist.all_gather(gs, mine)
+        slabs = [tuple(int(v) for v in x.cpu().tolist()) for x in gs]
+    else:
+        slabs = shard.slab_ranges(cfg.resolution, 1, 0)
     p2p = world > 1 and os.environ.get("HKF_SHARD_P2P", "1") != "0"
-    replicated = os.environ.get("HKF_SHARD_ICP", shard.DEFAULT_ICP_MODE) == "replicated"
     # Amdahl: preprocess + tracking run on every rank (the image does not shard), the volume stages shrink with the slab
     serial_us = float(np.mean([x[0] + x[1] for x in all_stage]))
     out = {"metric": f"fused frames/s at 640x480 into {cfg.resolution}^3 TSDF, z-slab-sharded (ICP + integrate + raycast)", "value": K / t,
@@ -650,9 +720,11 @@ def run_c4(args, rank, world, local_rank):
            "e2e": {"value": K / float(np.sort(t_e2e)[1]), "unit": "frames/s", "h2d_bytes_per_step": int(fbytes) * world, "d2h_bytes_per_step": 264 * world,
                    "runs_fps": [K / float(x) for x in t_e2e],
                    "note": "every rank uploads the 614 KB frame from pinned memory and reads pose + status back each frame; median of three passes, max over ranks"},
-           "shard": {"collective": ("P2P mailbox (cudaIpc peer memory, stores + flags inside k_icp / k_composite_p2p)" if p2p else "NCCL allreduce") if world > 1 else None,
+           "shard": {"collective": ("P2P over cudaIpc peer memory: ICP sums as (value, iteration) words stored into every rank's mailbox by k_icp_frame; raycast hits pushed into every rank's inbox by k_raycast, composited locally by k_composite_p2p" if p2p else "NCCL allreduce") if world > 1 else None,
                      "icp": None if world == 1 else ("replicated on every rank (no exchange)" if replicated else "banded rows + exchange of the 27 sums"),
-                     "peer_access_map": peer_map, "halo_planes": halo if world > 1 else 0,
+                     "other_icp_mode": None if world == 1 else {"icp": "banded rows + exchange of the 27 sums" if replicated else "replicated on every rank (no exchange)",
+                                                                "fps": [K / float(x) for x in t_other], "value": K / float(np.sort(t_other)[len(t_other) // 2])},
+                     "peer_access_map": peer_map, "halo_planes": halo if world > 1 else 0, "slab_balance": balance if world > 1 else None,
                      "owned_planes_per_rank": [s_[1] - s_[0] for s_ in slabs], "stored_planes_per_rank": [s_[3] - s_[2] for s_ in slabs],
                      "stage_us_per_rank": {"preprocess": [round(x[0], 1) for x in all_stage], "icp": [round(x[1], 1) for x in all_stage],
                                            "integrate": [round(x[2], 1) for x in all_stage], "raycast+composite": [round(x[3], 1) for x in all_stage]},

@@ -80,7 +80,7 @@ EXPORTS = [
     "hkf_set_pose", "hkf_icp_track", "hkf_sdf_track", "hkf_integrate_tracked", "hkf_raycast_tracked",
     "hkf_frame_result", "hkf_count_integrate_updates", "hkf_shard_unique_id", "hkf_shard_init",
     "hkf_shard_composite_raycast", "hkf_shard_ipc_handles", "hkf_shard_connect", "hkf_preprocess_next", "hkf_swap_frame",
-    "hkf_upload_color",
+    "hkf_upload_color", "hkf_integrate_profile", "hkf_integrate_profile_read", "hkf_shard_set_icp_mode",
 ]
 
 _lib = None
@@ -139,6 +139,10 @@ def load() -> C.CDLL:
     lib.hkf_frame_result.argtypes = [P, C.POINTER(Mat44), C.POINTER(C.c_int)]
     lib.hkf_count_integrate_updates.argtypes = [P, C.POINTER(Mat44), C.POINTER(IntegrateParams),
                                                 C.POINTER(CameraParams), C.POINTER(C.c_ulonglong)]
+    lib.hkf_integrate_profile.argtypes = [P, C.c_int]
+    lib.hkf_integrate_profile_read.argtypes = [P, C.c_void_p, C.c_size_t]
+    lib.hkf_integrate_profile_read.restype = C.c_long
+    lib.hkf_shard_set_icp_mode.argtypes = [P, C.c_int]
     lib.hkf_shard_unique_id.argtypes = [C.c_void_p]
     lib.hkf_shard_init.argtypes = [P, C.c_int, C.c_int, C.c_void_p]
     lib.hkf_shard_ipc_handles.argtypes = [P, C.c_void_p]
@@ -344,6 +348,19 @@ class Context:
         m = Mat44.from_np(pose)
         self._ck(self.lib.hkf_integrate_volume(self._h, self.cfg.use_color, self.cfg.color_angle_weight if self.cfg.use_color else 0,
                                                C.byref(m), C.byref(ip), C.byref(cam), C.byref(cam)), "hkf_integrate_volume")
+
+    def profile(self, enable: bool):
+        self._ck(self.lib.hkf_integrate_profile(self._h, 1 if enable else 0), "hkf_integrate_profile")
+
+    def profile_read(self) -> np.ndarray:
+        """[stored planes][general chunks, free bricks] accumulated since profile(True)"""
+        n = 2 * ((min(self.cfg.slab_z1 + self.cfg.slab_halo, self.cfg.resolution) - max(self.cfg.slab_z0 - self.cfg.slab_halo, 0))
+                 if (self.cfg.slab_z0 or self.cfg.slab_z1) else self.cfg.resolution)
+        out = np.zeros(n, np.uint32)
+        got = self.lib.hkf_integrate_profile_read(self._h, out.ctypes.data, n)
+        if got < 0:
+            raise HkfError(f"hkf_integrate_profile_read failed ({got}): {self.lib.hkf_last_error(self._h).decode()}")
+        return out[:got].reshape(-1, 2)
 
     def count_updates(self, pose) -> int:
         cam = self.cfg.camera()

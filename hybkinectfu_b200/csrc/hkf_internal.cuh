@@ -78,13 +78,14 @@ struct ShardMailbox {
     // low-latency protocol NCCL calls LL)
     unsigned long long sums[2][HKF_MAX_RANKS][32];
     unsigned ready[HKF_MAX_RANKS];         // raycast epoch whose keys/payload the source rank has finished writing
-    unsigned done[HKF_MAX_RANKS];          // raycast epoch the source rank has finished compositing (= reading its peers)
 };
 struct ShardPeers {
     ShardMailbox* mail[HKF_MAX_RANKS];                 // mail[r] = rank r's mailbox as mapped in this process
-    const unsigned long long* keys[HKF_MAX_RANKS];     // rank r's raycast keys
-    const float4* v[HKF_MAX_RANKS];                    // rank r's level-0 model vertices / normals
-    const float4* n[HKF_MAX_RANKS];
+    // rank r's compositing inboxes: keys_in[parity][source rank][pixel] (u64) and pay_in[parity][source rank][pixel][v|n]
+    // (2 x float4).  The raycast kernel of a rank PUSHES the key / payload of every pixel it hits into the inbox of every
+    // rank (posted stores over NVLink, overlapped with the march); compositing then reads local memory only.
+    unsigned long long* keys_in[HKF_MAX_RANKS];
+    float4* pay_in[HKF_MAX_RANKS];
     int rank, nranks;
 };
 
@@ -140,6 +141,10 @@ struct hkf_ctx {
     uint4* int_items = nullptr;        // integration work items (integrate.cu: make_free_item / make_general_item)
     unsigned int_capacity = 0;
     int int_parity = 0;
+    unsigned* int_hist = nullptr;      // per-plane work profile (hkf_integrate_profile)
+    unsigned* neg_flags = nullptr;     // bitmap over the (ceil(R/32))^3 bricks of 32^3 voxels: may hold a negative tsdf (integrate.cu sets, raycast.cu reads)
+    size_t neg_flag_bytes = 0;
+    bool int_hist_on = false;
     bool int_attr_set[3][2]{};         // cudaFuncSetAttribute done for k_integrate<FROM_STATE, {plain, COUNT_ONLY, COLOR}> on this context's device
     int sm_count = 148;
     unsigned z_lo = 0, z_hi = 0;       // stored planes
@@ -156,8 +161,11 @@ struct hkf_ctx {
     int rank = 0, nranks = 1;
     float* ray_payload = nullptr;
     ShardMailbox* mailbox = nullptr;   // this rank's mailbox (device memory, IPC-exported)
+    unsigned long long* keys_in = nullptr;   // this rank's compositing inboxes (IPC-exported), see ShardPeers
+    float4* pay_in = nullptr;
     ShardPeers peers{};
     bool p2p = false;                  // peers mapped: exchanges go over peer memory instead of NCCL
+    bool icp_replicated = false;       // sharded mode: every rank tracks on the whole image, no exchange of the 27 sums
     unsigned shard_seq = 0, shard_epoch = 0;
     void* ipc_opened[HKF_MAX_RANKS][4]{};
 };
@@ -229,6 +237,7 @@ __device__ __forceinline__ void hkf_pdl_enter_ordered()
 void hkf_shard_release(hkf_ctx* c);
 int hkf_shard_allreduce_sums(hkf_ctx* c);
 int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream = nullptr, bool track_begin = false);
+int hkf_neg_flags_rescan(hkf_ctx* c);   // rebuild neg_flags from the stored volume (after an upload)
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 int hkf_bounds_rmq(hkf_ctx* c, const DepthBounds& B, cudaStream_t stream);   // the coarser levels of the range-query table
 

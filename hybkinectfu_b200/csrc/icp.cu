@@ -838,10 +838,9 @@ extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
         HKF_LAUNCH_CHECK(c);
     }
     const int* iters = icp_schedule(c->levels);
-    // HKF_SHARD_ICP=replicated: every rank evaluates the whole image (no exchange at all; the poses are bit-identical
+    // hkf_shard_set_icp_mode(ctx, 1) / HKF_SHARD_ICP=replicated: every rank evaluates the whole image (no exchange at all; the poses are bit-identical
     // because inputs and arithmetic are).  Default in sharded mode: banded rows + all-reduce of the 27 sums.
-    static const bool replicated = getenv("HKF_SHARD_ICP") && !strcmp(getenv("HKF_SHARD_ICP"), "replicated");
-    const bool sharded = c->nranks > 1 && !replicated;
+    const bool sharded = c->nranks > 1 && !c->icp_replicated;
     if (!sharded || c->p2p) {
         // the whole schedule in one launch of co-resident blocks (k_icp_frame).  The launch is cooperative where the
         // driver accepts that together with programmatic stream serialisation: co-residency is then guaranteed rather

@@ -61,6 +61,8 @@ struct IntegrateArgs {
     int z_lo, z_hi;     // stored planes of this slab
     float size;         // S
     DepthBounds B;      // depth extrema of this frame per pixel tile (hkf_internal.cuh)
+    unsigned* hist;     // work profile (hkf_integrate_profile): [stored plane][general chunks, free bricks], or nullptr
+    unsigned* neg_flags; // sticky bitmap over 32^3-voxel bricks: "may hold a voxel with tsdf < 0" (raycast.cu skips the rest)
 };
 
 // colour integration (has_color): the frame's colour image, the new frame's level-0 normals (angle weighting), the
@@ -279,6 +281,10 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __res
         }
         const unsigned ng = (unsigned)__popc(gm);
         const bool isf = fm != 0;
+        if (A.hist != nullptr) {              // slab balancing: where the work of this view is, plane by plane
+            if (ng) atomicAdd(&A.hist[2 * zrel], ng);
+            if (isf) atomicAdd(&A.hist[2 * zrel + 1], 1u);
+        }
         unsigned incl = ng;                                        // inclusive warp scan of the general-chunk counts
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -300,7 +306,7 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __res
 // t' and w' of one voxel (tsdfvolume::updateVoxel, tsdfVolume.h:57-74, weight 1) with the reference's two IEEE divisions
 // skipped where their result is known: fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19), and
 // fma(1,w,1)/(w+1) is exactly 1.  Stores only when the voxel's bits change (saturated free space needs no store).
-__device__ __forceinline__ void update_voxel(float2* p, const float2 old, float sdf, float trunc, float thr_one, float wmax)
+__device__ __forceinline__ bool update_voxel(float2* p, const float2 old, float sdf, float trunc, float thr_one, float wmax)
 {
     const float w1 = __fadd_rn(old.y, 1.0f);
     const float wn = fminf(w1, wmax);
@@ -310,6 +316,7 @@ __device__ __forceinline__ void update_voxel(float2* p, const float2 old, float 
         tn = __fdiv_rn(__fmaf_rn(old.x, old.y, tsdf), w1);
     }
     if (tn != old.x || wn != old.y) *p = make_float2(tn, wn);
+    return tn < 0.f;
 }
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared memory with completion on an mbarrier.  One 4 KB
@@ -526,6 +533,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
             float d[INT_G];
 #pragma unroll
             for (int r = 0; r < INT_G; ++r) d[r] = (idx[r] >= 0) ? __ldg(depth + idx[r]) : 0.f;
+            bool neg = false;
 #pragma unroll
             for (int r = 0; r < INT_G; ++r) {
                 const float sdf = __fsub_rn(d[r], Z[r]);
@@ -533,7 +541,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                 if (COLOR) live = live && cidx[r] >= 0;
                 if (COUNT_ONLY) local_count += live ? 1u : 0u;
                 else if (live) {
-                    update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
+                    neg |= update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
                     if (COLOR) {
                         float wc = 2.0f;
                         if (CA.angled) {
@@ -552,6 +560,13 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                         *cp = nc;
                     }
                 }
+            }
+            // the item lies in ONE 32^3-voxel brick (4 rows of one y-group, a 32-aligned x chunk, one plane): mark it when a
+            // negative tsdf went in.  Only a voxel written here can be negative (free space writes 1), the mark is sticky.
+            if (!COUNT_ONLY && __any_sync(0xffffffffu, neg) && lane == 0) {
+                const unsigned nb = ((unsigned)A.R + 31u) >> 5;
+                const unsigned bit = (((((cur.y >> 10) & 0xfffu) + (unsigned)A.z_lo) >> 5) * nb + ((cur.y & 0x3ffu) >> 3)) * nb + (cur.y >> 22);
+                if (!(__ldcg(A.neg_flags + (bit >> 5)) & (1u << (bit & 31u)))) atomicOr(A.neg_flags + (bit >> 5), 1u << (bit & 31u));
             }
             // a free brick whenever the general list has advanced by its share (my_free : my_gen)
             credit += my_free;
@@ -580,6 +595,8 @@ static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* 
     A->z_lo = (int)c->z_lo; A->z_hi = (int)c->z_hi;
     A->size = c->ip.volume_size;
     A->B = c->bounds;
+    A->hist = c->int_hist_on ? c->int_hist : nullptr;
+    A->neg_flags = c->neg_flags;
 }
 
 #ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
@@ -642,6 +659,32 @@ extern "C" int hkf_integrate_tracked(hkf_ctx* c, const HkfFrameParams* fp)
         return launch_integrate<true, false, true>(c, A, CA);
     }
     return launch_integrate<true, false, false>(c, A);
+}
+
+// Work profile for slab balancing: while enabled, every integration adds the number of general chunks and free bricks
+// of each stored plane to a histogram (two atomics per 4 x 128 voxel brick of the item pass; off by default).
+extern "C" int hkf_integrate_profile(hkf_ctx* c, int enable)
+{
+    if (!c) return HKF_ERR_ARG;
+    const size_t n = 2 * (size_t)(c->z_hi - c->z_lo);
+    if (enable) {
+        if (!c->int_hist) HKF_CUDA(c, cudaMalloc(&c->int_hist, n * sizeof(unsigned)));
+        HKF_CUDA(c, cudaMemsetAsync(c->int_hist, 0, n * sizeof(unsigned), c->stream));
+    }
+    c->int_hist_on = enable != 0;
+    return HKF_OK;
+}
+
+extern "C" long hkf_integrate_profile_read(hkf_ctx* c, uint32_t* out, size_t cap_entries)
+{
+    if (!c || !out) return -HKF_ERR_ARG;
+    const size_t n = 2 * (size_t)(c->z_hi - c->z_lo);
+    if (!c->int_hist) { c->err = "hkf_integrate_profile_read: profiling was never enabled"; return -HKF_ERR_STATE; }
+    if (cap_entries < n) { c->err = "hkf_integrate_profile_read: destination too small"; return -HKF_ERR_ARG; }
+    cudaError_t e = cudaMemcpyAsync(out, c->int_hist, n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { c->err = std::string("hkf_integrate_profile_read: ") + cudaGetErrorString(e); return -HKF_ERR_CUDA; }
+    return (long)n;
 }
 
 extern "C" int hkf_count_integrate_updates(hkf_ctx* c, const HkfMat44* transform, const HkfIntegrateParams* ip,

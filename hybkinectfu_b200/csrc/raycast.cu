@@ -33,7 +33,8 @@ struct RaycastArgs {
     float inc, near_plane, far_plane;
     float pose[16];
     int own_z0, own_z1, rank;
-    const ShardMailbox* mailbox; int nranks; unsigned epoch;   // peer-memory mode: epoch of this raycast
+    int nranks; unsigned epoch;        // peer-memory mode: epoch of this raycast (its parity selects the inbox)
+    ShardPeers peers;                  // peer-memory mode: where hits are pushed (peers.nranks == 0: no push)
     // has_color (raycastingVolume.cu:101-106): the voxel colour plane and raycast_rgb; nullptr = depth only.  The colour
     // of a hit is interpolated at the refined vertex BEFORE the gradient is evaluated and is written whenever that
     // interpolation succeeds, even if the gradient then fails and the pixel's vertex / normal stay zero.
@@ -241,7 +242,19 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
     }
     out_v[pix] = ov;
     out_n[pix] = on;
-    if (SLAB) keys[pix] = key;
+    if (SLAB) {
+        keys[pix] = key;
+        if (A.peers.nranks > 0 && key != ~0ull) {
+            // a hit: its key (and, if the refinement succeeded, its vertex / normal) goes into the inbox of every rank,
+            // this one included.  Posted stores: nothing waits for them here.
+            const size_t npix = (size_t)A.cols * A.rows;
+            const size_t slot = ((size_t)(A.epoch & 1u) * HKF_MAX_RANKS + (unsigned)A.rank) * npix + pix;
+            for (int r = 0; r < A.peers.nranks; ++r) {
+                A.peers.keys_in[r][slot] = key;
+                if ((key >> 8) & 1ull) { A.peers.pay_in[r][2 * slot] = ov; A.peers.pay_in[r][2 * slot + 1] = on; }
+            }
+        }
+    }
 }
 
 #ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
@@ -254,9 +267,10 @@ static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParam
     A->inc = rp->fRayIncrement; A->near_plane = near_plane; A->far_plane = far_plane;
     if (pose) memcpy(A->pose, pose, 64); else memset(A->pose, 0, 64);
     A->own_z0 = (int)c->own_z0; A->own_z1 = (int)c->own_z1; A->rank = c->rank;
-    A->mailbox = nullptr; A->nranks = c->nranks; A->epoch = 0;
+    A->nranks = c->nranks; A->epoch = 0;
+    A->peers = ShardPeers{};
     A->color_vol = nullptr; A->color_out = nullptr;
-    if (c->p2p) { A->mailbox = c->mailbox; A->epoch = ++c->shard_epoch; }
+    if (c->p2p) { A->peers = c->peers; A->epoch = ++c->shard_epoch; }
 }
 
 static inline bool is_slab(const hkf_ctx* c) { return !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution); }

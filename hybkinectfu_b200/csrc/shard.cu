@@ -81,6 +81,14 @@ extern "C" int hkf_shard_init(hkf_ctx* c, int rank, int nranks, const void* uniq
     ncclComm_t comm = nullptr;
     HKF_NCCL(c, a->CommInitRank(&comm, nranks, id, rank));
     c->nccl_comm = comm; c->rank = rank; c->nranks = nranks;
+    c->icp_replicated = getenv("HKF_SHARD_ICP") && !strcmp(getenv("HKF_SHARD_ICP"), "replicated");
+    return HKF_OK;
+}
+
+extern "C" int hkf_shard_set_icp_mode(hkf_ctx* c, int replicated)
+{
+    if (!c) return HKF_ERR_ARG;
+    c->icp_replicated = replicated != 0;
     return HKF_OK;
 }
 
@@ -92,6 +100,8 @@ void hkf_shard_release(hkf_ctx* c)
             if (c->ipc_opened[r][k]) { cudaIpcCloseMemHandle(c->ipc_opened[r][k]); c->ipc_opened[r][k] = nullptr; }
     c->p2p = false;
     if (c->mailbox) { cudaFree(c->mailbox); c->mailbox = nullptr; }
+    if (c->keys_in) { cudaFree(c->keys_in); c->keys_in = nullptr; }
+    if (c->pay_in) { cudaFree(c->pay_in); c->pay_in = nullptr; }
     if (c->nccl_comm) { nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
 }
 
@@ -105,11 +115,20 @@ extern "C" int hkf_shard_ipc_handles(hkf_ctx* c, void* out)
         HKF_CUDA(c, cudaMalloc(&c->mailbox, sizeof(ShardMailbox)));
         HKF_CUDA(c, cudaMemset(c->mailbox, 0, sizeof(ShardMailbox)));
     }
+    const size_t npix = (size_t)c->cols[0] * c->rows[0];
+    if (!c->keys_in) {
+        const size_t nk = 2 * (size_t)HKF_MAX_RANKS * npix;
+        HKF_CUDA(c, cudaMalloc(&c->keys_in, nk * sizeof(unsigned long long)));
+        HKF_CUDA(c, cudaMemset(c->keys_in, 0xff, nk * sizeof(unsigned long long)));       // "no hit" everywhere
+        HKF_CUDA(c, cudaMalloc(&c->pay_in, nk * 2 * sizeof(float4)));
+        HKF_CUDA(c, cudaMemset(c->pay_in, 0, nk * 2 * sizeof(float4)));
+        HKF_CUDA(c, cudaDeviceSynchronize());
+    }
     cudaIpcMemHandle_t h[4];
+    memset(h, 0, sizeof(h));
     HKF_CUDA(c, cudaIpcGetMemHandle(&h[0], c->mailbox));
-    HKF_CUDA(c, cudaIpcGetMemHandle(&h[1], c->ray_keys));
-    HKF_CUDA(c, cudaIpcGetMemHandle(&h[2], c->model_v[0]));
-    HKF_CUDA(c, cudaIpcGetMemHandle(&h[3], c->model_n[0]));
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[1], c->keys_in));
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[2], c->pay_in));
     memcpy(out, h, sizeof(h));
     return HKF_OK;
 }
@@ -124,30 +143,29 @@ extern "C" int hkf_shard_connect(hkf_ctx* c, const void* all_handles, int nranks
     ShardPeers P{};
     P.rank = c->rank; P.nranks = nranks;
     for (int r = 0; r < nranks; ++r) {
-        void* ptr[4];
+        void* ptr[3];
         if (r == c->rank) {
-            ptr[0] = c->mailbox; ptr[1] = c->ray_keys; ptr[2] = c->model_v[0]; ptr[3] = c->model_n[0];
+            ptr[0] = c->mailbox; ptr[1] = c->keys_in; ptr[2] = c->pay_in;
         } else {
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 3; ++k) {
                 HKF_CUDA(c, cudaIpcOpenMemHandle(&ptr[k], h[r * 4 + k], cudaIpcMemLazyEnablePeerAccess));
                 c->ipc_opened[r][k] = ptr[k];
             }
         }
-        P.mail[r] = (ShardMailbox*)ptr[0]; P.keys[r] = (const unsigned long long*)ptr[1];
-        P.v[r] = (const float4*)ptr[2]; P.n[r] = (const float4*)ptr[3];
+        P.mail[r] = (ShardMailbox*)ptr[0]; P.keys_in[r] = (unsigned long long*)ptr[1]; P.pay_in[r] = (float4*)ptr[2];
     }
     c->peers = P;
     c->p2p = true;
     return HKF_OK;
 }
 
-// One kernel composites the per-slab raycasts.  Block 0 is the only one that talks to the peers' flags: it announces
-// that this rank's keys / payload of the epoch are complete, waits until every rank has announced the same, and
-// releases the other blocks through a device-local word (one system-scope fence per launch instead of one per block
-// and peer).  Then, per pixel, the minimum key over ranks is read straight from peer memory and, where another rank
-// won with a successful refinement, that rank's vertex/normal.  In place: a rank only overwrites pixels it did not
-// win, and nobody reads a loser's payload.  The last block to finish tells the peers that this rank is done reading
-// and waits for the same from them, so the next raycast may overwrite keys and payload without any further check.
+// One kernel composites the per-slab raycasts from this rank's OWN inboxes (the peers' raycast kernels pushed their hits
+// there).  Block 0 is the only one that talks to the peers' flags: it announces that this rank's raycast of the epoch -
+// and with it every store it pushed - is complete (stream order + one system-scope fence), waits until every rank has
+// announced the same, and releases the other blocks through a device-local word.  Then, per pixel, the minimum of the
+// nranks local keys and the winner's payload; the key slots are reset to "no hit" for their next use two epochs later.
+// The inboxes are double-buffered by epoch parity: a peer can only push epoch e + 2 after this rank has announced
+// e + 1, i.e. after this kernel of epoch e has completed - no trailing barrier.
 __global__ void __launch_bounds__(256)
 k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ out_n, unsigned npix, unsigned epoch, HkfDeviceState* st)
 {
@@ -155,12 +173,14 @@ k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ o
     if (threadIdx.x == 0) {
         bool ok = true;
         if (blockIdx.x == 0) {
-            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->ready[P.rank] = epoch;    // stream order: the raycast is complete
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->ready[P.rank] = epoch;
             const long long t0 = clock64();
             for (int r = 0; r < P.nranks && ok; ++r)
                 while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->ready[r] - epoch) < 0)
                     if (clock64() - t0 > 4000000000ll) { ok = false; break; }                          // ~2 s: a peer died
             __threadfence_system();
+            if (!ok) st->track_status = HKF_TRACK_PEER_TIMEOUT;
             *(volatile unsigned*)&st->comp_go = ok ? epoch : (epoch | 0x80000000u);
         } else {
             unsigned g;
@@ -175,10 +195,11 @@ k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ o
     __syncthreads();
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (s_ok && i < npix) {
-        // peer memory is read through L2 only (never a stale L1 line); all loads are issued before the first compare
+        // the inboxes were written by peers: read through L2 only (never a stale L1 line); all loads first
+        unsigned long long* kin = P.keys_in[P.rank] + (size_t)(epoch & 1u) * HKF_MAX_RANKS * npix + i;
         unsigned long long k[HKF_MAX_RANKS];
 #pragma unroll
-        for (int r = 0; r < HKF_MAX_RANKS; ++r) k[r] = r < P.nranks ? __ldcg(P.keys[r] + i) : ~0ull;
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) k[r] = r < P.nranks ? __ldcg(kin + (size_t)r * npix) : ~0ull;
         unsigned long long best = ~0ull;
 #pragma unroll
         for (int r = 0; r < HKF_MAX_RANKS; ++r) best = k[r] < best ? k[r] : best;
@@ -186,24 +207,11 @@ k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ o
         if (best == ~0ull || !((best >> 8) & 1ull)) {
             out_v[i] = make_float4(0.f, 0.f, 0.f, 0.f); out_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else if (w != P.rank) {
-            out_v[i] = __ldcg(P.v[w] + i); out_n[i] = __ldcg(P.n[w] + i);
+            const float4* pay = P.pay_in[P.rank] + 2 * (((size_t)(epoch & 1u) * HKF_MAX_RANKS + (unsigned)w) * npix + i);
+            out_v[i] = __ldcg(pay); out_n[i] = __ldcg(pay + 1);
         }
-    }
-    // everything this rank reads from its peers for this epoch has been read
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(&st->ticket, 1u);
-        if (t == gridDim.x - 1) {
-            st->ticket = 0;
-            if (!s_ok) st->track_status = HKF_TRACK_PEER_TIMEOUT;
-            __threadfence_system();
-            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->done[P.rank] = epoch;
-            const long long t0 = clock64();
-            for (int r = 0; r < P.nranks; ++r)
-                while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->done[r] - epoch) < 0)
-                    if (clock64() - t0 > 4000000000ll) break;
-        }
+#pragma unroll
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) if (r < P.nranks && k[r] != ~0ull) kin[(size_t)r * npix] = ~0ull;
     }
 }
 

@@ -64,14 +64,24 @@ def plane_work(cfg, pose=None, samples: int = 48) -> np.ndarray:
     return np.sqrt(w) + 0.05
 
 
-def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int = 8):
+def plane_cost_from_profile(profile: np.ndarray) -> np.ndarray:
+    """relative cost of every plane from a measured work profile [R][general chunks, free bricks] (Context.profile_read,
+    summed over a representative run): a general chunk (4 x 32 voxels, every voxel projected) costs about four times a
+    free brick (4 x 128 voxels streamed) on B200 (profiles/r2_integrate_e_rmq.txt), plus the per-plane share of the
+    classification pass"""
+    c = profile[:, 0].astype(np.float64) + 0.23 * profile[:, 1].astype(np.float64)
+    return c + 0.02 * max(c.mean(), 1e-9)
+
+
+def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int = 8, plane_cost=None):
     """slab_ranges with boundaries chosen so that every rank gets the same share of plane_work over the planes it
     STORES (owned + halo: the halo is integrated and marched redundantly, so thin slabs cost more than they own).
     The view frustum widens with depth: equal-thickness slabs are not equal work."""
     R = cfg.resolution
     if nranks == 1:
         return [(0, R, 0, R)]
-    w = plane_work(cfg, pose)
+    w = plane_work(cfg, pose) if plane_cost is None else np.asarray(plane_cost, np.float64)
+    assert len(w) == R
     cum = np.concatenate([[0.0], np.cumsum(w)])
 
     def stored_cost(z0, z1):
@@ -169,12 +179,12 @@ def broadcast_unique_id(make_id, src: int = 0) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def sharded_context(cfg, rank: int, nranks: int, device: int, p2p=None, balanced: bool = True):
+def sharded_context(cfg, rank: int, nranks: int, device: int, p2p=None, balanced: bool = True, plane_cost=None):
     """hkf context of `rank`'s slab, joined to the library's own NCCL communicator.  Needs an initialised
     torch.distributed process group (any backend) to hand the unique id round."""
     from . import capi
     halo = halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
-    ranges = balanced_slab_ranges(cfg, nranks, halo) if balanced else slab_ranges(cfg.resolution, nranks, halo)
+    ranges = balanced_slab_ranges(cfg, nranks, halo, plane_cost=plane_cost) if balanced else slab_ranges(cfg.resolution, nranks, halo)
     z0, z1, _, _ = ranges[rank]
     c = dataclasses.replace(cfg, slab_z0=z0, slab_z1=z1, slab_halo=halo)
     ctx = capi.Context(c, device=device)
@@ -194,3 +204,20 @@ def sharded_context(cfg, rank: int, nranks: int, device: int, p2p=None, balanced
         allh = all_gather_bytes(bytes(h))
         ctx._ck(ctx.lib.hkf_shard_connect(ctx._h, allh, nranks), "hkf_shard_connect")
     return ctx
+
+
+def gather_plane_profile(ctx, cfg, rank: int, nranks: int, device: int) -> np.ndarray:
+    """[R][2] work profile of the whole volume: every rank contributes the counters of the planes it OWNS (halo planes
+    are profiled by their owners), summed over the ranks"""
+    import torch
+    import torch.distributed as dist
+    R = cfg.resolution
+    mine = ctx.profile_read().astype(np.int64)
+    z_lo = max(ctx.cfg.slab_z0 - ctx.cfg.slab_halo, 0)
+    full = np.zeros((R, 2), np.int64)
+    full[ctx.cfg.slab_z0:ctx.cfg.slab_z1] = mine[ctx.cfg.slab_z0 - z_lo:ctx.cfg.slab_z1 - z_lo]
+    t = torch.from_numpy(full)
+    if dist.get_backend() == "nccl":
+        t = t.to(f"cuda:{device}")
+    dist.all_reduce(t)
+    return t.cpu().numpy()

@@ -225,20 +225,34 @@ int hkf_count_integrate_updates(hkf_ctx* ctx, const HkfMat44* transform,
         const HkfIntegrateParams* integrate_params, const HkfCameraParams* depth_camera_params,
         unsigned long long* n_upd);
 
+/* Work profile of the integration, plane by plane (for balancing z-slabs on MEASURED work): while enabled, every
+ * integration adds, per stored plane, the number of general 4x32-voxel chunks and of free 4x128-voxel bricks it
+ * processed.  hkf_integrate_profile(ctx, 1) clears and enables, (ctx, 0) disables; _read copies 2 x stored-planes
+ * counters {general, free} and returns the number of entries or a negative HKF_ERR_*. */
+int  hkf_integrate_profile(hkf_ctx* ctx, int enable);
+long hkf_integrate_profile_read(hkf_ctx* ctx, uint32_t* out, size_t cap_entries);
+
 /* ------------------------------------------------------------------ 4. z-slab sharding */
 /* Join an NCCL communicator: `unique_id` is the 128-byte ncclUniqueId produced by
  * hkf_shard_unique_id() on rank 0 and distributed by the caller (torch.distributed). */
 int hkf_shard_unique_id(void* unique_id_128);
 int hkf_shard_init(hkf_ctx* ctx, int rank, int nranks, const void* unique_id_128);
+/* ICP in sharded mode.  0 (default, or env HKF_SHARD_ICP unset): every rank evaluates its band of pixel rows and the 27
+ * partial sums are all-reduced (peer-memory exchange inside the tracking kernel, ncclAllReduce without peer memory),
+ * summed in rank order so that every rank holds the same bits.  1 (or HKF_SHARD_ICP=replicated): every rank tracks on
+ * the whole image, no exchange - ICP is latency-bound, so on NVLink-connected B200s this is the faster mode.  Must be
+ * set identically on all ranks. */
+int hkf_shard_set_icp_mode(hkf_ctx* ctx, int replicated);
 /* nearest-hit compositing of per-slab partial raycasts (min over ranks of (t, ok, rank) keys,
  * then payload from the winner) -> full model maps on every rank */
 int hkf_shard_composite_raycast(hkf_ctx* ctx);
 /* Peer-memory fast path (optional, after hkf_shard_init): each rank exports HKF_SHARD_IPC_BYTES bytes of cudaIpc
- * handles (its mailbox, raycast keys and level-0 model maps); the caller gathers them from all ranks (rank order)
- * and hands the concatenation to hkf_shard_connect.  Afterwards the ICP sums are exchanged by the tracking kernel
- * itself (P2P stores + flags over NVLink, summed in rank order so every rank holds the same bits) and the raycast is
- * composited by one kernel that reads its peers' keys and the winner's payload directly; NCCL is no longer on the
- * per-frame path.  Without it the same exchanges use ncclAllReduce. */
+ * handles (its mailbox and its compositing inboxes); the caller gathers them from all ranks (rank order) and hands the
+ * concatenation to hkf_shard_connect.  Afterwards the ICP sums are exchanged by the tracking kernel itself (P2P stores
+ * of (value, iteration) words over NVLink, summed in rank order so every rank holds the same bits), the raycast kernel
+ * pushes the key and payload of every pixel it hits into the inbox of every rank while it marches, and compositing is
+ * one kernel over local memory; NCCL is no longer on the per-frame path.  Without it the same exchanges use
+ * ncclAllReduce. */
 #define HKF_SHARD_IPC_BYTES 256
 int hkf_shard_ipc_handles(hkf_ctx* ctx, void* out_handles);
 int hkf_shard_connect(hkf_ctx* ctx, const void* all_handles, int nranks);

@@ -94,6 +94,7 @@ extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S,
     A.trunc = trunc; A.maxdist = maxdist; A.wmax = wmax;
     A.R = R; A.z_lo = 0; A.z_hi = R; A.size = S;
     A.B = f->bounds.B;
+    A.hist = nullptr;
     HkfDeviceState st;
     memset(&st, 0, sizeof(st));
     const unsigned capacity = 4u * (unsigned)R * (unsigned)(R / 4) * div_up((unsigned)R, 128);

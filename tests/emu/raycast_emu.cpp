@@ -17,7 +17,7 @@ extern "C" int emu_raycast(const float* vol, int R, float S, unsigned cols, unsi
     A.cols = (int)cols; A.rows = (int)rows; A.cx = cx; A.cy = cy; A.fx = fx; A.fy = fy;
     A.inc = inc; A.near_plane = near_plane; A.far_plane = far_plane;
     memcpy(A.pose, pose16, 64);
-    A.own_z0 = 0; A.own_z1 = R; A.rank = 0; A.mailbox = nullptr; A.nranks = 1; A.epoch = 0;
+    A.own_z0 = 0; A.own_z1 = R; A.rank = 0; A.nranks = 1; A.epoch = 0;
     float4* ov = reinterpret_cast<float4*>(out_v4);
     float4* on = reinterpret_cast<float4*>(out_n4);
     const unsigned gx = (cols + 15) / 16, gy = (rows + 15) / 16;
