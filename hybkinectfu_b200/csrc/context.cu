@@ -40,7 +40,7 @@ static void free_all(hkf_ctx* c)
     cudaFree(c->depth_mm); cudaFree(c->raw_depth); cudaFree(c->trunc_depth); cudaFree(c->filtered_depth); cudaFree(c->bounds.base); cudaFree(c->bounds.tab);
     for (int l = 0; l < HKF_MAX_LEVELS; ++l) { cudaFree(c->new_v[l]); cudaFree(c->new_n[l]); cudaFree(c->model_v[l]); cudaFree(c->model_n[l]); }
     cudaFree(c->color); cudaFree(c->raw_rgb); cudaFree(c->raycast_rgb);
-    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->int_hist); cudaFree(c->neg_flags); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
+    cudaFree(c->ray_keys); cudaFree(c->ray_payload); cudaFree(c->partials); cudaFree(c->vol); cudaFree(c->int_items); cudaFree(c->int_hist); cudaFree(c->tris); cudaFree(c->mc_cand); cudaFree(c->st);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->depth_mm_pinned) cudaFreeHost(c->depth_mm_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -139,12 +139,6 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
     // at most four work items per 4 x 128 voxel brick: one per general chunk, or one for its free chunks (integrate.cu)
     c->int_capacity = 4u * (c->z_hi - c->z_lo) * (R / 4) * div_up(R, 128);
     CREATE_CUDA(cudaMalloc(&c->int_items, (size_t)c->int_capacity * sizeof(uint4)));
-    {
-        const size_t nb = (R + 31) / 32;
-        c->neg_flag_bytes = ((nb * nb * nb + 31) / 32) * sizeof(unsigned);
-        CREATE_CUDA(cudaMalloc(&c->neg_flags, c->neg_flag_bytes));
-        CREATE_CUDA(cudaMemset(c->neg_flags, 0, c->neg_flag_bytes));
-    }
     c->sm_count = prop.multiProcessorCount;
     if (p->max_triangles) CREATE_CUDA(cudaMalloc(&c->tris, (size_t)p->max_triangles * sizeof(HkfTriangle)));
     CREATE_CUDA(cudaMalloc(&c->st, sizeof(HkfDeviceState)));
@@ -182,7 +176,6 @@ extern "C" int hkf_reset_volume(hkf_ctx* c)
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution;
     HKF_CUDA(c, cudaMemsetAsync(c->vol, 0, nvox * sizeof(float2), c->stream));
     if (c->color) HKF_CUDA(c, cudaMemsetAsync(c->color, 0, nvox * sizeof(uchar4), c->stream));
-    HKF_CUDA(c, cudaMemsetAsync(c->neg_flags, 0, c->neg_flag_bytes, c->stream));
     HKF_CUDA(c, cudaMemsetAsync(c->st, 0, sizeof(HkfDeviceState), c->stream));
     for (int l = 0; l < c->levels; ++l) {
         size_t nb = (size_t)c->cols[l] * c->rows[l] * sizeof(float4);
@@ -250,28 +243,6 @@ extern "C" long hkf_download(hkf_ctx* c, int buffer, unsigned level, void* dst, 
     return (long)nb;
 }
 
-// rebuild the "may hold a negative tsdf" brick bitmap from the stored planes (a volume was uploaded)
-__global__ void k_neg_flags_rescan(const float2* __restrict__ vol, unsigned R, unsigned z_lo, unsigned z_hi, unsigned* __restrict__ flags)
-{
-    const unsigned nb = (R + 31u) >> 5;
-    const size_t n = (size_t)(z_hi - z_lo) * R * R;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (vol[i].x < 0.f) {
-            const unsigned x = (unsigned)(i % R), y = (unsigned)((i / R) % R), z = (unsigned)(i / ((size_t)R * R)) + z_lo;
-            const unsigned bit = ((z >> 5) * nb + (y >> 5)) * nb + (x >> 5);
-            if (!(flags[bit >> 5] & (1u << (bit & 31u)))) atomicOr(flags + (bit >> 5), 1u << (bit & 31u));
-        }
-    }
-}
-
-int hkf_neg_flags_rescan(hkf_ctx* c)
-{
-    HKF_CUDA(c, cudaMemsetAsync(c->neg_flags, 0, c->neg_flag_bytes, c->stream));
-    k_neg_flags_rescan<<<c->sm_count * 8, 256, 0, c->stream>>>(c->vol, c->ip.volume_resolution, c->z_lo, c->z_hi, c->neg_flags);
-    HKF_LAUNCH_CHECK(c);
-    return HKF_OK;
-}
-
 extern "C" long hkf_upload(hkf_ctx* c, int buffer, unsigned level, const void* src, size_t nbytes)
 {
     if (!c || !src) return -HKF_ERR_ARG;
@@ -284,9 +255,6 @@ extern "C" long hkf_upload(hkf_ctx* c, int buffer, unsigned level, const void* s
     if (!p || buffer == HKF_BUF_SOLVER_SUMS) { c->err = "hkf_upload: buffer not writable"; return -HKF_ERR_ARG; }
     if (nbytes != nb) { c->err = "hkf_upload: size mismatch"; return -HKF_ERR_ARG; }
     cudaError_t e = cudaMemcpyAsync(p, src, nb, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess && buffer == HKF_BUF_VOLUME) {
-        if (hkf_neg_flags_rescan(c) != HKF_OK) return -HKF_ERR_CUDA;
-    }
     if (e == cudaSuccess && buffer == HKF_BUF_TRUNC_DEPTH) {
         // keep the depth bounds used by integration culling consistent with the uploaded map
         if (hkf_depth_bounds(c) != HKF_OK) return -HKF_ERR_CUDA;

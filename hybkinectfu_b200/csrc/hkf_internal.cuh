@@ -142,8 +142,6 @@ struct hkf_ctx {
     unsigned int_capacity = 0;
     int int_parity = 0;
     unsigned* int_hist = nullptr;      // per-plane work profile (hkf_integrate_profile)
-    unsigned* neg_flags = nullptr;     // bitmap over the (ceil(R/32))^3 bricks of 32^3 voxels: may hold a negative tsdf (integrate.cu sets, raycast.cu reads)
-    size_t neg_flag_bytes = 0;
     bool int_hist_on = false;
     bool int_attr_set[3][2]{};         // cudaFuncSetAttribute done for k_integrate<FROM_STATE, {plain, COUNT_ONLY, COLOR}> on this context's device
     int sm_count = 148;
@@ -237,7 +235,6 @@ __device__ __forceinline__ void hkf_pdl_enter_ordered()
 void hkf_shard_release(hkf_ctx* c);
 int hkf_shard_allreduce_sums(hkf_ctx* c);
 int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream = nullptr, bool track_begin = false);
-int hkf_neg_flags_rescan(hkf_ctx* c);   // rebuild neg_flags from the stored volume (after an upload)
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 int hkf_bounds_rmq(hkf_ctx* c, const DepthBounds& B, cudaStream_t stream);   // the coarser levels of the range-query table
 

@@ -62,7 +62,6 @@ struct IntegrateArgs {
     float size;         // S
     DepthBounds B;      // depth extrema of this frame per pixel tile (hkf_internal.cuh)
     unsigned* hist;     // work profile (hkf_integrate_profile): [stored plane][general chunks, free bricks], or nullptr
-    unsigned* neg_flags; // sticky bitmap over 32^3-voxel bricks: "may hold a voxel with tsdf < 0" (raycast.cu skips the rest)
 };
 
 // colour integration (has_color): the frame's colour image, the new frame's level-0 normals (angle weighting), the
@@ -306,7 +305,7 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __res
 // t' and w' of one voxel (tsdfvolume::updateVoxel, tsdfVolume.h:57-74, weight 1) with the reference's two IEEE divisions
 // skipped where their result is known: fminf(sdf/trunc, 1) is exactly 1 once sdf >= trunc*(1+2^-19), and
 // fma(1,w,1)/(w+1) is exactly 1.  Stores only when the voxel's bits change (saturated free space needs no store).
-__device__ __forceinline__ bool update_voxel(float2* p, const float2 old, float sdf, float trunc, float thr_one, float wmax)
+__device__ __forceinline__ void update_voxel(float2* p, const float2 old, float sdf, float trunc, float thr_one, float wmax)
 {
     const float w1 = __fadd_rn(old.y, 1.0f);
     const float wn = fminf(w1, wmax);
@@ -316,7 +315,6 @@ __device__ __forceinline__ bool update_voxel(float2* p, const float2 old, float 
         tn = __fdiv_rn(__fmaf_rn(old.x, old.y, tsdf), w1);
     }
     if (tn != old.x || wn != old.y) *p = make_float2(tn, wn);
-    return tn < 0.f;
 }
 
 // ---- bulk asynchronous copies (TMA, cp.async.bulk) global -> shared memory with completion on an mbarrier.  One 4 KB
@@ -533,7 +531,6 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
             float d[INT_G];
 #pragma unroll
             for (int r = 0; r < INT_G; ++r) d[r] = (idx[r] >= 0) ? __ldg(depth + idx[r]) : 0.f;
-            bool neg = false;
 #pragma unroll
             for (int r = 0; r < INT_G; ++r) {
                 const float sdf = __fsub_rn(d[r], Z[r]);
@@ -541,7 +538,7 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                 if (COLOR) live = live && cidx[r] >= 0;
                 if (COUNT_ONLY) local_count += live ? 1u : 0u;
                 else if (live) {
-                    neg |= update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
+                    update_voxel(vp + (size_t)r * R, old[r], sdf, trunc, thr_one, wmax);
                     if (COLOR) {
                         float wc = 2.0f;
                         if (CA.angled) {
@@ -560,13 +557,6 @@ k_integrate(IntegrateArgs A, const float* __restrict__ depth, float2* __restrict
                         *cp = nc;
                     }
                 }
-            }
-            // the item lies in ONE 32^3-voxel brick (4 rows of one y-group, a 32-aligned x chunk, one plane): mark it when a
-            // negative tsdf went in.  Only a voxel written here can be negative (free space writes 1), the mark is sticky.
-            if (!COUNT_ONLY && __any_sync(0xffffffffu, neg) && lane == 0) {
-                const unsigned nb = ((unsigned)A.R + 31u) >> 5;
-                const unsigned bit = (((((cur.y >> 10) & 0xfffu) + (unsigned)A.z_lo) >> 5) * nb + ((cur.y & 0x3ffu) >> 3)) * nb + (cur.y >> 22);
-                if (!(__ldcg(A.neg_flags + (bit >> 5)) & (1u << (bit & 31u)))) atomicOr(A.neg_flags + (bit >> 5), 1u << (bit & 31u));
             }
             // a free brick whenever the general list has advanced by its share (my_free : my_gen)
             credit += my_free;
@@ -596,7 +586,6 @@ static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* 
     A->size = c->ip.volume_size;
     A->B = c->bounds;
     A->hist = c->int_hist_on ? c->int_hist : nullptr;
-    A->neg_flags = c->neg_flags;
 }
 
 #ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
