@@ -61,7 +61,6 @@ struct IntegrateArgs {
     int z_lo, z_hi;     // stored planes of this slab
     float size;         // S
     DepthBounds B;      // depth extrema of this frame per pixel tile (hkf_internal.cuh)
-    unsigned* hist;     // work profile (hkf_integrate_profile): [stored plane][general chunks, free bricks], or nullptr
 };
 
 // colour integration (has_color): the frame's colour image, the new frame's level-0 normals (angle weighting), the
@@ -185,9 +184,10 @@ __device__ __forceinline__ uint4 make_general_item(const IntegrateArgs& A, int y
 #define INT_GB 64                      // row groups per block of pass 1
 
 // NOFREE (colour integration): every updated voxel needs its colour pixel, so the projection-free class is not used.
-template <bool FROM_STATE, bool NOFREE>
+// PROFILE (hkf_integrate_profile): per-plane counts of general chunks / free bricks into hist, for slab balancing.
+template <bool FROM_STATE, bool NOFREE, bool PROFILE>
 __global__ void __launch_bounds__(256, 5)
-k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __restrict__ items, unsigned capacity, int parity)
+k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __restrict__ items, unsigned capacity, int parity, unsigned* __restrict__ hist)
 {
     __shared__ int s_lo[INT_GB], s_hi[INT_GB];
     __shared__ int s_any;
@@ -280,9 +280,9 @@ k_integrate_items(IntegrateArgs A, HkfDeviceState* __restrict__ st, uint4* __res
         }
         const unsigned ng = (unsigned)__popc(gm);
         const bool isf = fm != 0;
-        if (A.hist != nullptr) {              // slab balancing: where the work of this view is, plane by plane
-            if (ng) atomicAdd(&A.hist[2 * zrel], ng);
-            if (isf) atomicAdd(&A.hist[2 * zrel + 1], 1u);
+        if (PROFILE) {                        // slab balancing: where the work of this view is, plane by plane
+            if (ng) atomicAdd(&hist[2 * zrel], ng);
+            if (isf) atomicAdd(&hist[2 * zrel + 1], 1u);
         }
         unsigned incl = ng;                                        // inclusive warp scan of the general-chunk counts
 #pragma unroll
@@ -585,7 +585,6 @@ static void fill_args(hkf_ctx* c, const float* inv16, const HkfIntegrateParams* 
     A->z_lo = (int)c->z_lo; A->z_hi = (int)c->z_hi;
     A->size = c->ip.volume_size;
     A->B = c->bounds;
-    A->hist = c->int_hist_on ? c->int_hist : nullptr;
 }
 
 #ifndef HKF_EMULATE_DEVICE      /* host launch code below (tests/emu stops here) */
@@ -606,7 +605,8 @@ static int launch_integrate(hkf_ctx* c, const IntegrateArgs& A, const IntegrateC
     const int parity = c->int_parity;
     c->int_parity ^= 1;
     const dim3 g1(div_up(ngroups, INT_GB)), b1(256);
-    hkf_launch_pdl(k_integrate_items<FROM_STATE, COLOR>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity);
+    if (c->int_hist_on) hkf_launch_pdl(k_integrate_items<FROM_STATE, COLOR, true>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, c->int_hist);
+    else hkf_launch_pdl(k_integrate_items<FROM_STATE, COLOR, false>, g1, b1, 0, c->stream, A, c->st, c->int_items, c->int_capacity, parity, (unsigned*)nullptr);
     HKF_LAUNCH_CHECK(c);
     // function attributes are per device: set once per context (dynamic shared memory above the 48 KB default)
     const int variant = COLOR ? 2 : COUNT_ONLY ? 1 : 0;

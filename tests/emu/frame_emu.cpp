@@ -94,14 +94,13 @@ extern "C" unsigned long long emu_integrate(void* h, float* vol, int R, float S,
     A.trunc = trunc; A.maxdist = maxdist; A.wmax = wmax;
     A.R = R; A.z_lo = 0; A.z_hi = R; A.size = S;
     A.B = f->bounds.B;
-    A.hist = nullptr;
     HkfDeviceState st;
     memset(&st, 0, sizeof(st));
     const unsigned capacity = 4u * (unsigned)R * (unsigned)(R / 4) * div_up((unsigned)R, 128);
     std::vector<uint4> items(capacity);
     const int ngroups = R * (R / INT_G);
     const dim3 g1(div_up((unsigned)ngroups, INT_GB)), b1(256);
-    emu_launch(g1, b1, [&]() { k_integrate_items<false, false>(A, &st, items.data(), capacity, 0); });
+    emu_launch(g1, b1, [&]() { k_integrate_items<false, false, false>(A, &st, items.data(), capacity, 0, nullptr); });
     const unsigned long long counts = (unsigned long long)st.int_items[0] | ((unsigned long long)st.int_items[1] << 32);
     emu_launch(dim3(2), dim3(INT_THREADS), [&]() {          // persistent warps: any grid size walks the whole list
         k_integrate<false, false, false>(A, f->trunc.data(), reinterpret_cast<float2*>(vol), &st, items.data(), capacity, 0, IntegrateColor{});
