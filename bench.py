@@ -488,10 +488,42 @@ def run_config(args, rank, world, local_rank):
     launches = ctx.launches() - l0
     pose, st = ctx.frame_result()
     extra = {"track_status_last": int(st), "pose_err_vs_gt_m": float(np.abs(pose[:3, 3] - gt[(W + K - 1) % len(gt)][:3, 3]).max())}
+    c1_more = {}
     if wl == "c1":
-        peak, _ = measured_hbm_peak()
+        peak, peak_src = measured_hbm_peak()
         gbs = (16.0 * n_upd + 4.0 * cfg.cols * cfg.rows * K) / t / 1e9
         extra.update({"integration_GBps_algorithmic": gbs, "frac_of_hbm_peak": gbs / peak, "n_upd_mean": n_upd / K})
+        c1_more["roofline"] = {"bound": "hbm", "kernel": "k_integrate_items + k_integrate (both launches of every integration, CUDA events)",
+                               "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                               "algorithmic_bytes_per_launch": (16.0 * n_upd + 4.0 * cfg.cols * cfg.rows * K) / K, "kernel_ms_mean": t * 1e3 / K}
+        # e2e: host frames and host poses (CameraPoseFinderFromFile's situation): per step the 614 KB frame H2D inside
+        # hkf_preprocess, hkf_set_pose (asynchronous since round 2), the integration, and one D2H status read + sync
+        host = torch.from_numpy(frames.view(np.int16)).pin_memory()
+        runs = []
+        for rep in range(3):
+            ctx.reset_volume(); ctx.sync()
+            t0 = time.perf_counter()
+            for i in range(K):
+                ctx._ck(ctx.lib.hkf_preprocess(ctx._h, host.data_ptr() + i * fb, 0, ctx.fp), "hkf_preprocess")
+                ctx.set_pose(gt32[i])
+                ctx.integrate_tracked()
+                ctx.frame_result()
+            runs.append(K / (time.perf_counter() - t0))
+        c1_more["e2e"] = {"value": float(np.sort(runs)[1]), "unit": "frames/s", "h2d_bytes_per_step": int(fb), "d2h_bytes_per_step": 264,
+                          "runs_fps": runs, "note": "per step: hkf_preprocess(host u16 frame) + hkf_set_pose + hkf_integrate_tracked + hkf_frame_result; median of three"}
+        if rank == 0 and not args.no_cpu_baseline:
+            # the reference's host loop shape for this config: the C port of preprocess + integration at 256^3 on the host cores
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _oracle as O
+            nf = min(args.cpu_frames, K)
+            vol = np.zeros((256, 256, 256, 2), np.float32)
+            t0 = time.perf_counter()
+            for i in range(nf):
+                tr = O.trunc(O.decode_mm(frames[i]), cfg.trunc_min, cfg.trunc_max)
+                O.integrate(vol, cfg, tr, gt32[i])
+            dt = time.perf_counter() - t0
+            c1_more["cpu_baseline"] = {"value": nf / dt, "unit": "frames/s", "cores": int(O.cpu().orc_num_threads()), "kind": "port",
+                                       "sample": f"frames 0..{nf - 1} of the same sequence: decode + truncate + TSDF integration into 256^3 with the C port (gcc -O2 -fopenmp)"}
     if wl == "c3":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.marching_cubes()                                  # first call uploads the case table (one-off)
@@ -508,6 +540,7 @@ def run_config(args, rank, world, local_rank):
     out = {"metric": "fused frames/s" if wl != "c1" else "TSDF integrations/s", "value": world * K / t, "unit": "frames/s", "n_gpus": world, "steps": K,
            "warmup": W, "ms_per_step": t * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic analytic scene, 16-bit mm depth", "config": dict({"workload": names[wl]}, **extra), "gpu_launches": int(launches)}
+    out.update(c1_more)
     ctx.close()
     return out
 

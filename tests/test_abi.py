@@ -54,3 +54,40 @@ def test_config_defaults_follow_reference_config_ini():
     assert np.float32(cfg.ray_increment) == np.float32(0.8) * np.float32(0.04)
     c1 = cfg.level_camera(1)
     assert (c1.cols, c1.rows) == (320, 240) and c1.fx == 262.5 and c1.cx == 159.75
+
+
+def test_shim_compiles_against_the_reference_headers(tmp_path):
+    """integration/CudaWrappers.h - the file a maintainer of the reference drops over src/cuda/CudaWrappers.h - compiled
+    against the reference's OWN src/AppParams.h and src/cuda/Mat.h: the 13 wrapper signatures of
+    src/cuda/CudaWrappers.h:22-36 type-check with the reference's types and the reinterpret_cast layout claims hold
+    (static_asserts in the shim).  Needs the reference checkout (dev container only)."""
+    import shutil
+    import subprocess
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref) or shutil.which("g++") is None:
+        pytest.skip("reference checkout or g++ not available")
+    tree = tmp_path / "cuda"
+    tree.mkdir()
+    shutil.copy(os.path.join(ROOT, "integration", "CudaWrappers.h"), tree / "CudaWrappers.h")
+    tu = tmp_path / "tu.cpp"
+    tu.write_text('''#include <iostream>
+#include <string>
+#include <vector>
+using namespace std;
+#include "cuda/CudaWrappers.h"
+hkf_ctx* g_hkf = nullptr;
+void touch()
+{
+    Mat44 m = Mat44::getIdentity();
+    CameraParams c = AppParams::instance()->_depth_camera_params;
+    cudaTruncDepth(0.3f, 4.f); cudaBiliearFilterDepth(2.f, 0.02f); cudaCalculateNewVertices(c); cudaCalculateNewNormals();
+    cudaDownSampleNewVertices(); cudaDownSampleNewNormals(); cudaDownSampleModelVertices(); cudaDownSampleModelNormals();
+    cudaCalPointToPlaneErrSolverParams(0, m, m, c, 0.1f, 0.2f); cudaCalSDFSolverParams(c, m);
+    cudaIntegrateVolume(true, false, m, AppParams::instance()->_integrate_params, c, AppParams::instance()->_rgb_camera_params);
+    cudaRaycastingVolume(true, m, AppParams::instance()->_raycast_params, c, 0.3f, 4.f);
+    cudaMarchingcube(true, 1.f);
+}
+''')
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", f"-I{tmp_path}", f"-I{os.path.join(ROOT, 'include')}", f"-I{ref}", f"-I{ref}/cuda",
+                        "-I/usr/local/cuda/include", str(tu)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
