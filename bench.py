@@ -584,14 +584,19 @@ def run_c4(args, rank, world, local_rank):
                 ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev_frames.data_ptr() + i * frames[0].nbytes, 1, ctx.fp), "hkf_preprocess")
                 if i:
                     ctx.icp_track()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
                 e0.record(st_)
-                ctx.integrate_tracked(); ctx.raycast_tracked()
+                ctx.integrate_tracked()
                 e1.record(st_)
+                if ctx.peer_halo:                 # the slab raycast waits for the neighbours' integration inside the kernel:
+                    ctx.sync(); dist.barrier()    # keep that wait out of this rank's own cost (calibration only, untimed)
+                e2.record(st_)
+                ctx.raycast_tracked()
+                e3.record(st_)
                 ctx._ck(ctx.lib.hkf_shard_composite_raycast(ctx._h), "composite")
                 ctx.sync()
                 if i >= W:
-                    local_ms += e0.elapsed_time(e1)
+                    local_ms += e0.elapsed_time(e1) + e2.elapsed_time(e3)
             prof = shard.gather_plane_profile(ctx, cfg, rank, world, local_rank)
             ctx.profile(False)
             info = torch.tensor([local_ms, ctx.cfg.slab_z0, ctx.cfg.slab_z1], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -601,7 +606,8 @@ def run_c4(args, rank, world, local_rank):
             plane_cost = np.zeros(cfg.resolution)
             for x in allinfo:
                 ms, z0, z1 = float(x[0]), int(x[1]), int(x[2])
-                s0, s1 = max(z0 - halo_, 0), min(z1 + halo_, cfg.resolution)
+                h_ = ctx.cfg.slab_halo            # 0 with the peer-memory halo: a rank stores what it owns
+                s0, s1 = max(z0 - h_, 0), min(z1 + h_, cfg.resolution)
                 plane_cost[z0:z1] = shape[z0:z1] * (ms / max(shape[s0:s1].sum(), 1e-12))
             if rank == 0:
                 print(f"[c4 balance] round {rnd}: owned planes {[int(x[2]) - int(x[1]) for x in allinfo]}, slab-local ms per {K} frames "
@@ -735,7 +741,8 @@ def run_c4(args, rank, world, local_rank):
     slabs = [None] * world
     if world > 1:
         import torch.distributed as dist
-        mine = torch.tensor([ctx.cfg.slab_z0, ctx.cfg.slab_z1, max(ctx.cfg.slab_z0 - halo, 0), min(ctx.cfg.slab_z1 + halo, cfg.resolution)],
+        sh_ = ctx.cfg.slab_halo
+        mine = torch.tensor([ctx.cfg.slab_z0, ctx.cfg.slab_z1, max(ctx.cfg.slab_z0 - sh_, 0), min(ctx.cfg.slab_z1 + sh_, cfg.resolution)],
                             dtype=torch.int64, device=f"cuda:{local_rank}")
         gs = [torch.zeros(4, dtype=torch.int64, device=f"cuda:{local_rank}") for _ in range(world)]
         dist.all_gather(gs, mine)
@@ -757,7 +764,9 @@ def run_c4(args, rank, world, local_rank):
                      "icp": None if world == 1 else ("replicated on every rank (no exchange)" if replicated else "banded rows + exchange of the 27 sums"),
                      "other_icp_mode": None if world == 1 else {"icp": "banded rows + exchange of the 27 sums" if replicated else "replicated on every rank (no exchange)",
                                                                 "fps": [K / float(x) for x in t_other], "value": K / float(np.sort(t_other)[len(t_other) // 2])},
-                     "peer_access_map": peer_map, "halo_planes": halo if world > 1 else 0, "slab_balance": balance if world > 1 else None,
+                     "peer_access_map": peer_map, "halo_planes": halo if world > 1 else 0,
+                     "halo": (("read in the neighbours' memory over NVLink by the slab raycast (hkf_shard_peer_halo), not stored" if getattr(ctx, "peer_halo", False)
+                               else "stored and integrated by every rank") if world > 1 else None), "slab_balance": balance if world > 1 else None,
                      "owned_planes_per_rank": [s_[1] - s_[0] for s_ in slabs], "stored_planes_per_rank": [s_[3] - s_[2] for s_ in slabs],
                      "stage_us_per_rank": {"preprocess": [round(x[0], 1) for x in all_stage], "icp": [round(x[1], 1) for x in all_stage],
                                            "integrate": [round(x[2], 1) for x in all_stage], "raycast+composite": [round(x[3], 1) for x in all_stage]},

@@ -79,7 +79,7 @@ EXPORTS = [
     "hkf_integrate_volume", "hkf_raycasting_volume", "hkf_marchingcube", "hkf_triangle_count", "hkf_preprocess",
     "hkf_set_pose", "hkf_icp_track", "hkf_sdf_track", "hkf_integrate_tracked", "hkf_raycast_tracked",
     "hkf_frame_result", "hkf_count_integrate_updates", "hkf_shard_unique_id", "hkf_shard_init",
-    "hkf_shard_composite_raycast", "hkf_shard_ipc_handles", "hkf_shard_connect", "hkf_preprocess_next", "hkf_swap_frame",
+    "hkf_shard_composite_raycast", "hkf_shard_ipc_handles", "hkf_shard_connect", "hkf_shard_peer_halo", "hkf_preprocess_next", "hkf_swap_frame",
     "hkf_upload_color", "hkf_integrate_profile", "hkf_integrate_profile_read", "hkf_shard_set_icp_mode",
 ]
 
@@ -147,6 +147,7 @@ def load() -> C.CDLL:
     lib.hkf_shard_init.argtypes = [P, C.c_int, C.c_int, C.c_void_p]
     lib.hkf_shard_ipc_handles.argtypes = [P, C.c_void_p]
     lib.hkf_shard_connect.argtypes = [P, C.c_void_p, C.c_int]
+    lib.hkf_shard_peer_halo.argtypes = [P, C.c_uint, C.c_void_p, C.c_int]
     _lib = lib
     return lib
 

@@ -78,6 +78,7 @@ struct ShardMailbox {
     // low-latency protocol NCCL calls LL)
     unsigned long long sums[2][HKF_MAX_RANKS][32];
     unsigned ready[HKF_MAX_RANKS];         // raycast epoch whose keys/payload the source rank has finished writing
+    unsigned integ[HKF_MAX_RANKS];         // raycast epoch for which the source rank's integration is complete (peer-memory halo)
 };
 struct ShardPeers {
     ShardMailbox* mail[HKF_MAX_RANKS];                 // mail[r] = rank r's mailbox as mapped in this process
@@ -86,6 +87,8 @@ struct ShardPeers {
     // rank (posted stores over NVLink, overlapped with the march); compositing then reads local memory only.
     unsigned long long* keys_in[HKF_MAX_RANKS];
     float4* pay_in[HKF_MAX_RANKS];
+    const float2* vol[HKF_MAX_RANKS];                  // rank r's stored planes (peer-memory halo); z range below
+    int vol_z_lo[HKF_MAX_RANKS], vol_z_hi[HKF_MAX_RANKS];
     int rank, nranks;
 };
 
@@ -163,6 +166,9 @@ struct hkf_ctx {
     float4* pay_in = nullptr;
     ShardPeers peers{};
     bool p2p = false;                  // peers mapped: exchanges go over peer memory instead of NCCL
+    // peer-memory halo (hkf_shard_peer_halo): the neighbours' planes this rank reads instead of storing them
+    const float2* halo_lo = nullptr; const float2* halo_hi = nullptr;
+    unsigned halo_z_lo = 0, halo_z_hi = 0;
     bool icp_replicated = false;       // sharded mode: every rank tracks on the whole image, no exchange of the 27 sums
     unsigned shard_seq = 0, shard_epoch = 0;
     void* ipc_opened[HKF_MAX_RANKS][4]{};

@@ -71,22 +71,25 @@ template <bool SLAB>
 __device__ __forceinline__ bool mc_candidate(const VolView& V, int x, int y, int z, float2 ctr)
 {
     const int R = V.R;
-    if (!(x >= 1 && y >= 1 && z >= 1 && x <= R - 2 && y <= R - 2 && z <= R - 2 && (!SLAB || (z - 1 >= V.z_lo && z + 1 < V.z_hi)))) return true;
+    if (!(x >= 1 && y >= 1 && z >= 1 && x <= R - 2 && y <= R - 2 && z <= R - 2 && (!SLAB || (z - 1 >= V.kz_lo && z + 1 < V.kz_hi)))) return true;
     if (ctr.y == 0.f) return false;
     const float2* p0 = V.vol + vol_index(V, x, y, z);
     bool any_pos = false, any_neg = false, unobserved = false;
 #pragma unroll
-    for (int dz = -1; dz <= 1; ++dz)
+    for (int dz = -1; dz <= 1; ++dz) {
+        // SLAB: the plane above / below may be a neighbour's (peer-memory halo)
+        const float2* pz = SLAB ? vol_plane(V, z + dz) + ((size_t)y * R + x) : p0 + (ptrdiff_t)dz * R * R;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
-                const float2 q = __ldg(p0 + ((ptrdiff_t)dz * R + dy) * R + dx);
+                const float2 q = __ldg(pz + (ptrdiff_t)dy * R + dx);
                 unobserved |= (q.y == 0.f);
                 any_pos |= (q.x > 0.f);
                 any_neg |= (q.x < 0.f);
                 if (!(q.x > 0.f) && !(q.x < 0.f)) { any_pos = true; any_neg = true; }   // zero (or NaN): undecided
             }
+    }
     return !unobserved && any_pos && any_neg;
 }
 

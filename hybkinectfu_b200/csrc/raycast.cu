@@ -34,6 +34,7 @@ struct RaycastArgs {
     float pose[16];
     int own_z0, own_z1, rank;
     int nranks; unsigned epoch;        // peer-memory mode: epoch of this raycast (its parity selects the inbox)
+    int halo_wait;                     // peer-memory halo in use: wait for the neighbours' integration (see the kernel)
     ShardPeers peers;                  // peer-memory mode: where hits are pushed (peers.nranks == 0: no push)
     // has_color (raycastingVolume.cu:101-106): the voxel colour plane and raycast_rgb; nullptr = depth only.  The colour
     // of a hit is interpolated at the refined vertex BEFORE the gradient is evaluated and is written whenever that
@@ -56,6 +57,36 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
 {
     hkf_pdl_enter();
+#ifndef HKF_EMULATE_DEVICE             // (the host emulation of this kernel runs one thread at a time, one rank)
+    if (SLAB && A.halo_wait) {
+        // peer-memory halo: the neighbours' planes are read in place, so their integration of this frame must be complete.
+        // Block 0 announces this rank's (stream order: its integration launches have finished; system fence), every block
+        // waits for the two neighbours' announcements of the same epoch.  (The reverse hazard - a neighbour integrating the
+        // NEXT frame while this march still reads its planes - is excluded by the compositing handshake: its integration
+        // follows its compositing, which waits for this rank's raycast.)
+        __shared__ int s_go;
+        if (threadIdx.x == 0) {
+            const ShardPeers& P = A.peers;
+            if (blockIdx.x == 0 && blockIdx.y == 0) {
+                __threadfence_system();
+                if (P.rank > 0) *(volatile unsigned*)&P.mail[P.rank - 1]->integ[P.rank] = A.epoch;
+                if (P.rank + 1 < P.nranks) *(volatile unsigned*)&P.mail[P.rank + 1]->integ[P.rank] = A.epoch;
+            }
+            bool ok = true;
+            const long long t0 = clock64();
+            for (int d = -1; d <= 1 && ok; d += 2) {
+                const int r = P.rank + d;
+                if (r < 0 || r >= P.nranks) continue;
+                while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->integ[r] - A.epoch) < 0)
+                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }          // ~2 s: a peer died
+            }
+            __threadfence_system();
+            s_go = ok;
+        }
+        __syncthreads();
+        if (!s_go) return;                 // the compositing times out on the same peer and sets HKF_TRACK_PEER_TIMEOUT
+    }
+#endif
     // 16x16 pixel block, warps as 8x4 patches
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
@@ -101,14 +132,17 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         bool last_known = true;
         float t_leave = 3.0e38f;
         if (SLAB) {
-            // Samples before the ray enters the stored planes (minus two cells of slack) cannot be read by this rank:
-            // advance t through them with the same repeated float addition (the sample sequence is part of parity),
-            // skipping the voxel arithmetic; past the far side of the slab nothing more can be detected.
-            const float zl = V.z_lo == 0 ? -1.0e30f : ((float)V.z_lo - 2.0f) * V.cell;
-            const float zh = V.z_hi == R ? 1.0e30f : ((float)V.z_hi + 2.0f) * V.cell;
+            // A rank reports the crossings whose LATER sample lies in a plane it owns (any earlier crossing of the ray
+            // belongs to another rank, whose smaller key wins the compositing).  So only the samples inside the owned
+            // planes (one cell of slack for the rounding of the voxel index) and the one sample before them matter:
+            // t advances through everything earlier with the same repeated float addition (the sample sequence is part
+            // of parity) without the voxel arithmetic, and the march stops where the ray leaves the owned planes.  The
+            // halo planes are only touched by that one earlier sample and by the refinement of a crossing.
+            const float zl = A.own_z0 == 0 ? -1.0e30f : ((float)A.own_z0 - 1.0f) * V.cell;
+            const float zh = A.own_z1 == R ? 1.0e30f : ((float)A.own_z1 + 1.0f) * V.cell;
             const float ta = (zl - oz) / dz, tb = (zh - oz) / dz;
             const float t_enter = fminf(ta, tb) - A.inc;
-            t_leave = fmaxf(ta, tb) + A.inc;
+            t_leave = fmaxf(ta, tb);
             if (t < t_enter) {
                 while (t < t_enter && t < tmax) t = __fadd_rn(A.inc, t);
                 last_known = false;
@@ -160,9 +194,12 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 int gx, gy, gz;
                 voxel3(t, gx, gy, gz);
                 gzs[b] = gz;
-                const int gzc = SLAB ? min(max(gz, V.z_lo), V.z_hi - 1) : gz;      // keep the speculative read inside the slab
-                if (FAST) sd[b] = __ldg(&V.vol[((unsigned)(gzc - V.z_lo) * (unsigned)R + (unsigned)gy) * (unsigned)R + (unsigned)gx].x);
-                else sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gzc)].x);
+                if (SLAB) {
+                    // keep the speculative read inside the readable planes; a plane of the halo comes from a neighbour's memory
+                    const int gzc = min(max(gz, V.kz_lo), V.kz_hi - 1);
+                    sd[b] = __ldg(&(vol_plane(V, gzc) + ((unsigned)gy * (unsigned)R + (unsigned)gx))->x);
+                } else if (FAST) sd[b] = __ldg(&V.vol[((unsigned)gz * (unsigned)R + (unsigned)gy) * (unsigned)R + (unsigned)gx].x);
+                else sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gz)].x);
                 t = __fadd_rn(A.inc, t);
             }
             // Nothing can happen in this batch (the common case) unless a (+ -> -) pair shows up, the ray reaches t_max,
@@ -173,7 +210,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
 #pragma unroll
                 for (int b = 0; b < RAY_NB; ++b) {
                     event |= (prev > 0.0f) & (sd[b] < 0.0f);
-                    if (SLAB) event |= (unsigned)(gzs[b] - V.z_lo) >= (unsigned)(V.z_hi - V.z_lo);
+                    if (SLAB) event |= (unsigned)(gzs[b] - V.kz_lo) >= (unsigned)(V.kz_hi - V.kz_lo);
                     prev = sd[b];
                 }
                 if (!event) {
@@ -186,7 +223,7 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
                 if (done) break;
                 if (!(ts[b] < tmax)) { done = true; break; }
                 const int gz = gzs[b];
-                const bool known = !SLAB || (gz >= V.z_lo && gz < V.z_hi);
+                const bool known = !SLAB || (gz >= V.kz_lo && gz < V.kz_hi);
                 const float sdf = known ? sd[b] : 0.f;
                 if (known && last_known && last_sdf > 0.0f && sdf < 0.0f) {
                     // first zero crossing: the ray ends here whatever happens next
@@ -270,7 +307,8 @@ static void fill_ray_args(hkf_ctx* c, const float* pose, const HkfRayCasterParam
     A->nranks = c->nranks; A->epoch = 0;
     A->peers = ShardPeers{};
     A->color_vol = nullptr; A->color_out = nullptr;
-    if (c->p2p) { A->peers = c->peers; A->epoch = ++c->shard_epoch; }
+    A->halo_wait = 0;
+    if (c->p2p) { A->peers = c->peers; A->epoch = ++c->shard_epoch; A->halo_wait = (c->halo_lo || c->halo_hi) ? 1 : 0; }
 }
 
 static inline bool is_slab(const hkf_ctx* c) { return !(c->z_lo == 0 && c->z_hi == c->ip.volume_resolution); }

@@ -129,6 +129,7 @@ extern "C" int hkf_shard_ipc_handles(hkf_ctx* c, void* out)
     HKF_CUDA(c, cudaIpcGetMemHandle(&h[0], c->mailbox));
     HKF_CUDA(c, cudaIpcGetMemHandle(&h[1], c->keys_in));
     HKF_CUDA(c, cudaIpcGetMemHandle(&h[2], c->pay_in));
+    HKF_CUDA(c, cudaIpcGetMemHandle(&h[3], c->vol));
     memcpy(out, h, sizeof(h));
     return HKF_OK;
 }
@@ -143,19 +144,50 @@ extern "C" int hkf_shard_connect(hkf_ctx* c, const void* all_handles, int nranks
     ShardPeers P{};
     P.rank = c->rank; P.nranks = nranks;
     for (int r = 0; r < nranks; ++r) {
-        void* ptr[3];
+        void* ptr[4];
         if (r == c->rank) {
-            ptr[0] = c->mailbox; ptr[1] = c->keys_in; ptr[2] = c->pay_in;
+            ptr[0] = c->mailbox; ptr[1] = c->keys_in; ptr[2] = c->pay_in; ptr[3] = c->vol;
         } else {
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 HKF_CUDA(c, cudaIpcOpenMemHandle(&ptr[k], h[r * 4 + k], cudaIpcMemLazyEnablePeerAccess));
                 c->ipc_opened[r][k] = ptr[k];
             }
         }
         P.mail[r] = (ShardMailbox*)ptr[0]; P.keys_in[r] = (unsigned long long*)ptr[1]; P.pay_in[r] = (float4*)ptr[2];
+        P.vol[r] = (const float2*)ptr[3];
     }
     c->peers = P;
     c->p2p = true;
+    return HKF_OK;
+}
+
+// Peer-memory halo: instead of storing and integrating `halo` planes of its neighbours a second time (at 1024^3 over 8
+// ranks that is 40 planes on top of 60-80 owned ones), a rank reads them in the neighbours' memory over NVLink: only the
+// slab raycast needs them - about one 4-byte sample per ray at the slab's entry, and the refinement of crossings next to a
+// boundary.  own_ranges = nranks pairs (z0, z1) of the OWNED planes of every rank (= what each rank stores: contexts are
+// created with slab_halo = 0); every slab must be at least `halo` planes thick.  Call after hkf_shard_connect.
+extern "C" int hkf_shard_peer_halo(hkf_ctx* c, unsigned halo, const unsigned* own_ranges, int nranks)
+{
+    if (!c || !own_ranges) return HKF_ERR_ARG;
+    if (!c->p2p || nranks != c->nranks) { c->err = "hkf_shard_peer_halo: call hkf_shard_connect first (same rank count)"; return HKF_ERR_STATE; }
+    if (c->z_lo != c->own_z0 || c->z_hi != c->own_z1) { c->err = "hkf_shard_peer_halo: the context stores a halo of its own (create it with slab_halo = 0)"; return HKF_ERR_STATE; }
+    const unsigned R = c->ip.volume_resolution;
+    for (int r = 0; r < nranks; ++r) {
+        const unsigned z0 = own_ranges[2 * r], z1 = own_ranges[2 * r + 1];
+        if (z0 >= z1 || z1 > R || (r > 0 && z0 != own_ranges[2 * r - 1]) || z1 - z0 < halo) { c->err = "hkf_shard_peer_halo: slabs must tile [0, R) and be at least `halo` planes thick"; return HKF_ERR_ARG; }
+        c->peers.vol_z_lo[r] = (int)z0; c->peers.vol_z_hi[r] = (int)z1;
+    }
+    if (own_ranges[2 * c->rank] != c->own_z0 || own_ranges[2 * c->rank + 1] != c->own_z1) { c->err = "hkf_shard_peer_halo: own range mismatch"; return HKF_ERR_ARG; }
+    const size_t pl = (size_t)R * R;
+    c->halo_lo = c->halo_hi = nullptr;
+    if (c->rank > 0 && halo) {            // planes [own_z0 - halo, own_z0) of the lower neighbour
+        c->halo_z_lo = c->own_z0 - halo;
+        c->halo_lo = c->peers.vol[c->rank - 1] + (size_t)(c->halo_z_lo - own_ranges[2 * (c->rank - 1)]) * pl;
+    } else c->halo_z_lo = c->own_z0;
+    if (c->rank + 1 < nranks && halo) {   // planes [own_z1, own_z1 + halo) of the upper neighbour: its first planes
+        c->halo_z_hi = c->own_z1 + halo;
+        c->halo_hi = c->peers.vol[c->rank + 1];
+    } else c->halo_z_hi = c->own_z1;
     return HKF_OK;
 }
 

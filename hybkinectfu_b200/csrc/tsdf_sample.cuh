@@ -20,6 +20,11 @@ struct VolView {
     int R;
     float S, cell, Rf;
     int z_lo, z_hi;      // stored planes
+    // peer-memory halo (sharded mode, hkf_shard_peer_halo): planes [kz_lo, z_lo) are read from the lower neighbour's
+    // memory (vlo points at its plane kz_lo), planes [z_hi, kz_hi) from the upper neighbour's (vhi points at its plane
+    // z_hi) - over NVLink, instead of being stored and integrated twice.  Without it kz_lo = z_lo, kz_hi = z_hi.
+    const float2* vlo; const float2* vhi;
+    int kz_lo, kz_hi;    // planes this rank can READ
 };
 
 static inline VolView make_volview(const hkf_ctx* c)
@@ -28,6 +33,8 @@ static inline VolView make_volview(const hkf_ctx* c)
     V.vol = c->vol; V.R = (int)c->ip.volume_resolution; V.S = c->ip.volume_size;
     V.Rf = (float)V.R; V.cell = V.S / V.Rf;
     V.z_lo = (int)c->z_lo; V.z_hi = (int)c->z_hi;
+    V.vlo = c->halo_lo; V.vhi = c->halo_hi;
+    V.kz_lo = c->halo_lo ? (int)c->halo_z_lo : V.z_lo; V.kz_hi = c->halo_hi ? (int)c->halo_z_hi : V.z_hi;
     return V;
 }
 
@@ -40,6 +47,15 @@ __device__ __forceinline__ int vol_w2v(const VolView& V, float p)
 __device__ __forceinline__ size_t vol_index(const VolView& V, int x, int y, int z)
 {
     return ((size_t)(z - V.z_lo) * V.R + y) * V.R + x;
+}
+
+// voxel (0, 0, z) of a READABLE plane z in [kz_lo, kz_hi): this rank's memory or a neighbour's
+__device__ __forceinline__ const float2* vol_plane(const VolView& V, int z)
+{
+    const size_t pl = (size_t)V.R * V.R;
+    if (z < V.z_lo) return V.vlo + (size_t)(z - V.kz_lo) * pl;
+    if (z >= V.z_hi) return V.vhi + (size_t)(z - V.z_hi) * pl;
+    return V.vol + (size_t)(z - V.z_lo) * pl;
 }
 
 // SLAB: planes outside [z_lo, z_hi) are not stored; a read there reports "not available" (-1)
@@ -59,17 +75,19 @@ __device__ __forceinline__ int vol_interp_sdf(const VolView& V, float px, float 
     gx = (px < vx) ? gx - 1 : gx;
     gy = (py < vy) ? gy - 1 : gy;
     gz = (pz < vz) ? gz - 1 : gz;
-    if (SLAB && (gz < V.z_lo || gz + 1 >= V.z_hi)) return -1;
+    if (SLAB && (gz < V.kz_lo || gz + 1 >= V.kz_hi)) return -1;
     const float a = __fdiv_rn(__fmaf_rn(__fadd_rn((float)gx, 0.5f), -cell, px), cell);
     const float b = __fdiv_rn(__fmaf_rn(__fadd_rn((float)gy, 0.5f), -cell, py), cell);
     const float c = __fdiv_rn(__fmaf_rn(__fadd_rn((float)gz, 0.5f), -cell, pz), cell);
-    const float2* p0 = V.vol + vol_index(V, gx, gy, gz);
-    const size_t sy = (size_t)R, sz = (size_t)R * R;
+    const size_t sy = (size_t)R;
+    // the two planes of the cell (in sharded mode they may live in different ranks' memory)
+    const float2* p0 = SLAB ? vol_plane(V, gz) + ((size_t)gy * R + gx) : V.vol + vol_index(V, gx, gy, gz);
+    const float2* p1 = SLAB ? vol_plane(V, gz + 1) + ((size_t)gy * R + gx) : p0 + (size_t)R * R;
     // issue all eight loads before testing: independent requests, same 2 rows x 2 planes
     const float2 v000 = __ldg(p0), v100 = __ldg(p0 + 1);
     const float2 v010 = __ldg(p0 + sy), v110 = __ldg(p0 + sy + 1);
-    const float2 v001 = __ldg(p0 + sz), v101 = __ldg(p0 + sz + 1);
-    const float2 v011 = __ldg(p0 + sz + sy), v111 = __ldg(p0 + sz + sy + 1);
+    const float2 v001 = __ldg(p1), v101 = __ldg(p1 + 1);
+    const float2 v011 = __ldg(p1 + sy), v111 = __ldg(p1 + sy + 1);
     if (v000.y == 0.f || v001.y == 0.f || v010.y == 0.f || v011.y == 0.f ||
         v100.y == 0.f || v101.y == 0.f || v110.y == 0.f || v111.y == 0.f) return 0;
     const float ia = __fsub_rn(1.0f, a), ib = __fsub_rn(1.0f, b), ic = __fsub_rn(1.0f, c);

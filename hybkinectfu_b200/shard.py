@@ -76,7 +76,8 @@ def plane_cost_from_profile(profile: np.ndarray) -> np.ndarray:
 def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int = 8, plane_cost=None):
     """slab_ranges with boundaries chosen so that every rank gets the same share of plane_work over the planes it
     STORES (owned + halo: the halo is integrated and marched redundantly, so thin slabs cost more than they own).
-    The view frustum widens with depth: equal-thickness slabs are not equal work."""
+    The view frustum widens with depth: equal-thickness slabs are not equal work.
+    halo = 0 with min_planes >= the raycast halo: the peer-memory-halo cut (nothing stored or integrated twice)."""
     R = cfg.resolution
     if nranks == 1:
         return [(0, R, 0, R)]
@@ -108,6 +109,25 @@ def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int
             lo = mid
     cuts = greedy(hi)
     return [(cuts[r], cuts[r + 1], max(cuts[r] - halo, 0), min(cuts[r + 1] + halo, R)) for r in range(nranks)]
+
+
+def plan_slabs(cfg, nranks: int, halo: int, p2p: bool, balanced: bool = True, plane_cost=None):
+    """(ranges, peer_halo): the slab cut of sharded_context.  With peer memory (and env HKF_SHARD_PEER_HALO != 0) the
+    halo planes are READ in the neighbours' memory by the slab raycast (hkf_shard_peer_halo) instead of being stored
+    and integrated a second time: the cut then balances the owned planes only and keeps every slab at least `halo`
+    planes thick (a ray's halo reads must not reach past the adjacent rank); if the volume is too small for that the
+    stored-halo layout is used.  Every rank computes the same answer from the same arguments."""
+    R = cfg.resolution
+    peer = bool(p2p) and nranks > 1 and os.environ.get("HKF_SHARD_PEER_HALO", "1") != "0" and R // nranks >= max(halo, 8)
+    if peer:
+        if balanced:
+            rs = balanced_slab_ranges(cfg, nranks, 0, min_planes=max(halo, 8), plane_cost=plane_cost)
+        else:
+            rs = slab_ranges(R, nranks, 0)
+        if min(z1 - z0 for z0, z1, _, _ in rs) >= halo:
+            return rs, True
+    rs = balanced_slab_ranges(cfg, nranks, halo, plane_cost=plane_cost) if balanced else slab_ranges(R, nranks, halo)
+    return rs, False
 
 
 def icp_band(rows: int, rank: int, nranks: int):
@@ -184,9 +204,11 @@ def sharded_context(cfg, rank: int, nranks: int, device: int, p2p=None, balanced
     torch.distributed process group (any backend) to hand the unique id round."""
     from . import capi
     halo = halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
-    ranges = balanced_slab_ranges(cfg, nranks, halo, plane_cost=plane_cost) if balanced else slab_ranges(cfg.resolution, nranks, halo)
+    if p2p is None:
+        p2p = os.environ.get("HKF_SHARD_P2P", "1") != "0" and nranks <= 8
+    ranges, peer_halo = plan_slabs(cfg, nranks, halo, p2p, balanced, plane_cost)
     z0, z1, _, _ = ranges[rank]
-    c = dataclasses.replace(cfg, slab_z0=z0, slab_z1=z1, slab_halo=halo)
+    c = dataclasses.replace(cfg, slab_z0=z0, slab_z1=z1, slab_halo=0 if peer_halo else halo)
     ctx = capi.Context(c, device=device)
 
     def make_id():
@@ -196,13 +218,15 @@ def sharded_context(cfg, rank: int, nranks: int, device: int, p2p=None, balanced
 
     uid = broadcast_unique_id(make_id)
     ctx._ck(ctx.lib.hkf_shard_init(ctx._h, rank, nranks, uid), "hkf_shard_init")
-    if p2p is None:
-        p2p = os.environ.get("HKF_SHARD_P2P", "1") != "0" and nranks <= 8
     if p2p:
         h = (C.c_char * IPC_BYTES)()
         ctx._ck(ctx.lib.hkf_shard_ipc_handles(ctx._h, h), "hkf_shard_ipc_handles")
         allh = all_gather_bytes(bytes(h))
         ctx._ck(ctx.lib.hkf_shard_connect(ctx._h, allh, nranks), "hkf_shard_connect")
+        if peer_halo:
+            own = (C.c_uint * (2 * nranks))(*[v for r_ in ranges for v in r_[:2]])
+            ctx._ck(ctx.lib.hkf_shard_peer_halo(ctx._h, halo, own, nranks), "hkf_shard_peer_halo")
+    ctx.peer_halo = bool(peer_halo)
     return ctx
 
 

@@ -256,6 +256,11 @@ int hkf_shard_composite_raycast(hkf_ctx* ctx);
 #define HKF_SHARD_IPC_BYTES 256
 int hkf_shard_ipc_handles(hkf_ctx* ctx, void* out_handles);
 int hkf_shard_connect(hkf_ctx* ctx, const void* all_handles, int nranks);
+/* Peer-memory halo (after hkf_shard_connect; contexts created with slab_halo = 0): the `halo` planes on either side of
+ * the owned range that the slab raycast needs are read in the neighbours' memory over NVLink instead of being stored and
+ * integrated a second time.  own_ranges = nranks pairs (z0, z1) of the owned planes of every rank, tiling [0, R), each at
+ * least `halo` planes thick.  The raycast then waits for the neighbours' integration of the frame (one more flag). */
+int hkf_shard_peer_halo(hkf_ctx* ctx, unsigned halo, const unsigned* own_ranges, int nranks);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ extern "C" int emu_raycast(const float* vol, int R, float S, unsigned cols, unsi
     RaycastArgs A;
     memset(&A, 0, sizeof(A));
     A.V.vol = reinterpret_cast<const float2*>(vol);
-    A.V.R = R; A.V.S = S; A.V.Rf = (float)R; A.V.cell = S / (float)R; A.V.z_lo = 0; A.V.z_hi = R;
+    A.V.R = R; A.V.S = S; A.V.Rf = (float)R; A.V.cell = S / (float)R; A.V.z_lo = 0; A.V.z_hi = R; A.V.kz_lo = 0; A.V.kz_hi = R;
     A.cols = (int)cols; A.rows = (int)rows; A.cx = cx; A.cy = cy; A.fx = fx; A.fy = fy;
     A.inc = inc; A.near_plane = near_plane; A.far_plane = far_plane;
     memcpy(A.pose, pose16, 64);

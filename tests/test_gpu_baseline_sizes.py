@@ -2,7 +2,7 @@
 that the CPU oracle finishes in seconds): every comparison here is against the reference's own UNMODIFIED kernels
 (oracle/_ref/libhkf_ref.so, driven by oracle/ref_harness.cu) running on the same GPU.
 
-  C2  100 frames 640x480 -> 512^3, fused ICP pipeline vs the reference pipeline frame by frame (pose tolerance of
+  C2  the whole 500-frame periodic trajectory 640x480 -> 512^3, fused ICP pipeline vs the reference pipeline frame by frame (pose tolerance of
       north_star: 1e-5 rotation, 1e-4 m translation; status equal), final volumes compared voxel by voxel
   C3  SDF tracking at 512^3 frame by frame, then marching cubes on the SAME volume bits: count + sorted multiset exact
   C5  every stage at 1280x960 (where the reference's own pyramid wrappers cannot launch: the fenced kernels define it)
@@ -39,9 +39,10 @@ def _volume_agreement(ours, ref):
     return observed, frac_w, float(d.max()), float((d > 1e-4).sum()) / max(observed, 1)
 
 
-def test_c2_100_frames_512_fused_pipeline_vs_reference_pipeline():
+def test_c2_500_frames_512_fused_pipeline_vs_reference_pipeline():
+    """the pose tolerance measured over the full 500-frame sequence, against the reference's poses"""
     cfg = capi.Config(resolution=512, pyramid_levels=3, max_triangles=1)
-    frames, gt, _ = _sequence(100)
+    frames, gt, _ = _sequence(500)
     ref = O.Ref(cfg)
     ref.reset_volume()
     worst = [0.0, 0.0]
@@ -63,7 +64,7 @@ def test_c2_100_frames_512_fused_pipeline_vs_reference_pipeline():
         ours, theirs = c.download(capi.BUF_VOLUME), ref.download(O.REF_VOLUME)
     ref.check()
     observed, frac_w, dmax, frac_d = _volume_agreement(ours, theirs)
-    print(f"C2 100 frames: worst pose delta rot {worst[0]:.2e} trans {worst[1]:.2e}; observed voxels {observed}, "
+    print(f"C2 500 frames: worst pose delta rot {worst[0]:.2e} trans {worst[1]:.2e}; observed voxels {observed}, "
           f"weight differs on {frac_w:.2e} of them, max |dtsdf| {dmax:.2e}, |dtsdf| > 1e-4 on {frac_d:.2e}")
     assert observed > 20_000_000
     assert frac_w < 1e-3 and frac_d < 1e-3

@@ -13,7 +13,7 @@ import socket
 import numpy as np
 import pytest
 
-from conftest import bits_equal, small_config
+from conftest import bits_equal, canon_tris, small_config
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +37,8 @@ def _frames(n=5):
     return np.stack([synth.render_depth_mm(p.astype(np.float64), cam) for p in poses]), poses
 
 
-def _worker(rank, world, port, q, res):
+def _worker(rank, world, port, q, res, peer_halo):
+    os.environ["HKF_SHARD_PEER_HALO"] = "1" if peer_halo else "0"
     import torch
     import torch.distributed as dist
     from hybkinectfu_b200 import capi, shard, synth
@@ -48,7 +49,7 @@ def _worker(rank, world, port, q, res):
         cfg = small_config(res)
         frames, gt = _frames()
         ctx = shard.sharded_context(cfg, rank, world, rank)
-        out = {"slab": (ctx.cfg.slab_z0, ctx.cfg.slab_z1, ctx.cfg.slab_halo)}
+        out = {"slab": (ctx.cfg.slab_z0, ctx.cfg.slab_z1, ctx.cfg.slab_halo), "peer_halo": ctx.peer_halo}
         # ---- poses given
         ctx.set_pose(gt[0])
         for i, mm in enumerate(frames):
@@ -60,6 +61,10 @@ def _worker(rank, world, port, q, res):
         out["given_v"] = ctx.download(capi.BUF_MODEL_VERTICES)
         out["given_n"] = ctx.download(capi.BUF_MODEL_NORMALS)
         out["given_vol"] = ctx.download(capi.BUF_VOLUME)
+        dist.barrier()                    # marching cubes reads neighbour planes (peer halo): everybody has finished
+        n = ctx.marching_cubes()
+        out["given_tris"] = ctx.download(capi.BUF_TRIANGLES)[:n].copy()
+        dist.barrier()
         # ---- ICP tracking
         ctx.reset_volume()
         ctx.set_pose(synth.pose0().astype(np.float32))
@@ -82,14 +87,17 @@ def _worker(rank, world, port, q, res):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("peer_halo", [1, 0])
 @pytest.mark.parametrize("world,res", [(2, 128), (max(2, min(_ngpu(), 8)), 256)])
-def test_sharded_equals_single_gpu(world, res):
+def test_sharded_equals_single_gpu(world, res, peer_halo):
+    """peer_halo=1: the halo planes are read in the neighbours' memory (hkf_shard_peer_halo), every rank stores exactly
+    the planes it owns; peer_halo=0: every rank stores and integrates its halo itself"""
     import torch.multiprocessing as mp
     from hybkinectfu_b200 import capi, shard, synth
     mpc = mp.get_context("spawn")
     q = mpc.Queue()
     port = _free_port()
-    procs = [mpc.Process(target=_worker, args=(r, world, port, q, res)) for r in range(world)]
+    procs = [mpc.Process(target=_worker, args=(r, world, port, q, res, peer_halo)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=600) for _ in range(world))
@@ -105,13 +113,21 @@ def test_sharded_equals_single_gpu(world, res):
         c.preprocess(mm); c.set_pose(gt[i]); c.integrate_tracked(); c.raycast_tracked()
     c.frame_result()
     v1, n1, vol1 = c.download(capi.BUF_MODEL_VERTICES), c.download(capi.BUF_MODEL_NORMALS), c.download(capi.BUF_VOLUME)
-    assert (n1[..., :3] != 0).any(-1).sum() > 1000
+    ntri = c.marching_cubes()
+    tris1 = c.download(capi.BUF_TRIANGLES)[:ntri].copy()
+    assert (n1[..., :3] != 0).any(-1).sum() > 1000 and ntri > 1000
     halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
+    os.environ["HKF_SHARD_PEER_HALO"] = "1" if peer_halo else "0"
+    ranges, peer = shard.plan_slabs(cfg, world, halo, True)
+    assert peer == bool(peer_halo)
+    assert np.array_equal(canon_tris(np.concatenate([got[r]["given_tris"] for r in range(world)])).view(np.uint32),
+                          canon_tris(tris1).view(np.uint32)), "per-slab marching cubes do not add up to the whole mesh"
     for r in range(world):
         assert bits_equal(got[r]["given_v"], v1), f"composited vertices differ on rank {r}"
         assert bits_equal(got[r]["given_n"], n1), f"composited normals differ on rank {r}"
-        z0, z1, s0, s1 = shard.balanced_slab_ranges(cfg, world, halo)[r]
-        assert got[r]["slab"] == (z0, z1, halo)
+        z0, z1, s0, s1 = ranges[r]
+        assert got[r]["peer_halo"] == peer and (s0, s1) == ((z0, z1) if peer else (max(z0 - halo, 0), min(z1 + halo, cfg.resolution)))
+        assert got[r]["slab"] == (z0, z1, 0 if peer else halo)
         assert bits_equal(got[r]["given_vol"], vol1[s0:s1]), f"slab {r} differs from planes [{s0},{s1}) of the whole volume"
     c.reset_volume(); c.set_pose(synth.pose0().astype(np.float32))
     poses = []
