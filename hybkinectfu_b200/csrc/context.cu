@@ -154,6 +154,7 @@ extern "C" int hkf_create(const HkfInitParams* p, int device, hkf_ctx** out)
 extern "C" void hkf_destroy(hkf_ctx* c)
 {
     if (!c) return;
+    if (c->composite_pending) { hkf_shard_flush(c); cudaStreamSynchronize(c->stream); }      // the peers wait for this rank's word
     hkf_shard_release(c);
     free_all(c);
     delete c;
@@ -162,6 +163,7 @@ extern "C" void hkf_destroy(hkf_ctx* c)
 extern "C" int hkf_sync(hkf_ctx* c)
 {
     if (!c) return HKF_ERR_ARG;
+    { const int rc = hkf_shard_flush(c); if (rc != HKF_OK) return rc; }
     if (c->stream2) HKF_CUDA(c, cudaStreamSynchronize(c->stream2));
     HKF_CUDA(c, cudaStreamSynchronize(c->stream));
     return HKF_OK;
@@ -224,6 +226,7 @@ extern "C" size_t hkf_buffer_bytes(hkf_ctx* c, int buffer, unsigned level)
 extern "C" long hkf_download(hkf_ctx* c, int buffer, unsigned level, void* dst, size_t cap)
 {
     if (!c || !dst) return -HKF_ERR_ARG;
+    if (hkf_shard_flush(c) != HKF_OK) return -HKF_ERR_CUDA;
     if (buffer == HKF_BUF_TRIANGLES) {
         unsigned n = 0;
         if (hkf_triangle_count(c, &n) != HKF_OK) return -HKF_ERR_CUDA;
@@ -297,6 +300,7 @@ extern "C" int hkf_upload_color(hkf_ctx* c, const uint8_t* rgb3, int is_device)
 extern "C" int hkf_frame_result(hkf_ctx* c, HkfMat44* pose_out, int* track_status)
 {
     if (!c) return HKF_ERR_ARG;
+    { const int rc = hkf_shard_flush(c); if (rc != HKF_OK) return rc; }
     HKF_CUDA(c, cudaMemcpyAsync(c->st_host, c->st, offsetof(HkfDeviceState, dmax_bits), cudaMemcpyDeviceToHost, c->stream));
     HKF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (pose_out) memcpy(pose_out->m, c->st_host->pose, 64);

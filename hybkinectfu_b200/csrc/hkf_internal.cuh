@@ -167,6 +167,10 @@ struct hkf_ctx {
     ShardPeers peers{};
     bool p2p = false;                  // peers mapped: exchanges go over peer memory instead of NCCL
     // peer-memory halo (hkf_shard_peer_halo): the neighbours' planes this rank reads instead of storing them
+    // sharded mode: the compositing of the last hkf_raycast_tracked is DEFERRED to the next call that needs the model maps
+    // (hkf_icp_track, hkf_frame_result, hkf_download, hkf_sync, the next raycast), so that the next frame's preprocess -
+    // which does not - runs while the peers' hits are still travelling and the slowest rank is still marching
+    bool composite_pending = false;
     const float2* halo_lo = nullptr; const float2* halo_hi = nullptr;
     unsigned halo_z_lo = 0, halo_z_hi = 0;
     bool icp_replicated = false;       // sharded mode: every rank tracks on the whole image, no exchange of the 27 sums
@@ -240,6 +244,7 @@ __device__ __forceinline__ void hkf_pdl_enter_ordered()
 // internal cross-file helpers (C++ linkage)
 void hkf_shard_release(hkf_ctx* c);
 int hkf_shard_allreduce_sums(hkf_ctx* c);
+int hkf_shard_flush(hkf_ctx* c);          // run the deferred compositing, if any
 int hkf_pyramids_fused(hkf_ctx* c, float4** pv, float4** pn, cudaStream_t stream = nullptr, bool track_begin = false);
 int hkf_depth_bounds(hkf_ctx* c);   // depth extrema of trunc_depth (after any write to it outside the fused preprocess)
 int hkf_bounds_rmq(hkf_ctx* c, const DepthBounds& B, cudaStream_t stream);   // the coarser levels of the range-query table

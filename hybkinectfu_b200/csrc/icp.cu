@@ -828,8 +828,9 @@ k_icp_frame(IcpFrameArgs F, HkfDeviceState* st)
 extern "C" int hkf_icp_track(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
+    int rc = hkf_shard_flush(c);             // sharded mode: the model maps of the last raycast, composited now
+    if (rc != HKF_OK) return rc;
     // cudaDownSampleModelVertices/Normals (the new-frame pyramids were built by hkf_preprocess)
-    int rc;
     if (c->levels >= 2) {
         rc = hkf_pyramids_fused(c, c->model_v, c->model_n, nullptr, true);      // also starts the frame's tracking state
         if (rc != HKF_OK) return rc;

@@ -52,7 +52,7 @@ struct RaycastArgs {
 // It has been removed.
 // COLOR: has_color (whole volumes only); a separate instantiation so that the depth-only kernels keep their registers.
 template <bool FROM_STATE, bool SLAB, bool FAST, bool COLOR = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, SLAB ? 3 : 0)
 k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
           unsigned long long* __restrict__ keys, const HkfDeviceState* __restrict__ st)
 {
@@ -131,7 +131,15 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         float t = tmin, last_sdf = 0.f, last_t = tmin;
         bool last_known = true;
         float t_leave = 3.0e38f;
+        int nlo = 0, nhi = 0;              // SLAB: planes whose samples this ray needs
         if (SLAB) {
+            // z is monotonic along a ray: the one sample before the owned planes lies below them when the ray climbs and
+            // above them when it descends; on the far side nothing is needed (a crossing there is another rank's).  The
+            // batches below read speculatively - eight samples span more planes than a thin slab has - and a sample
+            // outside [nlo, nhi) is not read where it lies (with a peer-memory halo that would be a neighbour's memory,
+            // over NVLink, for a value nobody uses) but replaced by "unknown".
+            nlo = dz >= 0.f ? V.kz_lo : A.own_z0;
+            nhi = dz >= 0.f ? A.own_z1 : V.kz_hi;
             // A rank reports the crossings whose LATER sample lies in a plane it owns (any earlier crossing of the ray
             // belongs to another rank, whose smaller key wins the compositing).  So only the samples inside the owned
             // planes (one cell of slack for the rounding of the voxel index) and the one sample before them matter:
@@ -169,7 +177,8 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         const float rRS = __fmul_rn(V.Rf, rS);
         const float guard = V.Rf * 2.384185791015625e-7f;       // R * 2^-22
         const float MAGIC = 12582912.0f;
-        const bool mono = A.inc > 0.f;                          // t never decreases: ts[b] <= ts[RAY_NB-1]
+        const bool mono = A.inc > 0.f;                          // t never decreases: ts[b] <= ts[NB-1]
+        constexpr int NB = SLAB ? 4 : RAY_NB;                   // a slab ray has a handful of samples to take
         // nearest-voxel indices of the sample at parameter tt (the reference's integers, whichever path computes them)
         auto voxel3 = [&](float tt, int& gx, int& gy, int& gz) {
             const float px = __fmaf_rn(dx, tt, ox), py = __fmaf_rn(dy, tt, oy), pz = __fmaf_rn(dz, tt, oz);
@@ -186,17 +195,17 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
         };
         bool done = false;
         while (!done && t < tmax && t < t_leave) {
-            float ts[RAY_NB], sd[RAY_NB];
-            int gzs[RAY_NB];
+            float ts[NB], sd[NB];
+            int gzs[NB];
 #pragma unroll
-            for (int b = 0; b < RAY_NB; ++b) {
+            for (int b = 0; b < NB; ++b) {
                 ts[b] = t;
                 int gx, gy, gz;
                 voxel3(t, gx, gy, gz);
                 gzs[b] = gz;
                 if (SLAB) {
                     // keep the speculative read inside the readable planes; a plane of the halo comes from a neighbour's memory
-                    const int gzc = min(max(gz, V.kz_lo), V.kz_hi - 1);
+                    const int gzc = min(max(gz, nlo), nhi - 1);
                     sd[b] = __ldg(&(vol_plane(V, gzc) + ((unsigned)gy * (unsigned)R + (unsigned)gx))->x);
                 } else if (FAST) sd[b] = __ldg(&V.vol[((unsigned)gz * (unsigned)R + (unsigned)gy) * (unsigned)R + (unsigned)gx].x);
                 else sd[b] = __ldg(&V.vol[vol_index(V, gx, gy, gz)].x);
@@ -205,25 +214,25 @@ k_raycast(RaycastArgs A, float4* __restrict__ out_v, float4* __restrict__ out_n,
             // Nothing can happen in this batch (the common case) unless a (+ -> -) pair shows up, the ray reaches t_max,
             // or a sample lies outside the stored planes: one predicate instead of the in-order scan below.
             {
-                bool event = !(mono && ts[RAY_NB - 1] < tmax) || !last_known;
+                bool event = !(mono && ts[NB - 1] < tmax) || !last_known;
                 float prev = last_sdf;
 #pragma unroll
-                for (int b = 0; b < RAY_NB; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     event |= (prev > 0.0f) & (sd[b] < 0.0f);
-                    if (SLAB) event |= (unsigned)(gzs[b] - V.kz_lo) >= (unsigned)(V.kz_hi - V.kz_lo);
+                    if (SLAB) event |= (unsigned)(gzs[b] - nlo) >= (unsigned)(nhi - nlo);
                     prev = sd[b];
                 }
                 if (!event) {
-                    last_sdf = sd[RAY_NB - 1]; last_t = ts[RAY_NB - 1];
+                    last_sdf = sd[NB - 1]; last_t = ts[NB - 1];
                     continue;
                 }
             }
 #pragma unroll
-            for (int b = 0; b < RAY_NB; ++b) {
+            for (int b = 0; b < NB; ++b) {
                 if (done) break;
                 if (!(ts[b] < tmax)) { done = true; break; }
                 const int gz = gzs[b];
-                const bool known = !SLAB || (gz >= V.kz_lo && gz < V.kz_hi);
+                const bool known = !SLAB || (gz >= nlo && gz < nhi);
                 const float sdf = known ? sd[b] : 0.f;
                 if (known && last_known && last_sdf > 0.0f && sdf < 0.0f) {
                     // first zero crossing: the ray ends here whatever happens next
@@ -345,6 +354,7 @@ extern "C" int hkf_raycasting_volume(hkf_ctx* c, int has_color, const HkfMat44* 
 extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
+    { const int rc = hkf_shard_flush(c); if (rc != HKF_OK) return rc; }      // one raycast at a time in the inboxes
     RaycastArgs A; fill_ray_args(c, nullptr, &fp->raycast, &c->ip.depth_camera, fp->trunc_min, fp->trunc_max, &A);
     if (fp->use_color) {
         if (!c->color) { c->err = "context was created without use_color"; return HKF_ERR_STATE; }
@@ -366,8 +376,10 @@ extern "C" int hkf_raycast_tracked(hkf_ctx* c, const HkfFrameParams* fp)
     HKF_LAUNCH_CHECK(c);
     // sharded volume: nearest-hit compositing of the per-slab partial raycasts -> full model maps on every rank
     // (HKF_SHARD_MANUAL_COMPOSITE=1: the caller invokes hkf_shard_composite_raycast itself, e.g. to time it separately)
+    // The compositing is deferred to the next call that needs the model maps (hkf_shard_flush): the next frame's preprocess
+    // does not, and runs while the other ranks' hits are still arriving.
     static const bool manual = getenv("HKF_SHARD_MANUAL_COMPOSITE") && getenv("HKF_SHARD_MANUAL_COMPOSITE")[0] == '1';
-    if (c->nranks > 1 && !manual) return hkf_shard_composite_raycast(c);
+    if (c->nranks > 1 && !manual) c->composite_pending = true;
     return HKF_OK;
 }
 #endif // HKF_EMULATE_DEVICE

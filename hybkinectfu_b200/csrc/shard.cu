@@ -247,6 +247,13 @@ k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ o
     }
 }
 
+extern "C" int hkf_shard_composite_raycast(hkf_ctx* c);
+int hkf_shard_flush(hkf_ctx* c)
+{
+    if (!c || !c->composite_pending) return HKF_OK;
+    return hkf_shard_composite_raycast(c);
+}
+
 // sum the 27 per-rank partial sums in place (st->sums), enqueued on the context's stream
 int hkf_shard_allreduce_sums(hkf_ctx* c)
 {
@@ -271,6 +278,7 @@ extern "C" int hkf_shard_composite_raycast(hkf_ctx* c)
 {
     if (!c) return HKF_ERR_ARG;
     if (!c->nccl_comm) { c->err = "hkf_shard_composite_raycast: hkf_shard_init has not been called"; return HKF_ERR_STATE; }
+    c->composite_pending = false;
     NcclApi* a = nccl_api();
     const unsigned npix = c->cols[0] * c->rows[0];
     if (c->p2p) {

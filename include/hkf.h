@@ -244,10 +244,13 @@ int hkf_shard_init(hkf_ctx* ctx, int rank, int nranks, const void* unique_id_128
  * set identically on all ranks. */
 int hkf_shard_set_icp_mode(hkf_ctx* ctx, int replicated);
 /* nearest-hit compositing of per-slab partial raycasts (min over ranks of (t, ok, rank) keys,
- * then payload from the winner) -> full model maps on every rank */
+ * then payload from the winner) -> full model maps on every rank.  hkf_raycast_tracked schedules it by itself, DEFERRED:
+ * it is issued by the next call that needs the model maps (hkf_icp_track, hkf_frame_result, hkf_download, hkf_sync, the
+ * next hkf_raycast_tracked), i.e. after the next frame's hkf_preprocess, which does not.  Call it directly only with
+ * env HKF_SHARD_MANUAL_COMPOSITE=1 (every rank, once per hkf_raycast_tracked, before the next hkf_icp_track). */
 int hkf_shard_composite_raycast(hkf_ctx* ctx);
 /* Peer-memory fast path (optional, after hkf_shard_init): each rank exports HKF_SHARD_IPC_BYTES bytes of cudaIpc
- * handles (its mailbox and its compositing inboxes); the caller gathers them from all ranks (rank order) and hands the
+ * handles (its mailbox, its compositing inboxes and its volume); the caller gathers them from all ranks (rank order) and hands the
  * concatenation to hkf_shard_connect.  Afterwards the ICP sums are exchanged by the tracking kernel itself (P2P stores
  * of (value, iteration) words over NVLink, summed in rank order so every rank holds the same bits), the raycast kernel
  * pushes the key and payload of every pixel it hits into the inbox of every rank while it marches, and compositing is

@@ -17,8 +17,13 @@ R = 1024
 cfg0 = bench_cfg(R)
 halo = shard.halo_planes(cfg0.ray_increment, cfg0.volume_size, R)
 ranges = shard.balanced_slab_ranges(cfg0, 8, halo)
+if len(sys.argv) > 1:                    # owned plane counts of a measured layout, e.g. 372,101,86,79,73,67,45,201
+    owned = [int(v) for v in sys.argv[1].split(",")]
+    cuts = np.concatenate([[0], np.cumsum(owned)])
+    assert cuts[-1] == R
+    ranges = [(int(cuts[i]), int(cuts[i + 1]), max(int(cuts[i]) - halo, 0), min(int(cuts[i + 1]) + halo, R)) for i in range(len(owned))]
 frames, gt = make_sequence(8)
-for r in (0, 3, 6, 7):
+for r in range(len(ranges)):
     z0, z1, s0, s1 = ranges[r]
     cfg = dataclasses.replace(cfg0, slab_z0=z0, slab_z1=z1, slab_halo=halo, max_triangles=1)
     ctx = capi.Context(cfg)
