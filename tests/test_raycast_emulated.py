@@ -62,3 +62,54 @@ def test_kernel_source_equals_oracle_in_every_variant(emu, res):
         for fast in (0, 1):
             v1, n1 = _run(emu, vol, cfg, pose, fast)
             assert bits_equal(v0, v1) and bits_equal(n0, n1), f"variant FAST={fast}"
+
+
+def _run_slab(lib, vol, cfg, pose, fast, rng, halo, peer, rank):
+    """slab `rng` = (own_z0, own_z1) of the whole volume `vol`; peer=False: the slab array holds owned + halo planes;
+    peer=True: it holds the owned planes only and the halo planes are handed over as the neighbours' arrays"""
+    R = cfg.resolution
+    z0, z1 = rng
+    k0, k1 = max(z0 - halo, 0), min(z1 + halo, R)
+    if peer:
+        own = np.ascontiguousarray(vol[z0:z1]); lo = np.ascontiguousarray(vol[k0:z0]); hi = np.ascontiguousarray(vol[z1:k1])
+        s0, s1 = z0, z1
+    else:
+        own = np.ascontiguousarray(vol[k0:k1]); lo = hi = None
+        s0, s1 = k0, k1
+    v = np.zeros((cfg.rows, cfg.cols, 4), np.float32)
+    n = np.zeros_like(v)
+    keys = np.zeros((cfg.rows, cfg.cols), np.uint64)
+    p = np.ascontiguousarray(pose, np.float32).reshape(16)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+    rc = lib.emu_raycast_slab(ptr(own), ptr(lo), ptr(hi), R, C.c_float(cfg.volume_size), s0, s1, k0 if peer else s0, k1 if peer else s1,
+                              z0, z1, rank, cfg.cols, cfg.rows, C.c_float(cfg.cx), C.c_float(cfg.cy), C.c_float(cfg.fx), C.c_float(cfg.fy),
+                              ptr(p), C.c_float(cfg.ray_increment), C.c_float(cfg.trunc_min), C.c_float(cfg.trunc_max), int(fast),
+                              ptr(v), ptr(n), ptr(keys))
+    assert rc == 0
+    return v, n, keys
+
+
+@pytest.mark.parametrize("peer", [False, True])
+def test_slab_kernel_source_composites_to_the_whole_raycast(emu, peer):
+    """N > 1 raycast on the CPU: the SLAB instantiation of the kernel source over three unequal slabs - with the halo
+    planes stored in the slab, and with the halo read in the neighbours' arrays (hkf_shard_peer_halo) - composited with
+    the rule of k_composite_p2p (shard.composite) equals the oracle's raycast of the whole volume bit for bit, from
+    views that climb and descend through the planes"""
+    from hybkinectfu_b200 import shard
+    cfg, vol, views = _scene(64)
+    halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
+    R = cfg.resolution
+    cuts = [0, max(halo, 20), max(halo, 20) + max(halo, 22), R]
+    assert all(b - a >= halo for a, b in zip(cuts, cuts[1:]))
+    # from above the floor, looking down and back towards -z: the rays DESCEND through the planes (the previous sample of
+    # a crossing then lies in the slab above)
+    f = np.array([0.0, 1.5, -0.3]); f /= np.linalg.norm(f)
+    back = np.eye(4); back[:3, 0] = [1.0, 0.0, 0.0]; back[:3, 1] = [0.0, f[2], -f[1]]; back[:3, 2] = f; back[:3, 3] = [1.0, 0.2, 1.5]
+    for pose in views + [back]:
+        pose = np.asarray(pose, np.float32)
+        v0, n0 = O.raycast(vol, cfg, pose)
+        assert (n0[..., :3] != 0).any(-1).sum() > 300
+        for fast in (0, 1):
+            parts = [_run_slab(emu, vol, cfg, pose, fast, (cuts[r], cuts[r + 1]), halo, peer, r) for r in range(3)]
+            best, v, n = shard.composite(np.stack([p[2] for p in parts]), np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+            assert bits_equal(v, v0) and bits_equal(n, n0), f"peer={peer} FAST={fast}"
