@@ -81,6 +81,9 @@ def balanced_slab_ranges(cfg, nranks: int, halo: int, pose=None, min_planes: int
     R = cfg.resolution
     if nranks == 1:
         return [(0, R, 0, R)]
+    if R < nranks:
+        raise ValueError(f"{nranks} slabs do not fit into {R} planes")
+    min_planes = max(1, min(min_planes, R // nranks))      # a small volume over many ranks: thinner slabs, never an empty one
     w = plane_work(cfg, pose) if plane_cost is None else np.asarray(plane_cost, np.float64)
     assert len(w) == R
     cum = np.concatenate([[0.0], np.cumsum(w)])

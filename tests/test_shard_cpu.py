@@ -147,3 +147,33 @@ def test_two_rank_gloo_sharded_host_path():
     for r in range(2):
         s0, s1, planes = res[r]["slab"]
         assert bits_equal(planes, whole[s0:s1])
+
+
+def test_plan_slabs_chooses_the_halo_layout(monkeypatch):
+    """shard.plan_slabs: with peer memory the halo is READ in the neighbours' volumes (hkf_shard_peer_halo) - the cut
+    tiles [0, R), balances the owned planes only and keeps every slab at least `halo` planes thick; without peer memory,
+    when switched off, or when the volume is too small for that, every rank stores its halo"""
+    from conftest import small_config
+    cfg = small_config(256)
+    halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, cfg.resolution)
+    monkeypatch.delenv("HKF_SHARD_PEER_HALO", raising=False)
+    for n in (2, 4, 8):
+        rs, peer = shard.plan_slabs(cfg, n, halo, True)
+        assert peer
+        assert rs[0][0] == 0 and rs[-1][1] == 256 and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert all(z1 - z0 >= halo and (s0, s1) == (z0, z1) for z0, z1, s0, s1 in rs)
+        rs2, peer2 = shard.plan_slabs(cfg, n, halo, False)                 # NCCL fallback: no peer memory to read
+        assert not peer2 and all(s0 == max(z0 - halo, 0) and s1 == min(z1 + halo, 256) for z0, z1, s0, s1 in rs2)
+    monkeypatch.setenv("HKF_SHARD_PEER_HALO", "0")
+    assert not shard.plan_slabs(cfg, 4, halo, True)[1]
+    monkeypatch.delenv("HKF_SHARD_PEER_HALO")
+    tiny = small_config(32)
+    h = shard.halo_planes(tiny.ray_increment, tiny.volume_size, 32)
+    assert not shard.plan_slabs(tiny, 8, h, True)[1]                       # 4 planes per rank < halo: stored halos
+    assert shard.plan_slabs(cfg, 1, halo, True) == ([(0, 256, 0, 256)], False)
+    # every rank computes the same plan from a measured cost profile
+    cost = np.linspace(1.0, 3.0, 256)
+    a = shard.plan_slabs(cfg, 4, halo, True, plane_cost=cost)
+    assert a == shard.plan_slabs(cfg, 4, halo, True, plane_cost=cost.copy()) and a[1]
+    owned = [cost[z0:z1].sum() for z0, z1, _, _ in a[0]]
+    assert max(owned) <= 1.15 * (sum(owned) / 4)
