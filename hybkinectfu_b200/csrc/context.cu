@@ -175,6 +175,7 @@ extern "C" uint64_t hkf_launch_count(const hkf_ctx* c) { return c ? c->launches 
 extern "C" int hkf_reset_volume(hkf_ctx* c)
 {
     if (!c) return HKF_ERR_ARG;
+    { const int rc = hkf_shard_flush(c); if (rc != HKF_OK) return rc; }      // the neighbours may still be reading these planes
     size_t nvox = (size_t)(c->z_hi - c->z_lo) * c->ip.volume_resolution * c->ip.volume_resolution;
     HKF_CUDA(c, cudaMemsetAsync(c->vol, 0, nvox * sizeof(float2), c->stream));
     if (c->color) HKF_CUDA(c, cudaMemsetAsync(c->color, 0, nvox * sizeof(uchar4), c->stream));
@@ -249,6 +250,7 @@ extern "C" long hkf_download(hkf_ctx* c, int buffer, unsigned level, void* dst, 
 extern "C" long hkf_upload(hkf_ctx* c, int buffer, unsigned level, const void* src, size_t nbytes)
 {
     if (!c || !src) return -HKF_ERR_ARG;
+    if (hkf_shard_flush(c) != HKF_OK) return -HKF_ERR_CUDA;
     if (buffer == HKF_BUF_POSE) {
         if (nbytes != 64) return -HKF_ERR_ARG;
         HkfMat44 m; memcpy(m.m, src, 64);

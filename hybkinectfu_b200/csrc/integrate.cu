@@ -625,6 +625,7 @@ extern "C" int hkf_integrate_volume(hkf_ctx* c, int has_color, int use_angle_wei
                                     const HkfIntegrateParams* ip, const HkfCameraParams* cam, const HkfCameraParams* rgb_cam)
 {
     if (!c || !transform || !ip || !cam) return HKF_ERR_ARG;
+    { const int rc = hkf_shard_flush(c); if (rc != HKF_OK) return rc; }      // see hkf_integrate_tracked
     if (cam->cols != c->cols[0] || cam->rows != c->rows[0]) { c->err = "camera size mismatch"; return HKF_ERR_ARG; }
     float inv[16];
     hkf_mat44_inverse(transform->m, inv);      // host, float cofactors: cudaIntegrateVolume line 84
@@ -641,6 +642,10 @@ extern "C" int hkf_integrate_volume(hkf_ctx* c, int has_color, int use_angle_wei
 extern "C" int hkf_integrate_tracked(hkf_ctx* c, const HkfFrameParams* fp)
 {
     if (!c || !fp) return HKF_ERR_ARG;
+    // sharded mode: a deferred compositing is issued first.  With a peer-memory halo the neighbours' slab raycasts of the
+    // previous frame read THIS rank's planes; the compositing handshake is what orders this integration after them
+    // (a caller that supplies poses never passes through hkf_icp_track, which would have flushed).
+    { const int rc = hkf_shard_flush(c); if (rc != HKF_OK) return rc; }
     IntegrateArgs A; fill_args(c, nullptr, &fp->integrate, &c->ip.depth_camera, &A);
     if (fp->use_color) {
         IntegrateColor CA;

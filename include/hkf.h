@@ -245,9 +245,12 @@ int hkf_shard_init(hkf_ctx* ctx, int rank, int nranks, const void* unique_id_128
 int hkf_shard_set_icp_mode(hkf_ctx* ctx, int replicated);
 /* nearest-hit compositing of per-slab partial raycasts (min over ranks of (t, ok, rank) keys,
  * then payload from the winner) -> full model maps on every rank.  hkf_raycast_tracked schedules it by itself, DEFERRED:
- * it is issued by the next call that needs the model maps (hkf_icp_track, hkf_frame_result, hkf_download, hkf_sync, the
- * next hkf_raycast_tracked), i.e. after the next frame's hkf_preprocess, which does not.  Call it directly only with
- * env HKF_SHARD_MANUAL_COMPOSITE=1 (every rank, once per hkf_raycast_tracked, before the next hkf_icp_track). */
+ * it is issued by the next call that needs the model maps or changes the volume (hkf_icp_track, hkf_integrate_*,
+ * hkf_frame_result, hkf_download, hkf_upload, hkf_reset_volume, hkf_sync, the next hkf_raycast_tracked), i.e. after the
+ * next frame's hkf_preprocess, which does neither.  Its handshake is also what orders a rank's next integration after
+ * the neighbours' slab raycasts that read its planes (peer-memory halo).  Call it directly only with env
+ * HKF_SHARD_MANUAL_COMPOSITE=1 (every rank, once per hkf_raycast_tracked, before the next hkf_icp_track /
+ * hkf_integrate_tracked). */
 int hkf_shard_composite_raycast(hkf_ctx* ctx);
 /* Peer-memory fast path (optional, after hkf_shard_init): each rank exports HKF_SHARD_IPC_BYTES bytes of cudaIpc
  * handles (its mailbox, its compositing inboxes and its volume); the caller gathers them from all ranks (rank order) and hands the

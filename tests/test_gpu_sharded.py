@@ -65,6 +65,23 @@ def _worker(rank, world, port, q, res, peer_halo):
         n = ctx.marching_cubes()
         out["given_tris"] = ctx.download(capi.BUF_TRIANGLES)[:n].copy()
         dist.barrier()
+        # ---- the same, pipelined: no host synchronisation between the calls of a frame or between frames (the deferred
+        # compositing and, with a peer-memory halo, the ordering of a rank's integration after the neighbours' marches
+        # rest on the device-side handshakes alone)
+        import ctypes as C
+        ctx.reset_volume()
+        ctx.set_pose(gt[0])
+        dev = torch.from_numpy(frames.view(np.int16)).cuda()
+        for rep in range(3):
+            for i in range(len(frames)):
+                ctx._ck(ctx.lib.hkf_preprocess(ctx._h, dev.data_ptr() + i * frames[0].nbytes, 1, C.byref(ctx.fp)), "hkf_preprocess")
+                ctx.set_pose(gt[i])
+                ctx.integrate_tracked()
+                ctx.raycast_tracked()
+        ctx.frame_result()
+        out["async_v"] = ctx.download(capi.BUF_MODEL_VERTICES)
+        out["async_vol"] = ctx.download(capi.BUF_VOLUME)
+        dist.barrier()
         # ---- ICP tracking
         ctx.reset_volume()
         ctx.set_pose(synth.pose0().astype(np.float32))
@@ -129,6 +146,17 @@ def test_sharded_equals_single_gpu(world, res, peer_halo):
         assert got[r]["peer_halo"] == peer and (s0, s1) == ((z0, z1) if peer else (max(z0 - halo, 0), min(z1 + halo, cfg.resolution)))
         assert got[r]["slab"] == (z0, z1, 0 if peer else halo)
         assert bits_equal(got[r]["given_vol"], vol1[s0:s1]), f"slab {r} differs from planes [{s0},{s1}) of the whole volume"
+    # pipelined, three passes over the frames
+    c.reset_volume(); c.set_pose(gt[0])
+    for rep in range(3):
+        for i, mm in enumerate(frames):
+            c.preprocess(mm); c.set_pose(gt[i]); c.integrate_tracked(); c.raycast_tracked()
+    c.frame_result()
+    v3, vol3 = c.download(capi.BUF_MODEL_VERTICES), c.download(capi.BUF_VOLUME)
+    for r in range(world):
+        z0, z1, s0, s1 = ranges[r]
+        assert bits_equal(got[r]["async_v"], v3), f"pipelined run: composited vertices differ on rank {r}"
+        assert bits_equal(got[r]["async_vol"], vol3[s0:s1]), f"pipelined run: slab {r} differs"
     c.reset_volume(); c.set_pose(synth.pose0().astype(np.float32))
     poses = []
     for i, mm in enumerate(frames):
