@@ -1,7 +1,2 @@
 set -x
-for w in c1 c3 c5; do timeout 600 python bench.py --workload $w --steps 20 --warmup 3 > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err; tail -c 300 gpurun_out/r2_bench_$w.err; python - <<PY
-import json
-d=json.loads(open('gpurun_out/r2_bench_$w.json').read().strip().splitlines()[-1])
-print('$w', d['metric'][:60], d['value'], d.get('e2e',{}).get('value'), d.get('roofline',{}).get('frac'), {k:v for k,v in d.items() if k in ('diagnostics',)})
-PY
-done
+timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q 2>&1 | tail -12 | tee gpurun_out/r2_pytest_gpu_sharded_n2_final.log
