@@ -87,8 +87,6 @@ struct ShardPeers {
     // rank (posted stores over NVLink, overlapped with the march); compositing then reads local memory only.
     unsigned long long* keys_in[HKF_MAX_RANKS];
     float4* pay_in[HKF_MAX_RANKS];
-    const float2* vol[HKF_MAX_RANKS];                  // rank r's stored planes (peer-memory halo); z range below
-    int vol_z_lo[HKF_MAX_RANKS], vol_z_hi[HKF_MAX_RANKS];
     int rank, nranks;
 };
 
@@ -171,6 +169,8 @@ struct hkf_ctx {
     // (hkf_icp_track, hkf_frame_result, hkf_download, hkf_sync, the next raycast), so that the next frame's preprocess -
     // which does not - runs while the peers' hits are still travelling and the slowest rank is still marching
     bool composite_pending = false;
+    const float2* peer_vol[HKF_MAX_RANKS]{};      // rank r's stored planes as mapped in this process (host side only:
+                                                  // the kernels get the two halo pointers below through VolView)
     const float2* halo_lo = nullptr; const float2* halo_hi = nullptr;
     unsigned halo_z_lo = 0, halo_z_hi = 0;
     bool icp_replicated = false;       // sharded mode: every rank tracks on the whole image, no exchange of the 27 sums

@@ -154,7 +154,7 @@ extern "C" int hkf_shard_connect(hkf_ctx* c, const void* all_handles, int nranks
             }
         }
         P.mail[r] = (ShardMailbox*)ptr[0]; P.keys_in[r] = (unsigned long long*)ptr[1]; P.pay_in[r] = (float4*)ptr[2];
-        P.vol[r] = (const float2*)ptr[3];
+        c->peer_vol[r] = (const float2*)ptr[3];
     }
     c->peers = P;
     c->p2p = true;
@@ -175,18 +175,17 @@ extern "C" int hkf_shard_peer_halo(hkf_ctx* c, unsigned halo, const unsigned* ow
     for (int r = 0; r < nranks; ++r) {
         const unsigned z0 = own_ranges[2 * r], z1 = own_ranges[2 * r + 1];
         if (z0 >= z1 || z1 > R || (r > 0 && z0 != own_ranges[2 * r - 1]) || z1 - z0 < halo) { c->err = "hkf_shard_peer_halo: slabs must tile [0, R) and be at least `halo` planes thick"; return HKF_ERR_ARG; }
-        c->peers.vol_z_lo[r] = (int)z0; c->peers.vol_z_hi[r] = (int)z1;
     }
     if (own_ranges[2 * c->rank] != c->own_z0 || own_ranges[2 * c->rank + 1] != c->own_z1) { c->err = "hkf_shard_peer_halo: own range mismatch"; return HKF_ERR_ARG; }
     const size_t pl = (size_t)R * R;
     c->halo_lo = c->halo_hi = nullptr;
     if (c->rank > 0 && halo) {            // planes [own_z0 - halo, own_z0) of the lower neighbour
         c->halo_z_lo = c->own_z0 - halo;
-        c->halo_lo = c->peers.vol[c->rank - 1] + (size_t)(c->halo_z_lo - own_ranges[2 * (c->rank - 1)]) * pl;
+        c->halo_lo = c->peer_vol[c->rank - 1] + (size_t)(c->halo_z_lo - own_ranges[2 * (c->rank - 1)]) * pl;
     } else c->halo_z_lo = c->own_z0;
     if (c->rank + 1 < nranks && halo) {   // planes [own_z1, own_z1 + halo) of the upper neighbour: its first planes
         c->halo_z_hi = c->own_z1 + halo;
-        c->halo_hi = c->peers.vol[c->rank + 1];
+        c->halo_hi = c->peer_vol[c->rank + 1];
     } else c->halo_z_hi = c->own_z1;
     return HKF_OK;
 }
