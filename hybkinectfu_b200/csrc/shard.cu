@@ -1,20 +1,93 @@
 // shard.cu — z-slab sharding of one volume across the GPUs of a box (BASELINE.json config 4; new, the reference
-// is single-GPU).  One process per GPU; rank r stores planes [slab_z0 - halo, slab_z1 + halo) and owns
-// [slab_z0, slab_z1).
+// is single-GPU).  One process per GPU; rank r owns planes [slab_z0, slab_z1).
 //
-//  * integration needs no exchange: a voxel is a pure function of (depth map, pose), so each rank integrates its
-//    stored planes, halo included, and no volume byte ever crosses NVLink;
-//  * ICP: every rank evaluates a band of pixel rows of each level, the 27 partial sums are summed with one
-//    ncclAllReduce per iteration enqueued on the context's stream, and every rank runs the same 6x6 solve on the
-//    same bits, so the device-resident poses stay identical on all ranks without ever being compared;
-//  * raycast: every rank marches the global sample sequence over its stored planes and reports the first (+ -> -)
-//    crossing whose later sample lies in its OWNED planes as a 64-bit key (t | ok | rank).  Compositing = the
-//    minimum key over ranks (ncclAllReduce MIN on u64; a nearer failed refinement beats a farther success, as in
-//    the reference where the ray ends at its first crossing), then the winner's vertex/normal: losers zero their
-//    payload and an ncclAllReduce SUM delivers x + 0 + ... + 0 = x bit for bit to every rank.
+//  * integration needs no exchange: a voxel is a pure function of (depth map, pose).  The slab raycast needs `halo`
+//    planes on either side of the owned range: with peer memory it reads them in the neighbours' volumes
+//    (hkf_shard_peer_halo), otherwise every rank stores and integrates them itself;
+//  * ICP: replicated on every rank, or banded - every rank evaluates a band of pixel rows and the 27 partial sums are
+//    exchanged (inside k_icp_frame over peer memory, ncclAllReduce otherwise) and added in rank order, so that every rank
+//    runs the same 6x6 solve on the same bits and the device-resident poses stay identical without ever being compared;
+//  * raycast: every rank marches the global sample sequence over the planes it can read and reports the first
+//    (+ -> -) crossing whose later sample lies in its OWNED planes as a 64-bit key (t | ok | rank).  Compositing = the
+//    minimum key over ranks (a nearer failed refinement beats a farther success, as in the reference where the ray
+//    ends at its first crossing), then the winner's vertex / normal.  Peer memory: the raycast kernel pushes its hits
+//    into every rank's inbox and k_composite_p2p reads local memory only.  NCCL fallback: ncclAllReduce MIN on the keys,
+//    losers zero their payload and an ncclAllReduce SUM delivers x + 0 + ... + 0 = x bit for bit to every rank.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2, the library torch already loaded in this process), so
 // libhkf_b200.so has no link-time dependency on it and single-GPU users never touch it.
+#include "hkf_internal.cuh"
+
+// ---------------------------------------------------------------- device kernels (tests/emu compiles these for the host)
+// One kernel composites the per-slab raycasts from this rank's OWN inboxes (the peers' raycast kernels pushed their hits
+// there).  Block 0 is the only one that talks to the peers' flags: it announces that this rank's raycast of the epoch -
+// and with it every store it pushed - is complete (stream order + one system-scope fence), waits until every rank has
+// announced the same, and releases the other blocks through a device-local word.  Then, per pixel, the minimum of the
+// nranks local keys and the winner's payload; the key slots are reset to "no hit" for their next use two epochs later.
+// The inboxes are double-buffered by epoch parity: a peer can only push epoch e + 2 after this rank has announced
+// e + 1, i.e. after this kernel of epoch e has completed - no trailing barrier.
+__global__ void __launch_bounds__(256)
+k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ out_n, unsigned npix, unsigned epoch, HkfDeviceState* st)
+{
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        bool ok = true;
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->ready[P.rank] = epoch;
+            const long long t0 = clock64();
+            for (int r = 0; r < P.nranks && ok; ++r)
+                while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->ready[r] - epoch) < 0)
+                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }                          // ~2 s: a peer died
+            __threadfence_system();
+            if (!ok) st->track_status = HKF_TRACK_PEER_TIMEOUT;
+            *(volatile unsigned*)&st->comp_go = ok ? epoch : (epoch | 0x80000000u);
+        } else {
+            unsigned g;
+            const long long t0 = clock64();
+            while ((int)(((g = *(volatile const unsigned*)&st->comp_go) & 0x7fffffffu) - epoch) < 0)
+                if (clock64() - t0 > 6000000000ll) { g = 0x80000000u; break; }
+            ok = !(g & 0x80000000u);
+            __threadfence();
+        }
+        s_ok = ok;
+    }
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_ok && i < npix) {
+        // the inboxes were written by peers: read through L2 only (never a stale L1 line); all loads first
+        unsigned long long* kin = P.keys_in[P.rank] + (size_t)(epoch & 1u) * HKF_MAX_RANKS * npix + i;
+        unsigned long long k[HKF_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) k[r] = r < P.nranks ? __ldcg(kin + (size_t)r * npix) : ~0ull;
+        unsigned long long best = ~0ull;
+#pragma unroll
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) best = k[r] < best ? k[r] : best;
+        const int w = (int)(best & 0xffu);
+        if (best == ~0ull || !((best >> 8) & 1ull)) {
+            out_v[i] = make_float4(0.f, 0.f, 0.f, 0.f); out_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (w != P.rank) {
+            const float4* pay = P.pay_in[P.rank] + 2 * (((size_t)(epoch & 1u) * HKF_MAX_RANKS + (unsigned)w) * npix + i);
+            out_v[i] = __ldcg(pay); out_n[i] = __ldcg(pay + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < HKF_MAX_RANKS; ++r) if (r < P.nranks && k[r] != ~0ull) kin[(size_t)r * npix] = ~0ull;
+    }
+}
+
+// keep this rank's vertex/normal only where its key is the global minimum; payload = [v | n] as 8 floats per pixel
+__global__ void k_composite_select(const unsigned long long* __restrict__ mine, const unsigned long long* __restrict__ best,
+                                   const float4* __restrict__ v, const float4* __restrict__ n, float4* __restrict__ payload, unsigned npix)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const bool win = mine[i] != ~0ull && mine[i] == best[i];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    payload[i] = win ? v[i] : z;
+    payload[npix + i] = win ? n[i] : z;
+}
+
+#ifndef HKF_EMULATE_DEVICE      /* host code below (tests/emu stops here) */
 #include <dlfcn.h>
 #include "hkf_internal.cuh"
 
@@ -190,62 +263,6 @@ extern "C" int hkf_shard_peer_halo(hkf_ctx* c, unsigned halo, const unsigned* ow
     return HKF_OK;
 }
 
-// One kernel composites the per-slab raycasts from this rank's OWN inboxes (the peers' raycast kernels pushed their hits
-// there).  Block 0 is the only one that talks to the peers' flags: it announces that this rank's raycast of the epoch -
-// and with it every store it pushed - is complete (stream order + one system-scope fence), waits until every rank has
-// announced the same, and releases the other blocks through a device-local word.  Then, per pixel, the minimum of the
-// nranks local keys and the winner's payload; the key slots are reset to "no hit" for their next use two epochs later.
-// The inboxes are double-buffered by epoch parity: a peer can only push epoch e + 2 after this rank has announced
-// e + 1, i.e. after this kernel of epoch e has completed - no trailing barrier.
-__global__ void __launch_bounds__(256)
-k_composite_p2p(ShardPeers P, float4* __restrict__ out_v, float4* __restrict__ out_n, unsigned npix, unsigned epoch, HkfDeviceState* st)
-{
-    __shared__ int s_ok;
-    if (threadIdx.x == 0) {
-        bool ok = true;
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            for (int r = 0; r < P.nranks; ++r) *(volatile unsigned*)&P.mail[r]->ready[P.rank] = epoch;
-            const long long t0 = clock64();
-            for (int r = 0; r < P.nranks && ok; ++r)
-                while ((int)(*(volatile const unsigned*)&P.mail[P.rank]->ready[r] - epoch) < 0)
-                    if (clock64() - t0 > 4000000000ll) { ok = false; break; }                          // ~2 s: a peer died
-            __threadfence_system();
-            if (!ok) st->track_status = HKF_TRACK_PEER_TIMEOUT;
-            *(volatile unsigned*)&st->comp_go = ok ? epoch : (epoch | 0x80000000u);
-        } else {
-            unsigned g;
-            const long long t0 = clock64();
-            while ((int)(((g = *(volatile const unsigned*)&st->comp_go) & 0x7fffffffu) - epoch) < 0)
-                if (clock64() - t0 > 6000000000ll) { g = 0x80000000u; break; }
-            ok = !(g & 0x80000000u);
-            __threadfence();
-        }
-        s_ok = ok;
-    }
-    __syncthreads();
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s_ok && i < npix) {
-        // the inboxes were written by peers: read through L2 only (never a stale L1 line); all loads first
-        unsigned long long* kin = P.keys_in[P.rank] + (size_t)(epoch & 1u) * HKF_MAX_RANKS * npix + i;
-        unsigned long long k[HKF_MAX_RANKS];
-#pragma unroll
-        for (int r = 0; r < HKF_MAX_RANKS; ++r) k[r] = r < P.nranks ? __ldcg(kin + (size_t)r * npix) : ~0ull;
-        unsigned long long best = ~0ull;
-#pragma unroll
-        for (int r = 0; r < HKF_MAX_RANKS; ++r) best = k[r] < best ? k[r] : best;
-        const int w = (int)(best & 0xffu);
-        if (best == ~0ull || !((best >> 8) & 1ull)) {
-            out_v[i] = make_float4(0.f, 0.f, 0.f, 0.f); out_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else if (w != P.rank) {
-            const float4* pay = P.pay_in[P.rank] + 2 * (((size_t)(epoch & 1u) * HKF_MAX_RANKS + (unsigned)w) * npix + i);
-            out_v[i] = __ldcg(pay); out_n[i] = __ldcg(pay + 1);
-        }
-#pragma unroll
-        for (int r = 0; r < HKF_MAX_RANKS; ++r) if (r < P.nranks && k[r] != ~0ull) kin[(size_t)r * npix] = ~0ull;
-    }
-}
-
 extern "C" int hkf_shard_composite_raycast(hkf_ctx* c);
 int hkf_shard_flush(hkf_ctx* c)
 {
@@ -259,18 +276,6 @@ int hkf_shard_allreduce_sums(hkf_ctx* c)
     if (!c->nccl_comm) return HKF_OK;
     HKF_NCCL(c, nccl_api()->AllReduce(c->st->sums, c->st->sums, 28, ncclFloat32, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
     return HKF_OK;
-}
-
-// keep this rank's vertex/normal only where its key is the global minimum; payload = [v | n] as 8 floats per pixel
-__global__ void k_composite_select(const unsigned long long* __restrict__ mine, const unsigned long long* __restrict__ best,
-                                   const float4* __restrict__ v, const float4* __restrict__ n, float4* __restrict__ payload, unsigned npix)
-{
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix) return;
-    const bool win = mine[i] != ~0ull && mine[i] == best[i];
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    payload[i] = win ? v[i] : z;
-    payload[npix + i] = win ? n[i] : z;
 }
 
 extern "C" int hkf_shard_composite_raycast(hkf_ctx* c)
@@ -294,3 +299,4 @@ extern "C" int hkf_shard_composite_raycast(hkf_ctx* c)
     HKF_CUDA(c, cudaMemcpyAsync(c->model_n[0], c->ray_payload + (size_t)npix * 4, (size_t)npix * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
     return HKF_OK;
 }
+#endif // HKF_EMULATE_DEVICE

@@ -113,3 +113,53 @@ def test_slab_kernel_source_composites_to_the_whole_raycast(emu, peer):
             parts = [_run_slab(emu, vol, cfg, pose, fast, (cuts[r], cuts[r + 1]), halo, peer, r) for r in range(3)]
             best, v, n = shard.composite(np.stack([p[2] for p in parts]), np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
             assert bits_equal(v, v0) and bits_equal(n, n0), f"peer={peer} FAST={fast}"
+
+
+@pytest.fixture(scope="module")
+def shard_emu():
+    if not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("CUDA headers not found")
+    r = subprocess.run(["make", "-C", EMU_DIR, "libshard_emu.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    lib = C.CDLL(os.path.join(EMU_DIR, "libshard_emu.so"))
+    if not lib.emu_shard_can_run():
+        pytest.skip("cannot create 256 threads in this container")
+    return lib
+
+
+@pytest.mark.parametrize("peer", [1, 0])
+def test_hit_pushes_and_compositing_kernel_sources_over_three_epochs(shard_emu, peer):
+    """The N > 1 raycast data path without GPUs: three "ranks" (arrays of one process) run the SLAB ray-march kernel
+    source, which pushes every hit into the inbox of every rank, and the compositing kernel source (k_composite_p2p)
+    reads each rank's own inboxes.  Three raycasts in a row from different poses: the inboxes are double-buffered by
+    epoch parity and the used slots are reset, so the third epoch lands on the slots of the first.  Every rank's
+    composited maps must equal the oracle's raycast of the whole volume bit for bit."""
+    import dataclasses
+    from hybkinectfu_b200 import shard, synth
+    lib = shard_emu
+    cfg, vol, views = _scene(64)
+    cam = synth.Camera().scaled(96, 72)
+    cfg = dataclasses.replace(cfg, cols=96, rows=72, cx=cam.cx, cy=cam.cy, fx=cam.fx, fy=cam.fy)
+    R, npix, nranks = cfg.resolution, 96 * 72, 3
+    halo = shard.halo_planes(cfg.ray_increment, cfg.volume_size, R)
+    cuts = np.array([0, max(halo, 20), max(halo, 20) + max(halo, 22), R], np.int32)
+    maxr = lib.emu_shard_max_ranks()
+    keys_in = np.full((nranks, 2, maxr, npix), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    pay_in = np.zeros((nranks, 2, maxr, npix, 8), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    volc = np.ascontiguousarray(vol, np.float32)
+    for epoch, pose in enumerate(views, start=1):
+        pose = np.ascontiguousarray(pose, np.float32)
+        v0, n0 = O.raycast(vol, cfg, pose)
+        assert (n0[..., :3] != 0).any(-1).sum() > 200
+        out_v = np.full((nranks, cfg.rows, cfg.cols, 4), 7.0, np.float32)
+        out_n = np.full_like(out_v, 7.0)
+        rc = lib.emu_sharded_raycast(ptr(volc), R, C.c_float(cfg.volume_size), nranks, ptr(cuts), halo, peer, cfg.cols, cfg.rows,
+                                     C.c_float(cfg.cx), C.c_float(cfg.cy), C.c_float(cfg.fx), C.c_float(cfg.fy), ptr(pose.reshape(16)),
+                                     C.c_float(cfg.ray_increment), C.c_float(cfg.trunc_min), C.c_float(cfg.trunc_max), epoch & 1, epoch,
+                                     ptr(keys_in), ptr(pay_in), ptr(out_v), ptr(out_n))
+        assert rc == 0
+        for r in range(nranks):
+            assert bits_equal(out_v[r], v0) and bits_equal(out_n[r], n0), f"epoch {epoch}, rank {r}"
+        # every slot that was used has been reset to "no hit" by the rank that owns the inbox
+        assert (keys_in[:, epoch & 1] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
