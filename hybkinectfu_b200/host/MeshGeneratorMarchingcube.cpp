@@ -2,7 +2,6 @@
 #include <charconv>
 #include <cstdint>
 #include <cstring>
-#include <unordered_map>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -31,22 +30,6 @@ bool MeshGeneratorMarchingcube::copyTrianglesToCPU()
 }
 
 namespace {
-struct CellHash {
-    size_t operator()(const std::array<int32_t, 3>& k) const
-    {
-        uint64_t h = 0x9E3779B97F4A7C15ull;
-        for (int32_t w : k) { h ^= (uint32_t)w; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
-        return (size_t)h;
-    }
-};
-struct FaceHash {
-    size_t operator()(const std::array<uint32_t, 3>& k) const
-    {
-        uint64_t h = 0x9E3779B97F4A7C15ull;
-        for (uint32_t w : k) { h ^= w; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
-        return (size_t)h;
-    }
-};
 inline int sign_of(float v) { return (0 < v) - (v < 0); }                      // sign(), src/cuda/cuda_declar.h:95-97
 // toVirtualVoxelPos (src/utils/mesh/meshData.h:750-753): v * (float)(1.0 / voxelSize) + sign(v) * 0.5, truncated
 inline int32_t virtual_cell(float v, float inv_size) { const float t = v * inv_size; return (int32_t)(t + (float)(sign_of(v) * 0.5)); }
@@ -61,41 +44,107 @@ inline int32_t virtual_cell(float v, float inv_size) { const float t = v * inv_s
 // the soup is first put in canonical order (sorted by its nine position floats): the mesh - hence the file - is then a
 // deterministic function of the volume, and equals what the reference's code makes of the same ordered soup
 // (tests/test_mesh_reference.py drives the reference's own ml::MeshData next to this).
+namespace {
+// Open-addressing tables for the two passes of the weld (linear probing, power-of-two capacity, load <= 1/4): a lookup
+// that misses - 26 of the 27 neighbour cells of almost every vertex - costs one cache line, and the 27 lines of a
+// vertex are requested together before the first one is looked at.
+struct CellTable {
+    struct Entry { int32_t x, y, z; uint32_t id; };
+    std::vector<Entry> e;
+    size_t mask, count = 0;
+    explicit CellTable(size_t expected)
+    {
+        size_t cap = 64;
+        while (cap < 2 * expected) cap <<= 1;
+        e.assign(cap, Entry{ 0, 0, 0, ~0u });
+        mask = cap - 1;
+    }
+    // hash = finish(hx(x) ^ hy(y) ^ hz(z)): the three per-axis parts are shared by the 27 cells around a vertex
+    static uint64_t hx(int32_t x) { return (uint32_t)x * 0x9E3779B97F4A7C15ull; }
+    static uint64_t hy(int32_t y) { const uint64_t h = (uint32_t)y * 0xC2B2AE3D27D4EB4Full; return h ^ (h >> 31); }
+    static uint64_t hz(int32_t z) { const uint64_t h = (uint32_t)z * 0x165667B19E3779F9ull; return (h << 17) | (h >> 47); }
+    static uint64_t finish(uint64_t h) { h ^= h >> 32; return (h * 0xff51afd7ed558ccdull) >> 20; }
+    static uint64_t hash(int32_t x, int32_t y, int32_t z) { return finish(hx(x) ^ hy(y) ^ hz(z)); }
+    size_t slot(int32_t x, int32_t y, int32_t z) const { return (size_t)hash(x, y, z) & mask; }
+    uint32_t find(size_t s, int32_t x, int32_t y, int32_t z) const
+    {
+        for (;; s = (s + 1) & mask) {
+            const Entry& q = e[s];
+            if (q.id == ~0u) return ~0u;
+            if (q.x == x && q.y == y && q.z == z) return q.id;
+        }
+    }
+    void place(int32_t x, int32_t y, int32_t z, uint32_t id)
+    {
+        size_t s = slot(x, y, z);
+        while (e[s].id != ~0u) s = (s + 1) & mask;
+        e[s] = Entry{ x, y, z, id };
+    }
+    // the table stays small enough for the caches as long as the soup welds well (a vertex is shared by ~6 triangles)
+    // and doubles when it does not: load factor <= 1/2
+    void add(int32_t x, int32_t y, int32_t z, uint32_t id)
+    {
+        if (2 * (count + 1) > e.size()) {
+            std::vector<Entry> old;
+            old.swap(e);
+            e.assign(2 * old.size(), Entry{ 0, 0, 0, ~0u });
+            mask = e.size() - 1;
+            for (const Entry& q : old) if (q.id != ~0u) place(q.x, q.y, q.z, q.id);
+        }
+        place(x, y, z, id);
+        ++count;
+    }
+};
+struct SortedTriangle { float key[9]; uint32_t index; };
+inline bool soup_less(const SortedTriangle& a, const SortedTriangle& b)
+{
+    for (int i = 0; i < 9; ++i) { if (a.key[i] < b.key[i]) return true; if (b.key[i] < a.key[i]) return false; }
+    return false;
+}
+}
+
 void MeshGeneratorMarchingcube::weld(std::vector<HkfTriangle> soup, std::vector<std::array<float, 3>>& vertices,
                                      std::vector<std::array<unsigned, 3>>& faces, std::vector<std::array<float, 4>>* colors)
 {
     const size_t n = soup.size();
-    std::vector<unsigned> order(n);
-    for (size_t t = 0; t < n; ++t) order[t] = (unsigned)t;
-    std::vector<std::array<float, 9>> keys(n);
+    // canonical order: the nine position floats, lexicographically (keys sorted in place: the first float decides almost
+    // every comparison, and it sits in the element that is being moved, not behind an index)
+    std::vector<SortedTriangle> order(n);
     for (size_t t = 0; t < n; ++t) {
         const HkfVertex* v = &soup[t].v0;
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) keys[t][i * 3 + j] = v[i].pos[j];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) order[t].key[i * 3 + j] = v[i].pos[j];
+        order[t].index = (uint32_t)t;
     }
-    std::sort(order.begin(), order.end(), [&](unsigned a, unsigned b) { return keys[a] < keys[b]; });
+    std::sort(order.begin(), order.end(), soup_less);
     const float thresh = 0.0001f;
     const float inv_size = (float)(1.0 / thresh);
-    std::unordered_map<std::array<int32_t, 3>, unsigned, CellHash> grid;
-    grid.reserve(n * 2);
+    CellTable grid(n / 2 + 16);               // the usual outcome: about half as many vertices as triangles
     vertices.clear(); faces.clear();
     vertices.reserve(n); faces.reserve(n);
     if (colors) { colors->clear(); colors->reserve(n); }
-    for (unsigned t : order) {
-        const HkfVertex* tv = &soup[t].v0;
+    for (const SortedTriangle& st : order) {
+        const HkfVertex* tv = &soup[st.index].v0;
         std::array<unsigned, 3> f;
         for (int i = 0; i < 3; ++i) {
             const float* p = tv[i].pos;
-            const std::array<int32_t, 3> cell = { virtual_cell(p[0], inv_size), virtual_cell(p[1], inv_size), virtual_cell(p[2], inv_size) };
+            const int32_t cx = virtual_cell(p[0], inv_size), cy = virtual_cell(p[1], inv_size), cz = virtual_cell(p[2], inv_size);
+            size_t slots[27];
+            uint64_t ax[3], ay[3], az[3];
+            for (int d = 0; d < 3; ++d) { ax[d] = CellTable::hx(cx + d - 1); ay[d] = CellTable::hy(cy + d - 1); az[d] = CellTable::hz(cz + d - 1); }
+            int k = 0;
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b)
+                    for (int c = 0; c < 3; ++c, ++k) { slots[k] = (size_t)CellTable::finish(ax[a] ^ ay[b] ^ az[c]) & grid.mask; __builtin_prefetch(&grid.e[slots[k]]); }
             unsigned id = ~0u;
-            for (int a = -1; a <= 1 && id == ~0u; ++a)
+            for (int a = -1; a <= 1 && id == ~0u; ++a)           // x outermost, the first registered vertex found wins
                 for (int b = -1; b <= 1 && id == ~0u; ++b)
                     for (int c = -1; c <= 1; ++c) {
-                        auto it = grid.find({ cell[0] + a, cell[1] + b, cell[2] + c });
-                        if (it != grid.end()) { id = it->second; break; }
+                        id = grid.find(slots[(a + 1) * 9 + (b + 1) * 3 + (c + 1)], cx + a, cy + b, cz + c);
+                        if (id != ~0u) break;
                     }
             if (id == ~0u) {
                 id = (unsigned)vertices.size();
-                grid.emplace(cell, id);
+                grid.add(cx, cy, cz, id);
                 vertices.push_back({ p[0], p[1], p[2] });
                 if (colors) colors->push_back({ tv[i].color[2], tv[i].color[1], tv[i].color[0], 1.0f });   // (z, y, x, 1): BGR -> RGB, :53-55
             }
@@ -105,14 +154,16 @@ void MeshGeneratorMarchingcube::weld(std::vector<HkfTriangle> soup, std::vector<
         faces.push_back(f);
     }
     // removeDuplicateFaces: same vertex set, the first one stays
-    std::unordered_map<std::array<uint32_t, 3>, bool, FaceHash> seen;
-    seen.reserve(faces.size() * 2);
+    CellTable seen(faces.size());
     std::vector<std::array<unsigned, 3>> uniq;
     uniq.reserve(faces.size());
     for (const auto& f : faces) {
         std::array<uint32_t, 3> s3 = { f[0], f[1], f[2] };
         std::sort(s3.begin(), s3.end());
-        if (seen.emplace(s3, true).second) uniq.push_back(f);
+        const size_t s = seen.slot((int32_t)s3[0], (int32_t)s3[1], (int32_t)s3[2]);
+        if (seen.find(s, (int32_t)s3[0], (int32_t)s3[1], (int32_t)s3[2]) != ~0u) continue;
+        seen.add((int32_t)s3[0], (int32_t)s3[1], (int32_t)s3[2], 0u);
+        uniq.push_back(f);
     }
     faces.swap(uniq);
 }

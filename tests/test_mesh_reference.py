@@ -119,3 +119,25 @@ def test_weld_equals_reference_meshdata_512_soup():
     t0 = time.time(); got = run_host(tris, 1); t1 = time.time(); ref = run_ref(canonical(tris), 1); t2 = time.time()
     print(f"{n} triangles -> {len(ref[0])} vertices, {len(ref[3])} faces; host class {t1 - t0:.2f} s, reference ml::MeshData {t2 - t1:.2f} s")
     same_mesh(got, ref, 1)
+
+
+def test_weld_tables_grow_on_a_soup_that_does_not_weld():
+    """20 000 triangles scattered over 2 m: hardly any vertex is shared, so the weld registers three vertices per triangle
+    (its tables are sized for a marching-cubes soup - half a vertex per triangle - and must double twice), plus the
+    whole soup a second time (every face a duplicate) and a block of triangles on a 5e-5 m lattice, where vertices of
+    neighbouring cells merge by the first-found rule"""
+    rng = np.random.default_rng(11)
+    n = 20000
+    base = rng.uniform(0.0, 2.0, size=(n, 1, 3)).astype(np.float32)
+    tris = np.zeros((n, 3, 6), np.float32)
+    tris[:, :, :3] = base + rng.uniform(-0.01, 0.01, size=(n, 3, 3)).astype(np.float32)
+    tris[:, :, 3:] = rng.integers(0, 256, size=(n, 3, 3)).astype(np.float32)
+    lattice = np.zeros((3000, 3, 6), np.float32)
+    lattice[:, :, :3] = (rng.integers(0, 60, size=(3000, 3, 3)) * np.float32(5e-5) + np.float32(0.5)).astype(np.float32)
+    lattice[:, :, 3:] = 200.0
+    soup = np.concatenate([tris, tris, lattice])
+    for use_color in (0, 1):
+        ref = run_ref(canonical(soup), use_color)
+        got = run_host(soup[rng.permutation(len(soup))], use_color)
+        assert len(ref[0]) > 2.9 * n and len(ref[3]) < len(soup) - n + 1
+        same_mesh(ref, got, use_color)
